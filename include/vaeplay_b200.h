@@ -1,0 +1,175 @@
+/*
+ * vaeplay_b200.h -- C ABI of libvaeplay_b200.so, the B200 (sm_100a) kernel library under the
+ * vae-play VAE training step.
+ *
+ * The reference (kungyao/vae-play) has no FFI of its own: its hot path is the nn.Module API of
+ * models/blocks.py and models/networks.py, and every arithmetic call goes to torch.nn
+ * (SURVEY.md section 8b).  The entry points below are what a binding for that path binds instead
+ * of ATen/cuDNN/cuBLAS; each cites the reference call site it replaces.  INTEGRATION.md shows the
+ * ctypes stub used by vae_play_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*.
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate,
+ *     never synchronise, and are re-entrant per stream.
+ *   - return value: 0 on success, a negative VP_E* code otherwise (vp_last_error() has the text).
+ *   - activations are channels-last (NHWC) in `dtype` (VP_F32: fp32 check mode on CUDA cores;
+ *     VP_BF16: bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation).
+ *     Parameters, statistics, losses and gradients of parameters are always fp32.
+ *   - conv weights are consumed in a packed tap-major layout Wp[tap][N][K] produced by
+ *     vp_pack_weight (tap = ky*kw + kx); parameter gradients are produced in the same packed
+ *     layout in fp32 and scattered back to the torch layout by vp_unpack_wgrad.
+ */
+#ifndef VAEPLAY_B200_H
+#define VAEPLAY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VP_ABI_VERSION 1
+
+enum { VP_F32 = 0, VP_BF16 = 1 };
+enum { VP_ACT_NONE = 0, VP_ACT_RELU = 1, VP_ACT_LRELU = 2, VP_ACT_TANH = 3, VP_ACT_SIGMOID = 4 };
+/* backward only: OR into `act` when the tensor passed as x holds act(x) instead of the pre-activation */
+#define VP_ACT_FROM_OUTPUT 16
+enum { VP_OK = 0, VP_EINVAL = -1, VP_ECUDA = -2, VP_EUNSUPPORTED = -3 };
+/* engine selection for the contractions: AUTO = tcgen05 when dtype is bf16 and the shape is
+ * eligible, else the CUDA-core kernel; SIMT / TC force one (TC returns VP_EUNSUPPORTED if not eligible). */
+enum { VP_ENGINE_AUTO = 0, VP_ENGINE_SIMT = 1, VP_ENGINE_TC = 2 };
+
+/* Geometry of one Conv2d / ConvTranspose2d layer (nn.Conv2d at models/networks.py:14,101 and
+ * models/blocks.py:10-17; nn.ConvTranspose2d at models/networks.py:38, models/network_Style_GAN.py:49).
+ * `x` is always the layer's forward input [n,hi,wi,ci], `y` its forward output [n,ho,wo,co].
+ * nn.Linear (models/networks.py:65-70,88; models/blocks.py:39) is the case kh=kw=1, hi=wi=ho=wo=1. */
+typedef struct VpConvGeom {
+    int32_t n, hi, wi, ci;
+    int32_t ho, wo, co;
+    int32_t kh, kw;
+    int32_t stride, pad;
+    int32_t transposed; /* 0: Conv2d / Linear, 1: ConvTranspose2d */
+} VpConvGeom;
+
+const char* vp_last_error(void);
+int vp_abi_version(void);
+/* compute capability major*10+minor of the current device, or a negative error code */
+int vp_device_arch(void);
+
+/* ---- weight layout ------------------------------------------------------------------------------- */
+/* Wp[t][n][k] = (dtype) w[n*stride_n + k*stride_k + t*stride_t],  t in [0,taps).  `w` fp32 (torch layout).
+ * (Conv2d: stride_t = 1.  The NCHW-flatten Linear layers of models/networks.py:65,88 are expressed as
+ * 8x8-tap layers over the channels-last map by choosing the strides; see vae_play_b200/functional.py.) */
+int vp_pack_weight(const float* w, void* wp, int dtype, int taps, int n, int k,
+                   int64_t stride_n, int64_t stride_k, int64_t stride_t, void* stream);
+/* dw[n*stride_n + k*stride_k + t*stride_t] = dwp[t][n][k]   (fp32 -> fp32, torch layout) */
+int vp_unpack_wgrad(const float* dwp, float* dw, int taps, int n, int k,
+                    int64_t stride_n, int64_t stride_k, int64_t stride_t, void* stream);
+
+/* ---- contractions (implicit GEMM over filter taps) ------------------------------------------------- */
+/* y = conv(x, w) (+bias) then optional pointwise activation (only meaningful when no norm follows).
+ * wp: packed [taps][co][ci] in `dtype`; x in `dtype`; y in `out_dtype` (fp32 output of a bf16 contraction
+ * is used for the mu/logvar heads).  Replaces nn.Conv2d / nn.ConvTranspose2d / nn.Linear forward. */
+int vp_conv_fwd(const VpConvGeom* g, const void* x, const void* wp, const float* bias, void* y,
+                int dtype, int out_dtype, int act, float slope, int engine, void* stream);
+/* dx = dL/dx from dy.  wp_t: packed [taps][ci][co] in `dtype`.  Replaces the autograd dgrad. */
+int vp_conv_dgrad(const VpConvGeom* g, const void* dy, const void* wp_t, void* dx,
+                  int dtype, int out_dtype, int engine, void* stream);
+/* dwp (fp32, packed: [taps][co][ci] for Conv2d/Linear, [taps][ci][co] for ConvTranspose2d) = dL/dw.
+ * dwp is zeroed by the call (split-K partial sums are accumulated into it). */
+int vp_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dwp,
+                  int dtype, int engine, void* stream);
+
+/* ---- normalisation + activation over channels-last rows ------------------------------------------- */
+/* x: [groups*rows_per_group, c].  BatchNorm2d/1d: groups=1 (models/networks.py:16,40,66,89;
+ * blocks.py:21).  InstanceNorm2d: groups=n, rows_per_group=h*w (blocks.py:23).
+ * sums: double [2][groups][c] scratch (zeroed by the call) -> per-channel sum and sum of squares. */
+int vp_norm_stats(const void* x, double* sums, int dtype, int64_t groups, int64_t rows_per_group, int c,
+                  void* stream);
+/* From sums: mean/invstd (saved for backward, fp32 [groups][c]) and the fused affine
+ * scale = gamma*invstd, shift = beta - mean*scale (fp32 [groups][c]; gamma/beta may be NULL = 1/0).
+ * If running_mean/var are non-NULL they are blended in place with `momentum` (unbiased variance),
+ * torch convention running = (1-momentum)*running + momentum*batch. */
+int vp_norm_finalize(const double* sums, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, float momentum, float eps,
+                     float* mean, float* invstd, float* scale, float* shift,
+                     int64_t groups, int64_t rows_per_group, int c, void* stream);
+/* a = act(x*scale + shift) (scale/shift may be NULL = identity; bias-free pointwise activation). */
+int vp_norm_apply_act(const void* x, const float* scale, const float* shift, void* a, int dtype,
+                      int64_t groups, int64_t rows_per_group, int c, int act, float slope, void* stream);
+/* backward, pass 1: d = da * act'(x*scale+shift); sums (double [2][groups][c], zeroed by the call) get
+ * sum(d) and sum(d*xhat), xhat = (x-mean)*invstd.  With mean == NULL (no norm) only sum(d) is
+ * produced (bias gradient) and `dx` (if non-NULL) receives d.  */
+int vp_norm_bwd_reduce(const void* x, const void* da, const float* mean, const float* invstd,
+                       const float* scale, const float* shift, double* sums, void* dx_or_null, int dtype,
+                       int64_t groups, int64_t rows_per_group, int c, int act, float slope, void* stream);
+/* backward, pass 2: dx = scale * (d - sum(d)/m - xhat*sum(d*xhat)/m); dgamma = sum(d*xhat), dbeta = sum(d)
+ * (fp32 [c], written when non-NULL and groups == 1). */
+int vp_norm_bwd_apply(const void* x, const void* da, const float* mean, const float* invstd,
+                      const float* scale, const float* shift, const double* sums,
+                      void* dx, float* dgamma, float* dbeta, int dtype,
+                      int64_t groups, int64_t rows_per_group, int c, int act, float slope, void* stream);
+/* out[c] = sum over rows of x[rows,c] (bias gradients).  out fp32, written (not accumulated);
+ * scratch_c: double [2][c] (zeroed by the call). */
+int vp_colsum(const void* x, float* out, double* scratch_c, int dtype, int64_t rows, int c, void* stream);
+
+/* ---- reparameterisation + KL (models/networks.py:228-231 and :270; train_Style_GAN.py:156-160,218) -- */
+/* eps ~ N(0,1) from Philox4x32-10 with the exact element->counter mapping of Tensor.normal_() on
+ * CUDA (ATen DistributionTemplates.h:50-91, curand_normal4), so that (seed, offset) taken from
+ * torch's CUDA generator reproduce the reference's eps bit for bit.  n_total = rows*z.
+ * offset_dev (nullable): device uint64 added to `offset` at run time (CUDA-graph replay).
+ * If eps_in != NULL it is used instead of drawing.  mu/logvar: fp32 with row stride ld.
+ * z: `dtype` [rows,z]; eps_out fp32 [rows,z] (nullable); kl fp32 [rows]. */
+int vp_reparam_kl_fwd(const float* mu, const float* logvar, int64_t ld, const float* eps_in,
+                      uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int num_sms,
+                      void* z, int z_dtype, float* eps_out, float* kl, int64_t rows, int zdim, void* stream);
+/* dmu = dz + dkl*mu ; dlogvar = dz*eps*0.5*exp(0.5*logvar) + dkl*0.5*(exp(logvar)-1).
+ * dz (`dz_dtype`, nullable), dkl fp32 [rows] (nullable).  dmu/dlogvar in `out_dtype` with row stride ld_out. */
+int vp_reparam_kl_bwd(const float* mu, const float* logvar, int64_t ld, const float* eps,
+                      const void* dz, int dz_dtype, const float* dkl,
+                      void* dmu, void* dlogvar, int out_dtype, int64_t ld_out, int64_t rows, int zdim, void* stream);
+/* out[i] = N(0,1) sample i of the same stream (Tensor.normal_() drop-in; models/networks.py:241). */
+int vp_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                     int num_sms, void* stream);
+/* *offset_dev += inc  (advance a device-resident generator offset between graph replays) */
+int vp_philox_advance(uint64_t* offset_dev, uint64_t inc, void* stream);
+
+/* ---- reconstruction losses (train.py:62, train_Style_GAN.py:220, train_BE.py:58-59, tools/ops.py:12-19) */
+/* kind 0: mean((xt-x)^2)   kind 1: mean(|xt-x|).  x, xt fp32, n elements.
+ * loss_acc: double[1] and counter: u32[1], zero before first use (the kernel leaves them zero again);
+ * loss: fp32[1] = sum/n written by the last block to finish. */
+int vp_recon_loss_fwd(const float* x, const float* xt, int64_t n, int kind, double* loss_acc,
+                      unsigned int* counter, float* loss, void* stream);
+/* dxt = gscale[0] * d loss / d xt   (gscale: device fp32 scalar, the upstream gradient) */
+int vp_recon_loss_bwd(const float* x, const float* xt, int64_t n, int kind, const float* gscale,
+                      float* dxt, void* stream);
+/* 0.5*BCEWithLogits(mean) + dice(sigmoid(logits)) fused: per-sample sums then the scalar.
+ * acc: double [rows][4] (zeroed by the call; kept for the backward); counter u32[1] zero before first use;
+ * loss fp32[1].  rows = batch, per = elements per sample. */
+int vp_bce_dice_fwd(const float* logits, const float* target, int64_t rows, int64_t per, float bce_weight,
+                    double* acc, unsigned int* counter, float* loss, void* stream);
+int vp_bce_dice_bwd(const float* logits, const float* target, int64_t rows, int64_t per, float bce_weight,
+                    const double* acc, const float* gscale, float* dlogits, void* stream);
+
+/* acc[0] += scale * sum(v[0..n))  (single block, deterministic): folds sum_b kl_b (train.py:63) into the loss */
+int vp_sum_into(const float* v, int64_t n, float scale, float* acc, void* stream);
+/* out[i] = scale * g[0], i in [0,n): the gradient of that sum */
+int vp_fill_from(const float* g, float scale, float* out, int64_t n, void* stream);
+
+/* ---- layout conversion at the graph edges ------------------------------------------------------------ */
+int vp_nchw_to_nhwc(const float* x_nchw, void* y_nhwc, int dtype, int n, int c, int h, int w, void* stream);
+int vp_nhwc_to_nchw(const void* x_nhwc, float* y_nchw, int dtype, int n, int c, int h, int w, void* stream);
+/* elementwise cast between fp32 and `dtype` ([n] elements) */
+int vp_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
+/* sum += a (fp32, n elements): gradient accumulation helper */
+int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
+
+/* number of kernels this library has launched in this process (the bench's gpu_launches claim) */
+uint64_t vp_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VAEPLAY_B200_H */

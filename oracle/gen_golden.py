@@ -249,8 +249,19 @@ def gen_op_cases(networks, blocks, ops):
     print("ops.npz:", len(blob), "arrays")
 
 
+def gen_state_dict_keys(networks):
+    """state_dict key/shape lists of the stock VaeGan (the drop-in contract of SURVEY.md section 8b)."""
+    import json
+    out = {}
+    for img in (64, 128):
+        m = networks.VaeGan(img, 128)
+        out[str(img)] = [(k, list(v.shape)) for k, v in m.state_dict().items()]
+    json.dump(out, open(os.path.join(OUT, "state_dict_keys.json"), "w"))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     networks, blocks, ops = import_reference()
+    gen_state_dict_keys(networks)
     gen_op_cases(networks, blocks, ops)
     gen_vae_cases(networks)

@@ -157,3 +157,23 @@ def test_vae_step(golden_dir, case):
             assert rel(digest(out["grads"][key[5:]]), g[key]) < 1e-7, key
         if key.startswith("running/"):
             assert rel(out["running"][key[8:]], g[key]) < 1e-8, key
+
+
+@pytest.mark.parametrize("case", ["vae64_c1_b4", "vae64_c3_b4"])
+def test_torch_port_matches_golden(golden_dir, case):
+    import torch
+    from oracle.vae_torch import VaeTorchPort
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    img, cin, b, z, seed = [int(v) for v in g["meta"]]
+    P = vn.synth_vae_params(img, z, cin, cin, seed)
+    x, eps = vn.synth_batch(b, img, cin, z, seed)
+    port = VaeTorchPort(P, torch.float64)
+    loss, out = port.step(torch.from_numpy(x).double(), torch.from_numpy(eps).double(), optimize=False)
+    assert rel(loss.numpy(), g["loss"]) < 1e-10
+    for key in ("mu", "logvar", "z", "x_tilde", "kl"):
+        assert rel(out[key].detach().numpy(), g[key]) < 1e-9, key
+    for key, gr in port.grads().items():
+        assert rel(digest(gr.numpy()), g["grad/" + key]) < 1e-8, key
+    for key in g.files:
+        if key.startswith("running/"):
+            assert rel(port.P[key[8:]].detach().numpy(), g[key]) < 1e-9, key

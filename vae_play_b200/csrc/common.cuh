@@ -1,0 +1,133 @@
+// Shared helpers for libvaeplay_b200 (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vaeplay_b200.h"
+
+namespace vp {
+
+typedef __nv_bfloat16 bf16;
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define VP_CHECK_ARG(cond, ...)                  \
+    do {                                         \
+        if (!(cond)) {                           \
+            vp::set_error(__VA_ARGS__);          \
+            return VP_EINVAL;                    \
+        }                                        \
+    } while (0)
+
+#define VP_CHECK_LAUNCH(name)                                                        \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            vp::set_error("%s: CUDA launch failed: %s", name, cudaGetErrorString(e__)); \
+            return VP_ECUDA;                                                         \
+        }                                                                            \
+        vp::count_launch();                                                          \
+    } while (0)
+
+template <typename T> struct Cvt;
+template <> struct Cvt<float> {
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Cvt<bf16> {
+    static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+    switch (act) {
+        case VP_ACT_RELU: return v > 0.f ? v : 0.f;
+        case VP_ACT_LRELU: return v > 0.f ? v : slope * v;
+        case VP_ACT_TANH: return tanhf(v);
+        case VP_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        default: return v;
+    }
+}
+// derivative of act at pre-activation v; with (act & VP_ACT_FROM_OUTPUT) v is the post-activation value
+__device__ __forceinline__ float act_grad(float v, int act, float slope) {
+    if (act & VP_ACT_FROM_OUTPUT) {
+        switch (act & 15) {
+            case VP_ACT_RELU: return v > 0.f ? 1.f : 0.f;
+            case VP_ACT_LRELU: return v > 0.f ? 1.f : slope;
+            case VP_ACT_TANH: return 1.f - v * v;
+            case VP_ACT_SIGMOID: return v * (1.f - v);
+            default: return 1.f;
+        }
+    }
+    switch (act) {
+        case VP_ACT_RELU: return v > 0.f ? 1.f : 0.f;
+        case VP_ACT_LRELU: return v > 0.f ? 1.f : slope;
+        case VP_ACT_TANH: { float t = tanhf(v); return 1.f - t * t; }
+        case VP_ACT_SIGMOID: { float s = 1.f / (1.f + expf(-v)); return s * (1.f - s); }
+        default: return 1.f;
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The generic "tap GEMM": every Conv2d / ConvTranspose2d / Linear forward and data-gradient is
+//   D[n, gy*ds + doy, gx*ds + dox, :] = sum_t  A[n, gy*as + ty_t, gx*as + tx_t, :] . Wp[widx_t][:, :]
+// over an iteration grid (gy,gx) in [0,gh)x[0,gw), one launch per output phase.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxTaps = 64;
+
+struct TapList {
+    int ntaps;
+    int8_t ty[kMaxTaps];
+    int8_t tx[kMaxTaps];
+    int8_t widx[kMaxTaps];
+};
+
+struct TapGemm {
+    const void* A;   // [n, ha, wa, K]
+    const void* Wp;  // [taps_total][N][K]
+    void* D;         // [n, hd, wd, N]
+    const float* bias;  // [N] or null
+    int n, ha, wa, K;
+    int hd, wd, N;
+    int gh, gw;     // iteration grid
+    int as;         // stride applied to grid coords when reading A
+    int ds, doy, dox;  // stride / offset applied to grid coords when writing D
+    int act;
+    float slope;
+    int out_dtype;  // dtype of D (VP_F32 / VP_BF16); A and Wp are in the call's dtype
+    TapList taps;
+};
+
+// wgrad:  dWp[widx_t][gc][ac] += sum_{n,gy,gx} G[n,gy,gx,gc] * A[n, gy*as+ty_t, gx*as+tx_t, ac]
+struct TapWgrad {
+    const void* G;  // [n, gh, gw, GC]
+    const void* A;  // [n, ha, wa, AC]
+    float* dWp;     // [taps][GC][AC]
+    int n, gh, gw, GC;
+    int ha, wa, AC;
+    int as;
+    TapList taps;
+};
+
+int launch_tapgemm_simt(const TapGemm& p, int dtype, cudaStream_t s);
+int launch_tapwgrad_simt(const TapWgrad& p, int dtype, cudaStream_t s);
+// tcgen05 engine: returns VP_EUNSUPPORTED when the shape is not eligible
+int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s);
+int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s);
+bool tc_available();
+
+}  // namespace vp

@@ -1,0 +1,473 @@
+// Reparameterisation + KL (Philox eps, bit-compatible with Tensor.normal_() on CUDA), reconstruction
+// losses, layout conversion and weight (un)packing.  All single-pass, coalesced, warp-shuffle reductions.
+#include "common.cuh"
+
+namespace vp {
+namespace {
+
+// ---- Philox4x32-10 -------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+// curand_normal.h:70-87 (_curand_box_muller), device branch: logf + __sincosf
+__device__ __forceinline__ float2 box_muller(uint32_t x, uint32_t y) {
+    const float u = x * 2.3283064e-10f + (2.3283064e-10f / 2);
+    const float v = y * (2.3283064e-10f * 6.2831855f) + ((2.3283064e-10f * 6.2831855f) / 2);
+    const float s = sqrtf(-2.0f * logf(u));
+    float2 r;
+    __sincosf(v, &r.x, &r.y);
+    r.x *= s;
+    r.y *= s;
+    return r;
+}
+
+// Element li of an n-element Tensor.normal_() draw (ATen DistributionTemplates.h:65-91):
+//   thread = li % (grid*256), slot = li / (grid*256); counter = offset/4 + slot/4; component = slot%4
+__device__ __forceinline__ float aten_normal_element(int64_t li, int64_t nthreads, uint64_t seed, uint64_t offset) {
+    const uint64_t thread = (uint64_t)(li % nthreads);
+    const uint64_t slot = (uint64_t)(li / nthreads);
+    const uint64_t cnt = offset / 4 + slot / 4;
+    const uint4 ctr = make_uint4((uint32_t)cnt, (uint32_t)(cnt >> 32), (uint32_t)thread, (uint32_t)(thread >> 32));
+    const uint4 r = philox4x32_10(ctr, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const int comp = (int)(slot & 3);
+    const float2 n = (comp < 2) ? box_muller(r.x, r.y) : box_muller(r.z, r.w);
+    const float v = (comp & 1) ? n.y : n.x;
+    return v * 1.0f + 0.0f;  // transformation::normal(rand, mean=0, std=1)
+}
+
+__host__ __device__ inline int64_t aten_threads(int64_t n, int num_sms) {
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)num_sms * 8;  // maxThreadsPerMultiProcessor(2048) / 256
+    if (grid > cap) grid = cap;
+    return grid * 256;
+}
+
+__global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
+                                     const uint64_t* __restrict__ offset_dev, int64_t nthreads) {
+    if (offset_dev) offset += *offset_dev;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = aten_normal_element(i, nthreads, seed, offset);
+}
+
+__global__ void philox_advance_kernel(uint64_t* o, uint64_t inc) { *o += inc; }
+
+// one warp per row: z = eps*exp(.5*lv)+mu ; kl_row = -0.5*sum(-exp(lv) - mu^2 + lv + 1)
+template <typename TZ>
+__global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                                             int64_t ld, const float* __restrict__ eps_in,
+                                                             uint64_t seed, uint64_t offset,
+                                                             const uint64_t* __restrict__ offset_dev, int64_t nthreads,
+                                                             TZ* __restrict__ z, float* __restrict__ eps_out,
+                                                             float* __restrict__ kl, int64_t rows, int zdim) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    if (offset_dev) offset += *offset_dev;
+    float acc = 0.f;
+    for (int j = lane; j < zdim; j += 32) {
+        const float m = mu[row * ld + j], l = lv[row * ld + j];
+        const int64_t li = row * zdim + j;
+        const float e = eps_in ? eps_in[li] : aten_normal_element(li, nthreads, seed, offset);
+        const float sd = expf(0.5f * l);
+        Cvt<TZ>::st(z + li, fmaf(e, sd, m));
+        if (eps_out) eps_out[li] = e;
+        acc += -expf(l) - m * m + l + 1.f;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && kl) kl[row] = -0.5f * acc;
+}
+
+template <typename TZ, typename TO>
+__global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv,
+                                                             int64_t ld, const float* __restrict__ eps,
+                                                             const TZ* __restrict__ dz, const float* __restrict__ dkl,
+                                                             TO* __restrict__ dmu, TO* __restrict__ dlv,
+                                                             int64_t ldo, int64_t rows, int zdim) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * zdim) return;
+    const int64_t row = i / zdim;
+    const int j = (int)(i - row * zdim);
+    const float m = mu[row * ld + j], l = lv[row * ld + j];
+    const float g = dz ? Cvt<TZ>::ld(dz + i) : 0.f;
+    const float k = dkl ? dkl[row] : 0.f;
+    const float e = eps[i];
+    Cvt<TO>::st(dmu + row * ldo + j, g + k * m);
+    Cvt<TO>::st(dlv + row * ldo + j, g * e * 0.5f * expf(0.5f * l) + k * 0.5f * (expf(l) - 1.f));
+}
+
+// ---- reconstruction losses ------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_double(double v) {
+    __shared__ double sh[32];
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) sh[w] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) v = warp_sum(v);
+    __syncthreads();
+    return v;
+}
+
+__global__ void __launch_bounds__(256) recon_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xt,
+                                                        int64_t n, int kind, double* acc, unsigned int* counter,
+                                                        float* loss) {
+    float s = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+        if (i + 3 < n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(xt)) & 15) == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(x + i);
+            const float4 b = *reinterpret_cast<const float4*>(xt + i);
+            const float d0 = b.x - a.x, d1 = b.y - a.y, d2 = b.z - a.z, d3 = b.w - a.w;
+            s += kind == 0 ? (d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) : (fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3));
+        } else {
+            for (int64_t k = i; k < n && k < i + 4; ++k) {
+                const float d = xt[k] - x[k];
+                s += kind == 0 ? d * d : fabsf(d);
+            }
+        }
+    }
+    const double t = block_sum_double((double)s);
+    if (threadIdx.x == 0) {
+        atomicAdd(acc, t);
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            const double total = atomicAdd(acc, 0.0);
+            *loss = (float)(total / (double)n);
+            *acc = 0.0;  // self-cleaning: ready for the next call / graph replay
+            *counter = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) recon_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xt,
+                                                        int64_t n, int kind, const float* __restrict__ gscale,
+                                                        float* __restrict__ dxt) {
+    const float g = (gscale ? *gscale : 1.f) / (float)n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = xt[i] - x[i];
+        dxt[i] = kind == 0 ? 2.f * d * g : (d > 0.f ? g : (d < 0.f ? -g : 0.f));
+    }
+}
+
+// acc[row] = {sum bce, sum p*t, sum p, sum t}; block handles a slab of one sample
+__global__ void __launch_bounds__(256) bce_dice_fwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                           int64_t rows, int64_t per, float wbce, double* acc,
+                                                           unsigned int* counter, float* loss) {
+    const int64_t row = blockIdx.y;
+    float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+        const float zz = z[row * per + i], tt = t[row * per + i];
+        const float p = 1.f / (1.f + expf(-zz));
+        s0 += fmaxf(zz, 0.f) - zz * tt + log1pf(expf(-fabsf(zz)));
+        s1 += p * tt;
+        s2 += p;
+        s3 += tt;
+    }
+    const double a0 = block_sum_double(s0), a1 = block_sum_double(s1), a2 = block_sum_double(s2), a3 = block_sum_double(s3);
+    if (threadIdx.x == 0) {
+        atomicAdd(acc + row * 4 + 0, a0);
+        atomicAdd(acc + row * 4 + 1, a1);
+        atomicAdd(acc + row * 4 + 2, a2);
+        atomicAdd(acc + row * 4 + 3, a3);
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x * gridDim.y - 1) {
+            double bce = 0, dice = 0;
+            for (int64_t r = 0; r < rows; ++r) {
+                bce += atomicAdd(acc + r * 4 + 0, 0.0);
+                const double inter = atomicAdd(acc + r * 4 + 1, 0.0), sp = atomicAdd(acc + r * 4 + 2, 0.0),
+                             st = atomicAdd(acc + r * 4 + 3, 0.0);
+                dice += (2.0 * inter + 1.0) / (sp + st + 1.0);
+            }
+            *loss = (float)(wbce * bce / ((double)rows * (double)per) + (1.0 - dice / (double)rows));
+            *counter = 0;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bce_dice_bwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
+                                                           int64_t rows, int64_t per, float wbce,
+                                                           const double* __restrict__ acc, const float* __restrict__ gscale,
+                                                           float* __restrict__ dz) {
+    const int64_t row = blockIdx.y;
+    const float g = gscale ? *gscale : 1.f;
+    const double inter = acc[row * 4 + 1], den = acc[row * 4 + 2] + acc[row * 4 + 3] + 1.0;
+    const double num = 2.0 * inter + 1.0;
+    const float kb = wbce / ((float)rows * (float)per);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
+        const float zz = z[row * per + i], tt = t[row * per + i];
+        const float p = 1.f / (1.f + expf(-zz));
+        const float ddice = (float)(-(2.0 * tt * den - num) / (den * den) / (double)rows);
+        dz[row * per + i] = g * (kb * (p - tt) + ddice * p * (1.f - p));
+    }
+}
+
+// ---- layout / packing -------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int n, int c,
+                                                           int64_t hw) {
+    // y[(n*hw + p)*c + ch] = x[(n*c + ch)*hw + p]; tile-transpose through shared memory
+    __shared__ float tile[32][33];
+    const int img = blockIdx.z;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int ch = c0 + i;
+        const int64_t p = p0 + tx;
+        tile[i][tx] = (ch < c && p < hw) ? x[((int64_t)img * c + ch) * hw + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t p = p0 + i;
+        const int ch = c0 + tx;
+        if (ch < c && p < hw) Cvt<T>::st(y + ((int64_t)img * hw + p) * c + ch, tile[tx][i]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int n, int c,
+                                                           int64_t hw) {
+    __shared__ float tile[32][33];
+    const int img = blockIdx.z;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t p = p0 + i;
+        const int ch = c0 + tx;
+        tile[i][tx] = (ch < c && p < hw) ? Cvt<T>::ld(x + ((int64_t)img * hw + p) * c + ch) : 0.f;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int ch = c0 + i;
+        const int64_t p = p0 + tx;
+        if (ch < c && p < hw) y[((int64_t)img * c + ch) * hw + p] = tile[tx][i];
+    }
+}
+
+template <typename TS, typename TD>
+__global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        Cvt<TD>::st(d + i, Cvt<TS>::ld(s + i));
+}
+
+__global__ void __launch_bounds__(256) axpy_kernel(float alpha, const float* __restrict__ a, float* __restrict__ sum, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        sum[i] = fmaf(alpha, a[i], sum[i]);
+}
+
+// Wp[t][n][k] = w[n*sn + k*sk + t]; one thread per (n,k) reads its taps (contiguous in torch layout)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N,
+                                                          int K, int64_t sn, int64_t sk, int64_t st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
+    const float* src = w + n * sn + k * sk;
+    for (int t = 0; t < taps; ++t) Cvt<T>::st(wp + ((int64_t)t * N + n) * K + k, src[t * st]);
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int taps,
+                                                           int N, int K, int64_t sn, int64_t sk, int64_t st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)N * K) return;
+    const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
+    float* dst = dw + n * sn + k * sk;
+    for (int t = 0; t < taps; ++t) dst[t * st] = dwp[((int64_t)t * N + n) * K + k];
+}
+
+__global__ void __launch_bounds__(256) sum_into_kernel(const float* __restrict__ v, int64_t n, float scale, float* acc) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
+    s = block_sum_double(s);
+    if (threadIdx.x == 0) *acc += scale * (float)s;
+}
+
+__global__ void __launch_bounds__(256) fill_from_kernel(const float* __restrict__ g, float scale, float* __restrict__ out, int64_t n) {
+    const float v = scale * (g ? *g : 1.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
+}
+
+inline unsigned grid_for(int64_t n, int per_thread = 1) {
+    int64_t b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
+    const int64_t cap = 148 * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+}  // namespace
+}  // namespace vp
+
+using namespace vp;
+
+extern "C" int vp_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev,
+                                int num_sms, void* stream) {
+    VP_CHECK_ARG(out && n >= 0 && num_sms > 0, "vp_philox_normal: bad arguments");
+    if (n == 0) return VP_OK;
+    philox_normal_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, offset_dev, aten_threads(n, num_sms));
+    VP_CHECK_LAUNCH("vp_philox_normal");
+    return VP_OK;
+}
+
+extern "C" int vp_philox_advance(uint64_t* offset_dev, uint64_t inc, void* stream) {
+    VP_CHECK_ARG(offset_dev, "vp_philox_advance: null");
+    philox_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(offset_dev, inc);
+    VP_CHECK_LAUNCH("vp_philox_advance");
+    return VP_OK;
+}
+
+extern "C" int vp_reparam_kl_fwd(const float* mu, const float* logvar, int64_t ld, const float* eps_in, uint64_t seed,
+                                 uint64_t offset, const uint64_t* offset_dev, int num_sms, void* z, int z_dtype,
+                                 float* eps_out, float* kl, int64_t rows, int zdim, void* stream) {
+    VP_CHECK_ARG(mu && logvar && z && rows >= 0 && zdim > 0 && ld >= zdim && num_sms > 0, "vp_reparam_kl_fwd: bad arguments");
+    if (rows == 0) return VP_OK;
+    const int64_t nthreads = aten_threads(rows * zdim, num_sms);
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    if (z_dtype == VP_F32)
+        reparam_kl_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(mu, logvar, ld, eps_in, seed, offset, offset_dev, nthreads, (float*)z, eps_out, kl, rows, zdim);
+    else
+        reparam_kl_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(mu, logvar, ld, eps_in, seed, offset, offset_dev, nthreads, (bf16*)z, eps_out, kl, rows, zdim);
+    VP_CHECK_LAUNCH("vp_reparam_kl_fwd");
+    return VP_OK;
+}
+
+extern "C" int vp_reparam_kl_bwd(const float* mu, const float* logvar, int64_t ld, const float* eps, const void* dz,
+                                 int dz_dtype, const float* dkl, void* dmu, void* dlogvar, int out_dtype, int64_t ld_out,
+                                 int64_t rows, int zdim, void* stream) {
+    VP_CHECK_ARG(mu && logvar && eps && dmu && dlogvar && rows >= 0 && zdim > 0, "vp_reparam_kl_bwd: bad arguments");
+    if (rows == 0) return VP_OK;
+    const unsigned grid = (unsigned)((rows * zdim + 255) / 256);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (dz_dtype == VP_F32 && out_dtype == VP_F32)
+        reparam_kl_bwd_kernel<float, float><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const float*)dz, dkl, (float*)dmu, (float*)dlogvar, ld_out, rows, zdim);
+    else if (dz_dtype == VP_F32)
+        reparam_kl_bwd_kernel<float, bf16><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const float*)dz, dkl, (bf16*)dmu, (bf16*)dlogvar, ld_out, rows, zdim);
+    else if (out_dtype == VP_F32)
+        reparam_kl_bwd_kernel<bf16, float><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const bf16*)dz, dkl, (float*)dmu, (float*)dlogvar, ld_out, rows, zdim);
+    else
+        reparam_kl_bwd_kernel<bf16, bf16><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const bf16*)dz, dkl, (bf16*)dmu, (bf16*)dlogvar, ld_out, rows, zdim);
+    VP_CHECK_LAUNCH("vp_reparam_kl_bwd");
+    return VP_OK;
+}
+
+extern "C" int vp_recon_loss_fwd(const float* x, const float* xt, int64_t n, int kind, double* loss_acc,
+                                 unsigned int* counter, float* loss, void* stream) {
+    VP_CHECK_ARG(x && xt && loss_acc && counter && loss && n > 0 && (kind == 0 || kind == 1), "vp_recon_loss_fwd: bad arguments");
+    recon_fwd_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(x, xt, n, kind, loss_acc, counter, loss);
+    VP_CHECK_LAUNCH("vp_recon_loss_fwd");
+    return VP_OK;
+}
+
+extern "C" int vp_recon_loss_bwd(const float* x, const float* xt, int64_t n, int kind, const float* gscale, float* dxt,
+                                 void* stream) {
+    VP_CHECK_ARG(x && xt && dxt && n > 0 && (kind == 0 || kind == 1), "vp_recon_loss_bwd: bad arguments");
+    recon_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, xt, n, kind, gscale, dxt);
+    VP_CHECK_LAUNCH("vp_recon_loss_bwd");
+    return VP_OK;
+}
+
+extern "C" int vp_bce_dice_fwd(const float* logits, const float* target, int64_t rows, int64_t per, float bce_weight,
+                               double* acc, unsigned int* counter, float* loss, void* stream) {
+    VP_CHECK_ARG(logits && target && acc && counter && loss && rows > 0 && rows <= 65535 && per > 0, "vp_bce_dice_fwd: bad arguments");
+    dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), (unsigned)rows);
+    cudaMemsetAsync(acc, 0, sizeof(double) * 4 * rows, (cudaStream_t)stream);
+    bce_dice_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, rows, per, bce_weight, acc, counter, loss);
+    VP_CHECK_LAUNCH("vp_bce_dice_fwd");
+    return VP_OK;
+}
+
+extern "C" int vp_bce_dice_bwd(const float* logits, const float* target, int64_t rows, int64_t per, float bce_weight,
+                               const double* acc, const float* gscale, float* dlogits, void* stream) {
+    VP_CHECK_ARG(logits && target && acc && dlogits && rows > 0 && rows <= 65535 && per > 0, "vp_bce_dice_bwd: bad arguments");
+    dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), (unsigned)rows);
+    bce_dice_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, rows, per, bce_weight, acc, gscale, dlogits);
+    VP_CHECK_LAUNCH("vp_bce_dice_bwd");
+    return VP_OK;
+}
+
+extern "C" int vp_nchw_to_nhwc(const float* x, void* y, int dtype, int n, int c, int h, int w, void* stream) {
+    VP_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "vp_nchw_to_nhwc: bad arguments");
+    const int64_t hw = (int64_t)h * w;
+    dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, n);
+    if (dtype == VP_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n, c, hw);
+    else nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n, c, hw);
+    VP_CHECK_LAUNCH("vp_nchw_to_nhwc");
+    return VP_OK;
+}
+
+extern "C" int vp_nhwc_to_nchw(const void* x, float* y, int dtype, int n, int c, int h, int w, void* stream) {
+    VP_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "vp_nhwc_to_nchw: bad arguments");
+    const int64_t hw = (int64_t)h * w;
+    dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, n);
+    if (dtype == VP_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, n, c, hw);
+    else nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n, c, hw);
+    VP_CHECK_LAUNCH("vp_nhwc_to_nchw");
+    return VP_OK;
+}
+
+extern "C" int vp_cast(const void* src, int sd, void* dst, int dd, int64_t n, void* stream) {
+    VP_CHECK_ARG(src && dst && n >= 0, "vp_cast: bad arguments");
+    if (n == 0) return VP_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned g = grid_for(n);
+    if (sd == VP_F32 && dd == VP_BF16) cast_kernel<float, bf16><<<g, 256, 0, s>>>((const float*)src, (bf16*)dst, n);
+    else if (sd == VP_BF16 && dd == VP_F32) cast_kernel<bf16, float><<<g, 256, 0, s>>>((const bf16*)src, (float*)dst, n);
+    else if (sd == VP_F32 && dd == VP_F32) cast_kernel<float, float><<<g, 256, 0, s>>>((const float*)src, (float*)dst, n);
+    else cast_kernel<bf16, bf16><<<g, 256, 0, s>>>((const bf16*)src, (bf16*)dst, n);
+    VP_CHECK_LAUNCH("vp_cast");
+    return VP_OK;
+}
+
+extern "C" int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream) {
+    VP_CHECK_ARG(a && sum && n >= 0, "vp_axpy: bad arguments");
+    if (n == 0) return VP_OK;
+    axpy_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(alpha, a, sum, n);
+    VP_CHECK_LAUNCH("vp_axpy");
+    return VP_OK;
+}
+
+extern "C" int vp_pack_weight(const float* w, void* wp, int dtype, int taps, int n, int k, int64_t sn, int64_t sk,
+                              int64_t st, void* stream) {
+    VP_CHECK_ARG(w && wp && taps > 0 && n > 0 && k > 0, "vp_pack_weight: bad arguments");
+    const unsigned g = (unsigned)(((int64_t)n * k + 255) / 256);
+    if (dtype == VP_F32) pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(w, (float*)wp, taps, n, k, sn, sk, st);
+    else pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, taps, n, k, sn, sk, st);
+    VP_CHECK_LAUNCH("vp_pack_weight");
+    return VP_OK;
+}
+
+extern "C" int vp_unpack_wgrad(const float* dwp, float* dw, int taps, int n, int k, int64_t sn, int64_t sk, int64_t st,
+                               void* stream) {
+    VP_CHECK_ARG(dwp && dw && taps > 0 && n > 0 && k > 0, "vp_unpack_wgrad: bad arguments");
+    const unsigned g = (unsigned)(((int64_t)n * k + 255) / 256);
+    unpack_wgrad_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(dwp, dw, taps, n, k, sn, sk, st);
+    VP_CHECK_LAUNCH("vp_unpack_wgrad");
+    return VP_OK;
+}
+
+extern "C" int vp_sum_into(const float* v, int64_t n, float scale, float* acc, void* stream) {
+    VP_CHECK_ARG(v && acc && n >= 0, "vp_sum_into: bad arguments");
+    sum_into_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(v, n, scale, acc);
+    VP_CHECK_LAUNCH("vp_sum_into");
+    return VP_OK;
+}
+
+extern "C" int vp_fill_from(const float* g, float scale, float* out, int64_t n, void* stream) {
+    VP_CHECK_ARG(out && n >= 0, "vp_fill_from: bad arguments");
+    if (n == 0) return VP_OK;
+    fill_from_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(g, scale, out, n);
+    VP_CHECK_LAUNCH("vp_fill_from");
+    return VP_OK;
+}
