@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""Benchmark of the VAE training step (the north-star metric: train images/sec).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on host cores
+
+A "step" is zero_grad -> Encoder -> reparameterise(+KL) -> Decoder -> mse + sum(kl) -> backward
+(-> bucketed gradient all-reduce when N > 1) -> RMSprop(lr=1e-4) step, on one batch of synthetic
+64x64 grayscale images at batch 256 per GPU (BASELINE.json configs[1], resolved in SURVEY.md section 0 to
+the models/networks.py VAE).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic FLOPs per image per training step (fwd + dgrad + wgrad), SURVEY.md section 8d / BASELINE.md section 3
+STEP_MFLOP = {(64, 1): 3935.6, (64, 3): 4027.3, (128, 1): 21802.6}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline_sample(img, cin, steps=5, warmup=2, batch=16):
+    from oracle.vae_torch import time_cpu_steps
+    ips, ms, threads = time_cpu_steps(img=img, cin=cin, batch=batch, steps=steps, warmup=warmup)
+    return {"value": round(ips, 2), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": f"oracle/vae_torch.py (torch-CPU restatement of models/networks.py + train.py step), fp32, batch {batch}, "
+                      f"median of {steps} steps after {warmup} warm-up, {ms:.1f} ms/step"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (torch CPU ops) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import vae_numpy as vn
+    from oracle.vae_torch import VaeTorchPort
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    sample_b = args.ref_batch
+    P = vn.synth_vae_params(args.img, 128, args.cin, args.cin, 0)
+    port = VaeTorchPort(P, torch.float32)
+    x = torch.from_numpy(vn.synth_batch(sample_b, args.img, args.cin, 128, 0)[0])
+    for _ in range(args.warmup):
+        port.step(x)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        port.step(x)
+    dt = time.perf_counter() - t0
+    ips = sample_b * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "train_images_per_sec", "value": round(ips, 2), "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, sample_b, note=f"CPU sample: each step is one train step on {sample_b} images"),
+        "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"oracle/vae_torch.py fp32, {sample_b} images per step, {args.steps} steps"},
+        "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch, note=None):
+    cfg = {"workload": f"models/networks.py VAE (Encoder+reparameterize+Decoder, KL+MSE) {args.img}x{args.img}x{args.cin}, z=128, "
+                       f"batch {batch}/GPU, fwd+loss+bwd+RMSprop",
+           "img_size": args.img, "channels": args.cin, "batch_per_gpu": batch, "z": 128,
+           "optimizer": "torch.optim.RMSprop(lr=1e-4) inside the timed step (train.py:136-140)"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import vae_play_b200 as vp
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    from vae_play_b200.models.networks import VaeGan
+    from vae_play_b200.parallel import GradBuckets
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    vp.set_precision(args.precision)
+    B, img, cin = args.batch, args.img, args.cin
+    if cin != 1:
+        raise SystemExit("bench: the stock VaeGan is grayscale (models/networks.py:207-209); use --cin 1")
+    torch.manual_seed(0)
+    model = VaeGan(img, 128).to(dev).train()
+    params = list(model.encoder.parameters()) + list(model.decoder.parameters())
+    opt = torch.optim.RMSprop(params, lr=1e-4)
+    buckets = GradBuckets(params, world) if world > 1 else None
+    torch.manual_seed(1234 + rank)
+    x_host = torch.rand(B, cin, img, img).pin_memory()
+    x_dev = x_host.to(dev)
+    off_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    n_eps = B * 128
+    _, eps_inc = VF.philox_policy(n_eps, torch.cuda.get_device_properties(dev).multi_processor_count)
+    state = {"offset": 0}
+
+    def step(x):
+        opt.zero_grad(set_to_none=True)
+        # disjoint, reproducible Philox streams per rank: seed = rank, offset advances like normal_() would
+        xt, mulv, kl = model.vae_forward(x, rng=(rank, state["offset"], None))
+        state["offset"] += eps_inc
+        loss = VF.vae_loss(x, xt, kl)
+        loss.backward()
+        if buckets is not None:
+            buckets.allreduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(x_dev)
+    barrier()
+
+    # ---- timed region 1: inputs resident in HBM -----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = step(x_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    ips = world * B * args.steps / (ms / 1e3)
+
+    # ---- timed region 2: end to end through the public API with HOST inputs -----------------------
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        xd = x_host.to(dev, non_blocking=True)
+        loss = step(xd)
+        loss_host = loss.item()           # D2H read of the step's result
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    t = torch.tensor([ms2], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms2 = float(t.item())
+    e2e_ips = world * B * args.steps / (ms2 / 1e3)
+    assert math.isfinite(loss_host), "non-finite loss"
+
+    # ---- dominant-kernel probe: decoder.conv.2 transposed conv forward (largest contraction) -----
+    peaks = load_peaks()
+    roof = kernel_probe(model, B, dev, peaks) if rank == 0 else None
+
+    if rank == 0:
+        mflop = STEP_MFLOP.get((img, cin))
+        step_tf = ips / world * mflop * 1e6 / 1e12 if mflop else None
+        line = {
+            "metric": "train_images_per_sec", "value": round(ips, 1), "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": dict(workload_config(args, B), parallelism=f"dp{world}",
+                           l2="no explicit flush: per-step working set (~1 GB of activations at batch 256) exceeds the 126 MB L2",
+                           cuda_graph=False),
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_ips, 1), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": round(ms2 / args.steps, 4)},
+            "gpu_launches": int(launches),
+            "roofline": roof,
+            "step_tflops_per_gpu": round(step_tf, 2) if step_tf else None,
+            "step_frac_of_sustained_bf16": round(step_tf / peaks["tf_sustained"], 4) if step_tf else None,
+            "peaks": peaks["src"],
+            "loss": loss_host,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample(img, cin)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_probe(model, B, dev, peaks, iters=20):
+    """Time the dominant contraction alone with CUDA events on the launching stream."""
+    import torch
+
+    import vae_play_b200.functional as VF
+    blk = list(model.decoder.conv)[-2]          # last DecoderBlock: convT 5x5 s2, 128->64 at 32x32 -> 64x64 (64x64 model)
+    layer = blk._layer
+    hin = model.decoder.conv[0]._layer and (8 * 2 ** (len(list(model.decoder.conv)) - 2))
+    x = torch.randn(B, hin, hin, layer.cin, device=dev).to(VF.act_dtype())
+    w = blk.conv.weight.detach()
+    for _ in range(3):
+        layer.fwd(x, w, None)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        layer.fwd(x, w, None)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 2.0 * B * hin * hin * layer.cin * layer.cout * 25          # 2*MAC of the transposed conv
+    tf = flops / (ms / 1e3) / 1e12
+    return {"bound": "tensor", "kernel": f"decoder.conv.{len(list(model.decoder.conv)) - 2} ConvTranspose2d fwd (4 phase launches)",
+            "achieved": round(tf, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_burst"], 4),
+            "traffic": None, "ms_per_launch_group": round(ms, 4), "peak_kind": f"{peaks['src']} burst"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--img", type=int, default=64)
+    ap.add_argument("--cin", type=int, default=1)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--ref-batch", type=int, default=16)
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

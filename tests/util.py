@@ -20,6 +20,14 @@ def rel(a, b):
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300))
 
 
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2"""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    return float(np.sqrt(((a - b) ** 2).sum()) / (np.sqrt((b ** 2).sum()) + 1e-300))
+
+
 def digest(a, nsamp=64):
     a = np.asarray(a, np.float64).ravel()
     idx = np.linspace(0, a.size - 1, num=min(nsamp, a.size)).astype(np.int64)

@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT) tapgemm_simt_kernel(const TapGemm p) {
 }
 
 // dWp[widx_t][gc][ac] += sum_m G[m][gc] * A[pix(m,t)][ac]; block = (gc tile, ac tile, tap*split)
-template <typename T>
+template <typename T, typename TAcc>
 __global__ void __launch_bounds__(NT) tapwgrad_simt_kernel(const TapWgrad p, int nsplit) {
     __shared__ float Gs[BK][BM + 4];
     __shared__ float As[BK][BN + 4];
@@ -124,11 +124,11 @@ __global__ void __launch_bounds__(NT) tapwgrad_simt_kernel(const TapWgrad p, int
     const int lc = (tid & 15) * 4;
     const int tr = (tid >> 4) * 4;
     const int tc = (tid & 15) * 4;
-    float acc[4][4];
+    TAcc acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = (TAcc)0;
 
     for (int64_t mb = mbeg; mb < mend; mb += BK) {
         const int64_t m = mb + lm;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NT) tapwgrad_simt_kernel(const TapWgrad p, int
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 4; ++j) acc[i][j] += (TAcc)a[i] * (TAcc)b[j];
         }
         __syncthreads();
     }
@@ -174,8 +174,8 @@ __global__ void __launch_bounds__(NT) tapwgrad_simt_kernel(const TapWgrad p, int
         for (int j = 0; j < 4; ++j) {
             const int ac = ac0 + tc + j;
             if (ac < p.AC) {
-                if (nsplit == 1) out[(int64_t)gc * p.AC + ac] = acc[i][j];
-                else atomicAdd(out + (int64_t)gc * p.AC + ac, acc[i][j]);
+                if (nsplit == 1) out[(int64_t)gc * p.AC + ac] = (float)acc[i][j];
+                else atomicAdd(out + (int64_t)gc * p.AC + ac, (float)acc[i][j]);
             }
         }
     }
@@ -200,12 +200,15 @@ int launch_tapwgrad_simt(const TapWgrad& p, int dtype, cudaStream_t s) {
     if (M == 0 || p.GC == 0 || p.AC == 0) return VP_OK;
     const int tiles = ((p.GC + BM - 1) / BM) * ((p.AC + BN - 1) / BN) * p.taps.ntaps;
     // split the pixel reduction so that a few waves of CTAs are in flight (148 SMs)
+    // fp32 check mode: one double-precision accumulation chain per output (deterministic, single rounding);
+    // the gradient of a conv that feeds BatchNorm is a heavily cancelling sum, fp32 chains lose ~1e-3 there.
     int nsplit = 1;
     const int64_t max_split = (M + 255) / 256;
-    while ((int64_t)tiles * nsplit < 148 * 4 && nsplit * 2 <= max_split) nsplit *= 2;
+    if (dtype != VP_F32)
+        while ((int64_t)tiles * nsplit < 148 * 4 && nsplit * 2 <= max_split) nsplit *= 2;
     dim3 grid((p.GC + BM - 1) / BM, (p.AC + BN - 1) / BN, p.taps.ntaps * nsplit);
-    if (dtype == VP_F32) tapwgrad_simt_kernel<float><<<grid, NT, 0, s>>>(p, nsplit);
-    else tapwgrad_simt_kernel<bf16><<<grid, NT, 0, s>>>(p, nsplit);
+    if (dtype == VP_F32) tapwgrad_simt_kernel<float, double><<<grid, NT, 0, s>>>(p, nsplit);
+    else tapwgrad_simt_kernel<bf16, float><<<grid, NT, 0, s>>>(p, nsplit);
     VP_CHECK_LAUNCH("tapwgrad_simt");
     return VP_OK;
 }

@@ -18,6 +18,23 @@ from . import _lib
 from ._lib import ACT, BF16, F32, VpConvGeom
 
 _STATE = {"precision": "bf16", "engine": _lib.ENGINE_AUTO}
+_TRACE = None      # when a list: every fused layer appends its activated output (tests / diagnostics only)
+_GRAD_SINKS = {}   # param.data_ptr() -> (bucket view, param): where wgrad writes directly (vae_play_b200.parallel)
+
+
+def set_grad_sinks(sinks_by_param_id, params=None):
+    """Register flat-bucket slots for parameter gradients (data-parallel training)."""
+    _GRAD_SINKS.clear()
+    _GRAD_SINKS.update(sinks_by_param_id)
+
+
+def _grad_target(weight):
+    hit = _GRAD_SINKS.get(weight.data_ptr())
+    if hit is not None:
+        view, param = hit
+        if param.grad is None and view.shape == weight.shape:
+            return view
+    return torch.empty_like(weight, dtype=torch.float32)
 
 
 def set_precision(mode: str):
@@ -198,7 +215,7 @@ class TapLayer:
             ho, wo = dy.shape[1], dy.shape[2]
             g = self._geom(n, h, w, self.cin, ho, wo, self.cout, self.k, self.stride, self.pad, int(self.kind == "convT"))
             _lib.call("vp_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dwp), _code(dt), _STATE["engine"], _stream())
-        dw = torch.empty_like(weight, dtype=torch.float32)
+        dw = _grad_target(weight)
         _lib.call("vp_unpack_wgrad", _ptr(dwp), _ptr(dw), p.taps, p.n, p.k, p.sn, p.sk, p.st, _stream())
         return dw
 
@@ -233,6 +250,7 @@ class _FusedLayerFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, gamma, beta, layer: TapLayer, norm: NormCfg, act, slope, training, bn_module,
                 out_dtype):
         _require_cuda(x, "fused layer input")
+        ctx.set_materialize_grads(False)
         dt = x.dtype
         out_dtype = out_dtype or dt
         ctx.layer, ctx.norm, ctx.act, ctx.slope = layer, norm, act, slope
@@ -303,6 +321,8 @@ class _FusedLayerFn(torch.autograd.Function):
         dgamma = dbeta = dbias = None
         if norm.kind is None:
             x, weight, a = ctx.saved_tensors
+            if da is None:
+                return (None,) * 12
             da = da.contiguous()
             dt = x.dtype
             n, h, w, c = a.shape
@@ -330,6 +350,8 @@ class _FusedLayerFn(torch.autograd.Function):
             mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
             groups, rpg, cc, c = ctx.dims
             dt = y.dtype
+            if da is None and dy_extra is None:
+                return (None,) * 12
             if da is None:
                 # only the pre-norm output was used (Discriminator 'REC' mode, networks.py:180-185)
                 dy = dy_extra.contiguous()
@@ -363,7 +385,17 @@ class _FusedLayerFn(torch.autograd.Function):
 
 
 def fused_layer(x, weight, bias, gamma, beta, layer, norm, act, slope, training, bn_module=None, out_dtype=None):
-    return _FusedLayerFn.apply(x, weight, bias, gamma, beta, layer, norm, act, slope, training, bn_module, out_dtype)
+    out = _FusedLayerFn.apply(x, weight, bias, gamma, beta, layer, norm, act, slope, training, bn_module, out_dtype)
+    if _TRACE is not None:
+        _TRACE.append(out[0].detach())
+    return out
+
+
+def trace_activations(enable: bool):
+    """Start (returns the list that will be filled) or stop recording each fused layer's activated output."""
+    global _TRACE
+    _TRACE = [] if enable else None
+    return _TRACE
 
 
 # ------------------------------------------------------------------------------------------------
@@ -448,6 +480,7 @@ class _ReparamKL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu, logvar, eps, z_dtype, rng):
         _require_cuda(mu, "reparameterize mu")
+        ctx.set_materialize_grads(False)
         ctx.packed = logvar is None
         if ctx.packed:  # mu is the fused head output [B, 2Z] = (mu | logvar)
             packed = mu

@@ -1,0 +1,102 @@
+"""Data-parallel gradient exchange for the VAE step: one process per GPU, batch sharded per rank,
+parameters replicated, ONE sum all-reduce of the gradients per step in a few large buckets.
+
+The reference is single-GPU; batch sharding is the path's only natural
+partition (section 8e).  Buckets are flat fp32 buffers filled in reverse layer order; the wgrad
+kernels write parameter gradients straight into their bucket slot (``functional.set_grad_sinks``), a
+post-accumulate hook marks the slot ready, and as soon as a bucket is complete its NCCL all-reduce
+is issued asynchronously so that it overlaps the rest of backward.  BatchNorm statistics stay
+per-rank (DDP semantics), so a rank reproduces the single-GPU reference at its own batch.
+
+Loss scaling: with L = mean-type mse + sum-type KL, the single-process equivalent of W ranks is
+L = (1/W) sum_r mse_r + sum_r kl_r, i.e. each rank scales its mse term by 1/W and gradients are
+summed -- no post-scaling pass.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    def __init__(self, params: List[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.world = world_size
+        self.group = group
+        cap = int(bucket_mb * (1 << 20) / 4)
+        # reverse registration order ~ the order gradients become ready in backward
+        order = list(reversed(self.params))
+        self.buckets = []          # list of dict(buf, params, ready, handle)
+        cur, cur_n = [], 0
+        for p in order:
+            if cur and cur_n + p.numel() > cap:
+                self._close(cur)
+                cur, cur_n = [], 0
+            cur.append(p)
+            cur_n += p.numel()
+        if cur:
+            self._close(cur)
+        self.slot = {}
+        for bi, b in enumerate(self.buckets):
+            off = 0
+            for p in b["params"]:
+                view = b["buf"][off: off + p.numel()].view_as(p)
+                self.slot[id(p)] = (bi, view)
+                off += p.numel()
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._install_sinks()
+
+    def _close(self, plist):
+        n = sum(p.numel() for p in plist)
+        dev = plist[0].device
+        self.buckets.append({"buf": torch.zeros(n, dtype=torch.float32, device=dev), "params": list(plist),
+                             "ready": 0, "handle": None})
+
+    def _install_sinks(self):
+        try:
+            from . import functional as VF
+            VF.set_grad_sinks({p.data_ptr(): (self.slot[id(p)][1], p) for p in self.params})
+        except Exception:  # pragma: no cover - CPU-only host-logic tests
+            pass
+
+    # ---- hook: called once per parameter per backward, after .grad has been accumulated -----------
+    def _on_grad(self, p):
+        bi, view = self.slot[id(p)]
+        g = p.grad
+        if g.data_ptr() != view.data_ptr():
+            # gradient was produced elsewhere (e.g. accumulated over several backward calls): copy in
+            view.copy_(g)
+            p.grad = view
+        b = self.buckets[bi]
+        b["ready"] += 1
+        if b["ready"] == len(b["params"]) and self.world > 1:
+            b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def allreduce(self):
+        """Finish the step's exchange: launch whatever is still pending, wait for everything."""
+        for b in self.buckets:
+            if self.world > 1 and b["handle"] is None:
+                # some parameter of this bucket received no gradient this step: its slot must not carry stale data
+                for p in b["params"]:
+                    if p.grad is None:
+                        self.slot[id(p)][1].zero_()
+                b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        for b in self.buckets:
+            if b["handle"] is not None:
+                b["handle"].wait()
+                b["handle"] = None
+            b["ready"] = 0
+
+    def total_bytes(self):
+        return sum(b["buf"].numel() * 4 for b in self.buckets)
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        try:
+            from . import functional as VF
+            VF.set_grad_sinks({})
+        except Exception:  # pragma: no cover
+            pass
