@@ -452,3 +452,62 @@ def test_abi_error_codes(vp):
     assert rc == -3
     with pytest.raises(_lib.VaePlayError):
         vp.mse_loss(torch.zeros(4), torch.zeros(4))  # CPU tensors: no CPU path
+
+
+# ------------------------------------------------------------------------------------------------
+# tcgen05 engine vs the CUDA-core engine on identical bf16 operands (fp32 outputs compared)
+# ------------------------------------------------------------------------------------------------
+TC_SHAPES = [
+    # kind, cin, cout, hw, batch
+    ("conv", 64, 128, 32, 4), ("conv", 128, 256, 16, 4), ("conv", 64, 128, 32, 3),
+    ("convT", 256, 256, 8, 4), ("convT", 256, 128, 16, 2), ("convT", 128, 64, 32, 2),
+    ("flatten_in", 256, 1024, 8, 16), ("flatten_out", 128, 256, 1, 16), ("linear", 1024, 256, 1, 40),
+    ("conv_s1", 64, 1, 64, 2), ("conv_s1", 64, 3, 32, 2), ("conv_k3", 64, 96, 20, 3),
+]
+
+
+def _tc_layer(kind, cin, cout):
+    import vae_play_b200.functional as VF
+    g = torch.Generator(device="cuda").manual_seed(11)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g) * 0.05
+    if kind == "conv":
+        return VF.TapLayer("conv", cin, cout, k=5, stride=2, pad=2), r(cout, cin, 5, 5)
+    if kind == "conv_s1":
+        return VF.TapLayer("conv", cin, cout, k=5, stride=1, pad=2), r(cout, cin, 5, 5)
+    if kind == "conv_k3":
+        return VF.TapLayer("conv", cin, cout, k=3, stride=1, pad=1), r(cout, cin, 3, 3)
+    if kind == "convT":
+        return VF.TapLayer("convT", cin, cout, k=5, stride=2, pad=2, out_pad=1), r(cin, cout, 5, 5)
+    if kind == "flatten_in":
+        return VF.TapLayer("flatten_in", cin, cout, spatial=8), r(cout, cin * 64)
+    if kind == "flatten_out":
+        return VF.TapLayer("flatten_out", cin, cout, spatial=8), r(cout * 64, cin)
+    return VF.TapLayer("linear", cin, cout), r(cout, cin)
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,b", TC_SHAPES)
+def test_tc_engine_matches_simt(vp, kind, cin, cout, hw, b):
+    import vae_play_b200.functional as VF
+    vp.set_precision("bf16")
+    layer, w = _tc_layer(kind, cin, cout)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(b, hw, hw, cin, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g) if kind.startswith("conv_") else None
+    try:
+        vp.set_engine("simt")
+        y_ref = layer.fwd(x, w, bias, out_dtype=torch.float32)
+        dy = torch.randn(y_ref.shape, device="cuda", generator=g).to(torch.bfloat16)
+        dx_ref = layer.dgrad(dy, w, tuple(x.shape), out_dtype=torch.float32)
+        vp.set_engine("tc")
+        layer._cache.clear()
+        y = layer.fwd(x, w, bias, out_dtype=torch.float32)
+        y16 = layer.fwd(x, w, bias, "relu")
+        torch.cuda.synchronize()
+        close(npy(y), npy(y_ref), 1e-4, f"{kind} fwd tc-vs-simt")
+        close(npy(y16), npy(torch.relu(y_ref).to(torch.bfloat16)), 8e-3, f"{kind} fwd bf16+relu epilogue")
+        if cin % 64 == 0 and cout % 64 == 0:
+            dx = layer.dgrad(dy, w, tuple(x.shape), out_dtype=torch.float32)
+            torch.cuda.synchronize()
+            close(npy(dx), npy(dx_ref), 1e-4, f"{kind} dgrad tc-vs-simt")
+    finally:
+        vp.set_engine("auto")

@@ -1,8 +1,436 @@
-// tcgen05 engine (placeholder until the TMA/UMMA kernels land): reports "unsupported" so that AUTO falls
-// back to the CUDA-core engine and ENGINE_TC fails loudly.
+// tcgen05 engine of the tap GEMM (sm_100a): TMA-fed implicit GEMM, bf16 operands, fp32 accumulation in TMEM.
+//
+//   D[n, gy*ds+doy, gx*ds+dox, :] = sum_t A[n, gy*as+ty_t, gx*as+tx_t, :] . Wp[widx_t][:, :]
+//
+// One CTA computes a 128 x BLOCK_N output tile; the 128 rows are a (bt x ht x wt) brick of the iteration grid,
+// so that for every filter tap the A operand of the tile is ONE 4-D TMA box of the channels-last activation
+// tensor (box {64 ch, wt, ht, bt}, element strides {1, as, as, 1}; out-of-bounds rows -- the conv zero padding
+// -- are zero-filled by the TMA unit).  The box lands in shared memory as 128 rows of 128 B with the 128-byte
+// swizzle, which is exactly the K-major SW128 canonical layout tcgen05.mma consumes.  B is a {64, BLOCK_N, 1}
+// box of the packed weights viewed as [K, N, taps].
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = barrier init + TMEM alloc + MMA issuer,
+// warps 2..5 = epilogue (TMEM -> registers -> bias/activation -> global, one output row per thread).
+// Pipelines: smem full/empty mbarriers between TMA and MMA, one "accumulator ready" mbarrier MMA -> epilogue.
+#include <cuda.h>
+
 #include "common.cuh"
+
 namespace vp {
-bool tc_available() { return false; }
-int launch_tapgemm_tc(const TapGemm&, cudaStream_t) { set_error("tcgen05 engine not built"); return VP_EUNSUPPORTED; }
-int launch_tapwgrad_tc(const TapWgrad&, cudaStream_t) { set_error("tcgen05 engine not built"); return VP_EUNSUPPORTED; }
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // bf16 elements = 128 bytes = one swizzle row
+constexpr int kThreads = 192;
+constexpr int kABytes = kBlockM * kBlockK * 2;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// Bounded wait: a pipeline bug must surface as a trapped kernel (launch error), never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    printf("vaeplay_b200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+    __trap();
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+            smem_u32(smem)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane (lane_base + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), start address advanced by
+// 32 B per UMMA_K=16 step.  Bits: [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,
+// [46,48) version=1 (Blackwell), [61,64) layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+struct TcParams {
+    void* D;
+    const float* bias;
+    int n, hd, wd, N;
+    int gh, gw;
+    int as, ds, doy, dox;
+    int act;
+    float slope;
+    int out_f32;
+    int kblocks;          // K / 64
+    int bt, ht, wt;       // tile brick, bt*ht*wt == 128
+    int tiles_w, tiles_h; // bricks along gx, gy (batch bricks are the remainder of blockIdx.x)
+    TapList taps;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int kBBytes = BN * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B operands need 1024-byte alignment of every tile
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + L::kBarOffset);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_ready = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr int kTmemCols = BN < 32 ? 32 : BN;
+
+    // tile -> brick origin
+    int tile = blockIdx.x;
+    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
+    const int th = tile % p.tiles_h; tile /= p.tiles_h;
+    const int n0 = tile * p.bt;
+    const int gy0 = th * p.ht, gx0 = tw * p.wt;
+    const int col0 = blockIdx.y * BN;
+    const int iters = p.taps.ntaps * p.kblocks;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            mbar_init(acc_ready, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                const int t = it / p.kblocks;
+                const int kb = it - t * p.kblocks;
+                uint8_t* sa = smem + s * L::kStageBytes;
+                uint8_t* sb = sa + kABytes;
+                mbar_expect_tx(&full[s], L::kStageBytes);
+                tma_load_4d(sa, &mapA, &full[s], kb * kBlockK, gx0 * p.as + p.taps.tx[t], gy0 * p.as + p.taps.ty[t], n0);
+                tma_load_3d(sb, &mapB, &full[s], kb * kBlockK, col0, p.taps.widx[t]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = idesc_bf16_f32(kBlockM, BN < 16 ? 16 : BN);
+        if (elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+                const uint32_t sb = sa + kABytes;
+                const uint64_t adesc = smem_desc_k_sw128(sa);
+                const uint64_t bdesc = smem_desc_k_sw128(sb);
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+                    tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                }
+                tc_commit(&empty[s]);          // frees the smem slot when these MMAs have read it
+            }
+            tc_commit(acc_ready);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+        const int lane_base = (warp & 3) * 32;
+        const int r = lane_base + lane;                       // row of the tile = TMEM lane
+        const int bw = r % p.wt;
+        const int bh = (r / p.wt) % p.ht;
+        const int bb = r / (p.wt * p.ht);
+        const int n = n0 + bb, gy = gy0 + bh, gx = gx0 + bw;
+        const int oy = gy * p.ds + p.doy, ox = gx * p.ds + p.dox;
+        const bool row_ok = n < p.n && gy < p.gh && gx < p.gw && oy < p.hd && ox < p.wd;
+        const int64_t row_off = (((int64_t)n * p.hd + oy) * p.wd + ox) * p.N;
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += CH) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c;
+            if (CH == 32) tmem_ld32(taddr, v);
+            else tmem_ld16(taddr, v);
+            tmem_ld_wait();
+            if (row_ok) {
+                const int cbase = col0 + c;
+                if (p.out_f32) {
+                    float* out = (float*)p.D + row_off + cbase;
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4) {
+                        float f[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float x = __uint_as_float(v[j + q]);
+                            if (p.bias && cbase + j + q < p.N) x += p.bias[cbase + j + q];
+                            f[q] = act_fwd(x, p.act, p.slope);
+                        }
+                        if (cbase + j + 3 < p.N && (p.N & 3) == 0) {
+                            *reinterpret_cast<float4*>(out + j) = make_float4(f[0], f[1], f[2], f[3]);
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) if (cbase + j + q < p.N) out[j + q] = f[q];
+                        }
+                    }
+                } else {
+                    bf16* out = (bf16*)p.D + row_off + cbase;
+#pragma unroll
+                    for (int j = 0; j < CH; j += 8) {
+                        float f[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float x = __uint_as_float(v[j + q]);
+                            if (p.bias && cbase + j + q < p.N) x += p.bias[cbase + j + q];
+                            f[q] = act_fwd(x, p.act, p.slope);
+                        }
+                        if (cbase + j + 7 < p.N && (p.N & 7) == 0) {
+                            uint4 pk;
+                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                            *reinterpret_cast<uint4*>(out + j) = pk;
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) if (cbase + j + q < p.N) out[j + q] = __float2bfloat16_rn(f[q]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // teardown: everyone is done with TMEM before the allocating warp frees it
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+template <int BN, int STAGES>
+int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp, dim3 grid, cudaStream_t s) {
+    using L = SmemLayout<BN, STAGES>;
+    constexpr int smem_bytes = L::kTotal + 1024;  // + alignment slack
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) { set_error("tapgemm_tc: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
+        attr_set = true;
+    }
+    tapgemm_tc_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, s>>>(mA, mB, tp);
+    VP_CHECK_LAUNCH("tapgemm_tc");
+    return VP_OK;
+}
+
+}  // namespace
+
+bool tc_available() {
+    static int cached = -1;
+    if (cached < 0) {
+        int dev = 0, maj = 0;
+        cached = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev) == cudaSuccess &&
+            maj == 10 && get_encode() != nullptr)
+            cached = 1;
+    }
+    return cached == 1;
+}
+
+int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) {
+    // ---- eligibility -----------------------------------------------------------------------------------
+    if (!tc_available()) { set_error("tcgen05 engine: needs an sm_100 device and cuTensorMapEncodeTiled"); return VP_EUNSUPPORTED; }
+    if (p.K % kBlockK != 0 || p.taps.ntaps < 1 || p.N < 1) { set_error("tcgen05 engine: K=%d must be a multiple of 64", p.K); return VP_EUNSUPPORTED; }
+    if (((uintptr_t)p.A & 15) || ((uintptr_t)p.Wp & 15) || ((uintptr_t)p.D & 15)) { set_error("tcgen05 engine: 16-byte alignment"); return VP_EUNSUPPORTED; }
+    if (p.as < 1 || p.as > 8) { set_error("tcgen05 engine: gather stride %d", p.as); return VP_EUNSUPPORTED; }
+    const int64_t M = (int64_t)p.n * p.gh * p.gw;
+    if (M <= 0) return VP_OK;
+    EncodeTiledFn encode = get_encode();
+
+    // ---- tile brick ------------------------------------------------------------------------------------
+    TcParams tp;
+    int wt = pow2_floor(p.gw < kBlockM ? p.gw : kBlockM);
+    if (wt * p.as > 256) wt = pow2_floor(256 / p.as);
+    int ht = pow2_ceil(p.gh);
+    if (ht > kBlockM / wt) ht = kBlockM / wt;
+    if (ht * p.as > 256) ht = pow2_floor(256 / p.as);
+    int bt = kBlockM / (wt * ht);
+    tp.bt = bt; tp.ht = ht; tp.wt = wt;
+    tp.tiles_w = (p.gw + wt - 1) / wt;
+    tp.tiles_h = (p.gh + ht - 1) / ht;
+    const int tiles_b = (p.n + bt - 1) / bt;
+    const int64_t mtiles = (int64_t)tp.tiles_w * tp.tiles_h * tiles_b;
+    if (mtiles > 0x7fffffff) { set_error("tcgen05 engine: too many tiles"); return VP_EUNSUPPORTED; }
+
+    // ---- tensor maps -----------------------------------------------------------------------------------
+    CUtensorMap mA, mB;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)p.K, (cuuint64_t)p.wa, (cuuint64_t)p.ha, (cuuint64_t)p.n};
+        cuuint64_t strides[3] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.wa * p.K * 2, (cuuint64_t)p.ha * p.wa * p.K * 2};
+        cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)(wt * p.as), (cuuint32_t)(ht * p.as), (cuuint32_t)bt};
+        cuuint32_t estr[4] = {1, (cuuint32_t)p.as, (cuuint32_t)p.as, 1};
+        CUresult r = encode(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.A), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return VP_EUNSUPPORTED; }
+    }
+    const int BN = (p.N % 128 == 0) ? 128 : (p.N >= 64 ? 64 : (p.N > 16 ? 32 : 16));
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.N, (cuuint64_t)kMaxTaps};
+        // the tap extent is only an upper bound for the descriptor; taps actually addressed are < the packed count
+        cuuint64_t strides[2] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.N * p.K * 2};
+        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)BN, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if ((strides[1] & 15) != 0) { set_error("tcgen05 engine: weight tap stride not 16-byte aligned"); return VP_EUNSUPPORTED; }
+        CUresult r = encode(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.Wp), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return VP_EUNSUPPORTED; }
+    }
+    tp.D = p.D; tp.bias = p.bias; tp.n = p.n; tp.hd = p.hd; tp.wd = p.wd; tp.N = p.N; tp.gh = p.gh; tp.gw = p.gw;
+    tp.as = p.as; tp.ds = p.ds; tp.doy = p.doy; tp.dox = p.dox; tp.act = p.act; tp.slope = p.slope;
+    tp.out_f32 = (p.out_dtype == VP_F32); tp.kblocks = p.K / kBlockK; tp.taps = p.taps;
+    dim3 grid((unsigned)mtiles, (unsigned)((p.N + BN - 1) / BN));
+    switch (BN) {
+        case 128: return launch_cfg<128, 3>(mA, mB, tp, grid, s);
+        case 64: return launch_cfg<64, 4>(mA, mB, tp, grid, s);
+        case 32: return launch_cfg<32, 4>(mA, mB, tp, grid, s);
+        default: return launch_cfg<16, 4>(mA, mB, tp, grid, s);
+    }
+}
+
+int launch_tapwgrad_tc(const TapWgrad&, cudaStream_t) {
+    set_error("tcgen05 wgrad engine not built yet");
+    return VP_EUNSUPPORTED;
+}
+
 }  // namespace vp
