@@ -428,9 +428,224 @@ int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) {
     }
 }
 
-int launch_tapwgrad_tc(const TapWgrad&, cudaStream_t) {
-    set_error("tcgen05 wgrad engine not built yet");
-    return VP_EUNSUPPORTED;
+// =====================================================================================================
+// wgrad:  dWp[widx_t][gc][ac] += sum_{pixels} G[pix][gc] * A[pix (+) tap_t][ac]
+//
+// GEMM view per tap: D[M=gc, N=ac] = G^T[gc, pix] . A_t[pix, ac], the reduction runs over pixels.  Both operands
+// are read straight from the channels-last tensors, i.e. with the GEMM's M/N index contiguous ("MN-major"):
+// a TMA box of {64 channels, 64 pixels} is 64 rows (K) of 128 B (64 MN elements) with the 128-byte swizzle =
+// the MN-major SW128 canonical layout (K-row stride 128 B inside an 8-row atom, SBO = 1024 B between atoms,
+// LBO = one whole box = 8192 B between 64-channel groups).  One CTA owns (tap, 128-gc tile, BN-ac tile,
+// pixel chunk); pixel chunks (split-K) are combined with fp32 red.global.add into the zeroed dWp.
+// =====================================================================================================
+namespace {
+
+constexpr int kBoxBytes = 64 * 128;  // {64 channels, 64 pixels} bf16
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(kBoxBytes >> 4) << 16;   // LBO: next 64-wide MN group
+    d |= (uint64_t)(1024 >> 4) << 32;        // SBO: next 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int m, int n) {
+    return idesc_bf16_f32(m, n) | (1u << 15) | (1u << 16);   // A and B MN-major
+}
+
+struct TcWgradParams {
+    float* dWp;
+    int GC, AC;
+    int as;
+    int bt, ht, wt;            // pixel brick, bt*ht*wt == 64
+    int tiles_w, tiles_h;
+    int nbricks, bricks_per_split;
+    int mtiles, ntiles;
+    TapList taps;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads) tapwgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG,
+                                                               const __grid_constant__ CUtensorMap mapA,
+                                                               const TcWgradParams p) {
+    constexpr int kGBytes = 2 * kBoxBytes;            // 128 gc
+    constexpr int kAStage = (BN / 64) * kBoxBytes;
+    constexpr int kStage = kGBytes + kAStage;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(smem + STAGES * kStage);
+    uint64_t* empty = full + STAGES;
+    uint64_t* acc_ready = empty + STAGES;
+    uint32_t* tmem_slot = (uint32_t*)(acc_ready + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int id = blockIdx.x;
+    const int nt = id % p.ntiles; id /= p.ntiles;
+    const int mt = id % p.mtiles; id /= p.mtiles;
+    const int tap = id;
+    const int b0 = blockIdx.y * p.bricks_per_split;
+    const int b1 = min(b0 + p.bricks_per_split, p.nbricks);
+    const int iters = b1 - b0;
+    if (iters <= 0) return;
+    const int m0 = mt * 128, c0 = nt * BN;
+    const int ty = p.taps.ty[tap], tx = p.taps.tx[tap];
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapG) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            mbar_init(acc_ready, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                int b = b0 + it;
+                const int tw = b % p.tiles_w; b /= p.tiles_w;
+                const int th = b % p.tiles_h; b /= p.tiles_h;
+                const int n0 = b * p.bt, gy0 = th * p.ht, gx0 = tw * p.wt;
+                uint8_t* sg = smem + s * kStage;
+                uint8_t* sa = sg + kGBytes;
+                mbar_expect_tx(&full[s], kStage);
+                tma_load_4d(sg, &mapG, &full[s], m0, gx0, gy0, n0);
+                tma_load_4d(sg + kBoxBytes, &mapG, &full[s], m0 + 64, gx0, gy0, n0);
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_4d(sa + j * kBoxBytes, &mapA, &full[s], c0 + 64 * j, gx0 * p.as + tx, gy0 * p.as + ty, n0);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = idesc_bf16_f32_mn(128, BN);
+        if (elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sg = smem_u32(smem + s * kStage);
+                const uint64_t adesc = smem_desc_mn_sw128(sg);
+                const uint64_t bdesc = smem_desc_mn_sw128(sg + kGBytes);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // 16 pixels (K rows) = two 8-row atoms = 2048 bytes: +128 in the (addr >> 4) field
+                    tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (it | k) != 0);
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(acc_ready);
+        }
+    } else {
+        const int lane_base = (warp & 3) * 32;
+        const int gc = m0 + lane_base + lane;
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        float* out = p.dWp + ((int64_t)p.taps.widx[tap] * p.GC + gc) * p.AC + c0;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (gc < p.GC) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (c0 + c + j < p.AC) atomicAdd(out + c + j, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    }
+}
+
+template <int BN, int STAGES>
+int launch_wgrad_cfg(const CUtensorMap& mG, const CUtensorMap& mA, const TcWgradParams& tp, dim3 grid, cudaStream_t s) {
+    constexpr int smem_bytes = STAGES * (2 * kBoxBytes + (BN / 64) * kBoxBytes) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tapwgrad_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) { set_error("tapwgrad_tc: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
+        attr_set = true;
+    }
+    tapwgrad_tc_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, s>>>(mG, mA, tp);
+    VP_CHECK_LAUNCH("tapwgrad_tc");
+    return VP_OK;
+}
+
+int encode_nhwc(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bb, int estride) {
+    EncodeTiledFn encode = get_encode();
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(bw * estride), (cuuint32_t)(bh * estride), (cuuint32_t)bb};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+}  // namespace
+
+int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
+    if (!tc_available()) { set_error("tcgen05 engine: needs an sm_100 device and cuTensorMapEncodeTiled"); return VP_EUNSUPPORTED; }
+    if (p.GC % 64 != 0 || p.AC % 64 != 0) { set_error("tcgen05 wgrad: channel counts %d/%d must be multiples of 64", p.GC, p.AC); return VP_EUNSUPPORTED; }
+    if (((uintptr_t)p.G & 15) || ((uintptr_t)p.A & 15) || p.as < 1 || p.as > 8) { set_error("tcgen05 wgrad: alignment/stride"); return VP_EUNSUPPORTED; }
+    const int64_t P = (int64_t)p.n * p.gh * p.gw;
+    if (P <= 0) return VP_OK;
+    TcWgradParams tp;
+    int wt = pow2_floor(p.gw < 64 ? p.gw : 64);
+    if (wt * p.as > 256) wt = pow2_floor(256 / p.as);
+    int ht = pow2_ceil(p.gh);
+    if (ht > 64 / wt) ht = 64 / wt;
+    if (ht * p.as > 256) ht = pow2_floor(256 / p.as);
+    const int bt = 64 / (wt * ht);
+    tp.bt = bt; tp.ht = ht; tp.wt = wt;
+    tp.tiles_w = (p.gw + wt - 1) / wt;
+    tp.tiles_h = (p.gh + ht - 1) / ht;
+    const int64_t nbricks = (int64_t)tp.tiles_w * tp.tiles_h * ((p.n + bt - 1) / bt);
+    if (nbricks > 0x7fffffff) { set_error("tcgen05 wgrad: too many bricks"); return VP_EUNSUPPORTED; }
+    tp.nbricks = (int)nbricks;
+    const int BN = (p.AC % 128 == 0) ? 128 : 64;
+    tp.mtiles = (p.GC + 127) / 128;
+    tp.ntiles = (p.AC + BN - 1) / BN;
+    const int out_tiles = p.taps.ntaps * tp.mtiles * tp.ntiles;
+    // split the pixel reduction so that ~2 waves of CTAs (2 per SM) are in flight, at least 4 bricks per CTA
+    int nsplit = (148 * 4 + out_tiles - 1) / out_tiles;
+    const int max_split = (tp.nbricks + 3) / 4;
+    if (nsplit > max_split) nsplit = max_split;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 65535) nsplit = 65535;
+    tp.bricks_per_split = (tp.nbricks + nsplit - 1) / nsplit;
+    nsplit = (tp.nbricks + tp.bricks_per_split - 1) / tp.bricks_per_split;
+    tp.dWp = p.dWp; tp.GC = p.GC; tp.AC = p.AC; tp.as = p.as; tp.taps = p.taps;
+    CUtensorMap mG, mA;
+    int r = encode_nhwc(&mG, p.G, p.GC, p.gw, p.gh, p.n, wt, ht, bt, 1);
+    if (r) { set_error("tcgen05 wgrad: cuTensorMapEncodeTiled(G) failed (%d)", r); return VP_EUNSUPPORTED; }
+    r = encode_nhwc(&mA, p.A, p.AC, p.wa, p.ha, p.n, wt, ht, bt, p.as);
+    if (r) { set_error("tcgen05 wgrad: cuTensorMapEncodeTiled(A) failed (%d)", r); return VP_EUNSUPPORTED; }
+    dim3 grid((unsigned)out_tiles, (unsigned)nsplit);
+    if (BN == 128) return launch_wgrad_cfg<128, 4>(mG, mA, tp, grid, s);
+    return launch_wgrad_cfg<64, 4>(mG, mA, tp, grid, s);
 }
 
 }  // namespace vp
