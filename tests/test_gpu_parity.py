@@ -515,3 +515,22 @@ def test_tc_engine_matches_simt(vp, kind, cin, cout, hw, b):
             close(npy(dw), npy(dw_ref), 1e-4, f"{kind} wgrad tc-vs-simt")
     finally:
         vp.set_engine("auto")
+
+
+@pytest.mark.parametrize("cin,cout,stride,hw,b", [(1, 64, 2, 64, 3), (64, 1, 1, 32, 3), (3, 64, 2, 32, 2), (64, 3, 1, 16, 2),
+                                                    (1, 64, 2, 20, 2), (64, 1, 1, 10, 5)])
+def test_thin_channel_wgrad(vp, cin, cout, stride, hw, b):
+    """First/last-layer weight gradients (one side has <= 4 channels) use a dedicated streaming kernel."""
+    import vae_play_b200.functional as VF
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    g = torch.Generator(device="cuda").manual_seed(2)
+    layer = VF.TapLayer("conv", cin, cout, k=5, stride=stride, pad=2)
+    w = torch.randn(cout, cin, 5, 5, device="cuda", generator=g) * 0.1
+    x = torch.randn(b, hw, hw, cin, device="cuda", generator=g).to(torch.bfloat16)
+    ho = (hw + 4 - 5) // stride + 1
+    dy = torch.randn(b, ho, ho, cout, device="cuda", generator=g).to(torch.bfloat16)
+    dw = layer.wgrad(x, dy, w)
+    want = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), w.shape, dy.double().permute(0, 3, 1, 2),
+                                       stride=stride, padding=2)
+    close(npy(dw), npy(want), 1e-5, f"thin wgrad {cin}->{cout}")

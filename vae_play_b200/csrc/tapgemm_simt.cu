@@ -1,5 +1,7 @@
 // CUDA-core engine of the tap GEMM: fp32 check mode, and odd shapes (Cin=1/3, Cout=1/3, K % 64 != 0)
 // in bf16 mode.  Classic 64x64x16 shared-memory tiling, 4x4 micro-tile per thread, fp32 accumulate.
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vp {
@@ -181,6 +183,141 @@ __global__ void __launch_bounds__(NT) tapwgrad_simt_kernel(const TapWgrad p, int
     }
 }
 
+// ---- "thin" wgrad: one side of the outer product has <= 4 channels (first layer: x has 1 or 3 channels;
+// last layer: dY has 1 or 3).  The wide side (64.. channels) is streamed once from HBM, one channel per thread;
+// the thin side's halo band is staged in shared memory and read as warp-wide broadcasts.
+//   wide pixel (y,x), tap t  <->  thin pixel (y*s + dir*ty_t, x*s + dir*tx_t)
+//   out[widx_t*so_t + c*so_w + g*so_th] += sum wide[n,y,x,c] * thin[n, ., ., g]
+struct ThinWgrad {
+    const void* wide;   // [n, hw, ww, Cw]
+    const void* thin;   // [n, ht, wt, Ct]
+    float* out;
+    int n, hw, ww, Cw, ht, wt, Ct;
+    int s, dir;
+    int so_t, so_w, so_th;
+    int tymin, tymax, txmin, txmax;   // of dir*ty, dir*tx
+    TapList taps;
+};
+
+constexpr int THIN_ROWS = 4;       // wide rows per band
+constexpr int THIN_MAXT = 25;
+
+template <typename T, int CT>
+__global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWgrad p) {
+    extern __shared__ float sh[];
+    const T* __restrict__ wide = (const T*)p.wide;
+    const T* __restrict__ thin = (const T*)p.thin;
+    const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int rr = threadIdx.x >> 6;                      // 0..3: row inside the band
+    const int nt = p.taps.ntaps;
+    const int band_rows = (THIN_ROWS - 1) * p.s + (p.tymax - p.tymin) + 1;
+    const int band_cols = (p.ww - 1) * p.s + (p.txmax - p.txmin) + 1;
+    const int bands_per_img = (p.hw + THIN_ROWS - 1) / THIN_ROWS;
+    const int nbands = p.n * bands_per_img;
+    float acc[THIN_MAXT][CT];
+#pragma unroll
+    for (int t = 0; t < THIN_MAXT; ++t)
+#pragma unroll
+        for (int g = 0; g < CT; ++g) acc[t][g] = 0.f;
+
+    for (int band = blockIdx.x; band < nbands; band += gridDim.x) {
+        const int img = band / bands_per_img;
+        const int y0 = (band - img * bands_per_img) * THIN_ROWS;
+        __syncthreads();
+        // stage the thin halo band (zero outside the tensor)
+        for (int i = threadIdx.x; i < band_rows * band_cols * CT; i += blockDim.x) {
+            const int g = i % CT;
+            const int col = (i / CT) % band_cols;
+            const int row = i / (CT * band_cols);
+            const int ty = y0 * p.s + p.tymin + row, tx = p.txmin + col;
+            float v = 0.f;
+            if (ty >= 0 && ty < p.ht && tx >= 0 && tx < p.wt)
+                v = Cvt<T>::ld(thin + (((int64_t)img * p.ht + ty) * p.wt + tx) * p.Ct + g);
+            sh[i] = v;
+        }
+        __syncthreads();
+        const int y = y0 + rr;
+        if (y < p.hw && c < p.Cw) {
+            const T* wrow = wide + (((int64_t)img * p.hw + y) * p.ww) * p.Cw + c;
+            for (int x = 0; x < p.ww; ++x) {
+                const float w = Cvt<T>::ld(wrow + (int64_t)x * p.Cw);
+#pragma unroll
+                for (int t = 0; t < THIN_MAXT; ++t) {
+                    if (t < nt) {
+                        const int row = rr * p.s + p.dir * p.taps.ty[t] - p.tymin;
+                        const int col = x * p.s + p.dir * p.taps.tx[t] - p.txmin;
+                        const float* th = sh + (row * band_cols + col) * CT;
+#pragma unroll
+                        for (int g = 0; g < CT; ++g) acc[t][g] = fmaf(w, th[g], acc[t][g]);
+                    }
+                }
+            }
+        }
+    }
+    // combine the 4 row lanes, then one atomic per (tap, channel, thin channel) per block
+    __syncthreads();
+    float* red = sh;  // [4][64] per (t,g) pass
+    for (int t = 0; t < nt; ++t)
+        for (int g = 0; g < CT; ++g) {
+            red[rr * 64 + (threadIdx.x & 63)] = acc[t][g];
+            __syncthreads();
+            if (rr == 0 && c < p.Cw) {
+                const float v = red[threadIdx.x] + red[64 + threadIdx.x] + red[128 + threadIdx.x] + red[192 + threadIdx.x];
+                atomicAdd(p.out + (int64_t)p.taps.widx[t] * p.so_t + (int64_t)c * p.so_w + (int64_t)g * p.so_th, v);
+            }
+            __syncthreads();
+        }
+}
+
+template <typename T>
+int launch_thin(const ThinWgrad& tp, cudaStream_t s) {
+    const int band_rows = (THIN_ROWS - 1) * tp.s + (tp.tymax - tp.tymin) + 1;
+    const int band_cols = (tp.ww - 1) * tp.s + (tp.txmax - tp.txmin) + 1;
+    size_t smem = sizeof(float) * (size_t)band_rows * band_cols * tp.Ct;
+    if (smem < 256 * sizeof(float)) smem = 256 * sizeof(float);
+    if (smem > 48 * 1024) return VP_EUNSUPPORTED;
+    const int nbands = tp.n * ((tp.hw + THIN_ROWS - 1) / THIN_ROWS);
+    dim3 grid((unsigned)(nbands < 148 * 8 ? nbands : 148 * 8), (unsigned)((tp.Cw + 63) / 64));
+    switch (tp.Ct) {
+        case 1: thin_wgrad_kernel<T, 1><<<grid, 256, smem, s>>>(tp); break;
+        case 2: thin_wgrad_kernel<T, 2><<<grid, 256, smem, s>>>(tp); break;
+        case 3: thin_wgrad_kernel<T, 3><<<grid, 256, smem, s>>>(tp); break;
+        default: thin_wgrad_kernel<T, 4><<<grid, 256, smem, s>>>(tp); break;
+    }
+    VP_CHECK_LAUNCH("thin_wgrad");
+    return VP_OK;
+}
+
+// returns VP_EUNSUPPORTED when the problem is not of the thin form
+int try_thin_wgrad(const TapWgrad& p, cudaStream_t s) {
+    if (p.taps.ntaps > THIN_MAXT) return VP_EUNSUPPORTED;
+    ThinWgrad tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.n = p.n; tp.out = p.dWp; tp.taps = p.taps;
+    int dir;
+    if (p.AC <= 4 && p.GC >= 16) {          // first-layer form: wide = G (grid side), thin = A
+        tp.wide = p.G; tp.hw = p.gh; tp.ww = p.gw; tp.Cw = p.GC;
+        tp.thin = p.A; tp.ht = p.ha; tp.wt = p.wa; tp.Ct = p.AC;
+        tp.s = p.as; dir = 1;
+        tp.so_t = p.GC * p.AC; tp.so_w = p.AC; tp.so_th = 1;
+    } else if (p.GC <= 4 && p.AC >= 16 && p.as == 1) {   // last-layer form: wide = A, thin = G
+        tp.wide = p.A; tp.hw = p.ha; tp.ww = p.wa; tp.Cw = p.AC;
+        tp.thin = p.G; tp.ht = p.gh; tp.wt = p.gw; tp.Ct = p.GC;
+        tp.s = 1; dir = -1;
+        tp.so_t = p.GC * p.AC; tp.so_w = 1; tp.so_th = p.AC;
+    } else {
+        return VP_EUNSUPPORTED;
+    }
+    tp.dir = dir;
+    tp.tymin = tp.txmin = 1 << 20; tp.tymax = tp.txmax = -(1 << 20);
+    for (int t = 0; t < p.taps.ntaps; ++t) {
+        const int a = dir * p.taps.ty[t], b = dir * p.taps.tx[t];
+        tp.tymin = a < tp.tymin ? a : tp.tymin; tp.tymax = a > tp.tymax ? a : tp.tymax;
+        tp.txmin = b < tp.txmin ? b : tp.txmin; tp.txmax = b > tp.txmax ? b : tp.txmax;
+    }
+    return launch_thin<bf16>(tp, s);
+}
+
 }  // namespace
 
 int launch_tapgemm_simt(const TapGemm& p, int dtype, cudaStream_t s) {
@@ -198,6 +335,10 @@ int launch_tapgemm_simt(const TapGemm& p, int dtype, cudaStream_t s) {
 int launch_tapwgrad_simt(const TapWgrad& p, int dtype, cudaStream_t s) {
     const int64_t M = (int64_t)p.n * p.gh * p.gw;
     if (M == 0 || p.GC == 0 || p.AC == 0) return VP_OK;
+    if (dtype == VP_BF16) {   // (the fp32 check mode keeps the double-accumulating generic kernel)
+        const int rc = try_thin_wgrad(p, s);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     const int tiles = ((p.GC + BM - 1) / BM) * ((p.AC + BN - 1) / BN) * p.taps.ntaps;
     // split the pixel reduction so that a few waves of CTAs are in flight (148 SMs)
     // fp32 check mode: one double-precision accumulation chain per output (deterministic, single rounding);
