@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import ACT, BF16, F32, VpConvGeom
 
 _STATE = {"precision": "bf16", "engine": _lib.ENGINE_AUTO}
+_EPOCH = [0]       # bumped by invalidate_caches(): forces every packed-weight cache to miss once
 _TRACE = None      # when a list: every fused layer appends its activated output (tests / diagnostics only)
 _GRAD_SINKS = {}   # param.data_ptr() -> (bucket view, param): where wgrad writes directly (vae_play_b200.parallel)
 
@@ -26,6 +27,12 @@ def set_grad_sinks(sinks_by_param_id, params=None):
     """Register flat-bucket slots for parameter gradients (data-parallel training)."""
     _GRAD_SINKS.clear()
     _GRAD_SINKS.update(sinks_by_param_id)
+
+
+def invalidate_caches():
+    """Force re-packing of all weight panels on next use (call before CUDA-graph capture so that the
+    pack kernels are part of the captured step)."""
+    _EPOCH[0] += 1
 
 
 def _grad_target(weight):
@@ -148,7 +155,7 @@ class TapLayer:
         return VpConvGeom(n, hi, wi, ci, ho, wo, co, k, k, stride, pad, transposed)
 
     def _packed(self, weight, which, dtype):
-        key = (which, dtype, weight.data_ptr(), weight._version)
+        key = (which, dtype, weight.data_ptr(), weight._version, _EPOCH[0])
         hit = self._cache.get(which)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -537,6 +544,11 @@ def reparam_kl(mu, logvar=None, eps=None, z_dtype=torch.float32, rng=None):
     return _ReparamKL.apply(mu, logvar, eps, z_dtype, rng)
 
 
+def philox_advance(offset_dev: torch.Tensor, inc: int):
+    """offset_dev (int64[1] on the device) += inc, stream-ordered (advances the Philox position inside a CUDA graph)."""
+    _lib.call("vp_philox_advance", _ptr(offset_dev), int(inc), _stream())
+
+
 def philox_normal(shape, device, rng=None):
     """Drop-in for ``torch.randn(shape, device='cuda')`` / ``Tensor.normal_()`` (same generator stream)."""
     n = int(math.prod(shape))
@@ -635,7 +647,7 @@ class _VaeLoss(torch.autograd.Function):
     """loss = F.mse_loss(x, x_tilde) + sum_b kl_b  (train.py:62-63, VAE terms) in two kernels, fused backward."""
 
     @staticmethod
-    def forward(ctx, x, xt, kl):
+    def forward(ctx, x, xt, kl, mse_scale):
         _require_cuda(xt, "vae_loss")
         x = x.contiguous().float()
         xt = xt.contiguous()
@@ -643,9 +655,12 @@ class _VaeLoss(torch.autograd.Function):
         acc, counter = _loss_scratch(x.device)
         loss = torch.empty(1, dtype=torch.float32, device=x.device)
         _lib.call("vp_recon_loss_fwd", _ptr(x), _ptr(xt), x.numel(), 0, _ptr(acc), _ptr(counter), _ptr(loss), _stream())
+        if mse_scale != 1.0:
+            _lib.call("vp_axpy", float(mse_scale) - 1.0, _ptr(loss), _ptr(loss), 1, _stream())   # loss *= mse_scale
         _lib.call("vp_sum_into", _ptr(kl), kl.numel(), 1.0, _ptr(loss), _stream())
         ctx.save_for_backward(x, xt)
         ctx.nkl = kl.numel()
+        ctx.mse_scale = float(mse_scale)
         return loss.reshape(())
 
     @staticmethod
@@ -654,14 +669,20 @@ class _VaeLoss(torch.autograd.Function):
         g = g.contiguous().float()
         dxt = torch.empty_like(xt)
         dkl = torch.empty(ctx.nkl, dtype=torch.float32, device=xt.device)
-        _lib.call("vp_recon_loss_bwd", _ptr(x), _ptr(xt), x.numel(), 0, _ptr(g), _ptr(dxt), _stream())
+        if ctx.mse_scale != 1.0:
+            gs = torch.empty_like(g)
+            _lib.call("vp_fill_from", _ptr(g), ctx.mse_scale, _ptr(gs), 1, _stream())
+        else:
+            gs = g
+        _lib.call("vp_recon_loss_bwd", _ptr(x), _ptr(xt), x.numel(), 0, _ptr(gs), _ptr(dxt), _stream())
         _lib.call("vp_fill_from", _ptr(g), 1.0, _ptr(dkl), ctx.nkl, _stream())
-        return None, dxt, dkl
+        return None, dxt, dkl, None
 
 
-def vae_loss(x, x_tilde, kl):
-    """F.mse_loss(x, x_tilde) + kl.sum() as one autograd node."""
-    return _VaeLoss.apply(x, x_tilde, kl)
+def vae_loss(x, x_tilde, kl, mse_scale=1.0):
+    """mse_scale * F.mse_loss(x, x_tilde) + kl.sum() as one autograd node (mse_scale = 1/world_size under
+    data parallelism, see vae_play_b200.parallel)."""
+    return _VaeLoss.apply(x, x_tilde, kl, mse_scale)
 
 
 class DualLinear:
@@ -674,7 +695,7 @@ class DualLinear:
         self._cache = {}
 
     def _packed(self, w1, w2, which, dtype):
-        key = (dtype, w1.data_ptr(), w1._version, w2.data_ptr(), w2._version)
+        key = (dtype, w1.data_ptr(), w1._version, w2.data_ptr(), w2._version, _EPOCH[0])
         hit = self._cache.get(which)
         if hit is not None and hit[0] == key:
             return hit[1]
