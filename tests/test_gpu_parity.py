@@ -534,3 +534,30 @@ def test_thin_channel_wgrad(vp, cin, cout, stride, hw, b):
     want = torch.nn.grad.conv2d_weight(x.double().permute(0, 3, 1, 2), w.shape, dy.double().permute(0, 3, 1, 2),
                                        stride=stride, padding=2)
     close(npy(dw), npy(want), 1e-5, f"thin wgrad {cin}->{cout}")
+
+
+@pytest.mark.parametrize("cin,cout,stride,hw,b", [(1, 64, 2, 64, 3), (3, 64, 2, 20, 2), (64, 1, 1, 32, 3), (64, 3, 1, 10, 2)])
+def test_thin_channel_fwd_and_dgrad(vp, cin, cout, stride, hw, b):
+    """First-layer forward (Cin <= 4) and last-layer data gradient (Cout <= 4) use the thin-K streaming kernel."""
+    import torch.nn.functional as F
+    import vae_play_b200.functional as VF
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    layer = VF.TapLayer("conv", cin, cout, k=5, stride=stride, pad=2)
+    w = torch.randn(cout, cin, 5, 5, device="cuda", generator=g) * 0.1
+    wq = w.to(torch.bfloat16).double()
+    x = torch.randn(b, hw, hw, cin, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    if cin <= 4:
+        y = layer.fwd(x, w, bias, out_dtype=torch.float32)
+        want = F.conv2d(x.double().permute(0, 3, 1, 2), wq, bias.double(), stride=stride, padding=2).permute(0, 2, 3, 1)
+        close(npy(y), npy(want), 1e-5, "thin fwd")
+        y16 = layer.fwd(x, w, bias, "relu")
+        close(npy(y16), npy(torch.relu(want)), 6e-3, "thin fwd bf16 relu")
+    else:
+        ho = (hw + 4 - 5) // stride + 1
+        dy = torch.randn(b, ho, ho, cout, device="cuda", generator=g).to(torch.bfloat16)
+        dx = layer.dgrad(dy, w, tuple(x.shape), out_dtype=torch.float32)
+        want = torch.nn.grad.conv2d_input((b, cin, hw, hw), wq, dy.double().permute(0, 3, 1, 2), stride=stride, padding=2)
+        close(npy(dx), npy(want.permute(0, 2, 3, 1)), 1e-5, "thin dgrad")

@@ -7,51 +7,57 @@ namespace vp {
 namespace {
 
 constexpr int NT = 256;
-constexpr int CPB = 64;          // channels per block (16 threads x 4)
-constexpr int RL = NT / (CPB / 4);  // 16 row lanes
-constexpr int ROWS_PER_BLOCK = 256;
+constexpr int V = 8;                 // channels per thread: one 16-byte load of bf16, two of fp32
+constexpr int CPB = 64;              // channels per block (8 threads x 8)
+constexpr int RL = NT / (CPB / V);   // 32 row lanes
+constexpr int ROWS_PER_BLOCK = 512;
 
-template <typename T> __device__ __forceinline__ void ld4(const T* p, int c, int C, float v[4]);
-template <> __device__ __forceinline__ void ld4<float>(const float* p, int c, int C, float v[4]) {
-    if (c + 3 < C && ((C & 3) == 0)) {
-        float4 t = *reinterpret_cast<const float4*>(p + c);
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+template <typename T> __device__ __forceinline__ void ld4(const T* p, int c, int C, float v[V]);
+template <> __device__ __forceinline__ void ld4<float>(const float* p, int c, int C, float v[V]) {
+    if (c + V - 1 < C && ((C & 3) == 0)) {
+        const float4 t0 = *reinterpret_cast<const float4*>(p + c);
+        const float4 t1 = *reinterpret_cast<const float4*>(p + c + 4);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (c + j < C) ? p[c + j] : 0.f;
+        for (int j = 0; j < V; ++j) v[j] = (c + j < C) ? p[c + j] : 0.f;
     }
 }
-template <> __device__ __forceinline__ void ld4<bf16>(const bf16* p, int c, int C, float v[4]) {
-    if (c + 3 < C && ((C & 3) == 0)) {
-        uint2 t = *reinterpret_cast<const uint2*>(p + c);
-        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&t.x);
-        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&t.y);
-        v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+template <> __device__ __forceinline__ void ld4<bf16>(const bf16* p, int c, int C, float v[V]) {
+    if (c + V - 1 < C && ((C & 7) == 0)) {
+        const uint4 t = *reinterpret_cast<const uint4*>(p + c);
+        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            v[2 * j] = __uint_as_float(w[j] << 16);
+            v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+        }
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (c + j < C) ? __bfloat162float(p[c + j]) : 0.f;
+        for (int j = 0; j < V; ++j) v[j] = (c + j < C) ? __bfloat162float(p[c + j]) : 0.f;
     }
 }
-template <typename T> __device__ __forceinline__ void st4(T* p, int c, int C, const float v[4]);
-template <> __device__ __forceinline__ void st4<float>(float* p, int c, int C, const float v[4]) {
-    if (c + 3 < C && ((C & 3) == 0)) {
+template <typename T> __device__ __forceinline__ void st4(T* p, int c, int C, const float v[V]);
+template <> __device__ __forceinline__ void st4<float>(float* p, int c, int C, const float v[V]) {
+    if (c + V - 1 < C && ((C & 3) == 0)) {
         *reinterpret_cast<float4*>(p + c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(p + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (c + j < C) p[c + j] = v[j];
+        for (int j = 0; j < V; ++j) if (c + j < C) p[c + j] = v[j];
     }
 }
-template <> __device__ __forceinline__ void st4<bf16>(bf16* p, int c, int C, const float v[4]) {
-    if (c + 3 < C && ((C & 3) == 0)) {
-        __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]);
-        __nv_bfloat162 b = __floats2bfloat162_rn(v[2], v[3]);
-        uint2 t;
-        t.x = *reinterpret_cast<uint32_t*>(&a);
-        t.y = *reinterpret_cast<uint32_t*>(&b);
-        *reinterpret_cast<uint2*>(p + c) = t;
+template <> __device__ __forceinline__ void st4<bf16>(bf16* p, int c, int C, const float v[V]) {
+    if (c + V - 1 < C && ((C & 7) == 0)) {
+        uint4 t;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+        t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+        t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(p + c) = t;
     } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) if (c + j < C) p[c + j] = __float2bfloat16_rn(v[j]);
+        for (int j = 0; j < V; ++j) if (c + j < C) p[c + j] = __float2bfloat16_rn(v[j]);
     }
 }
 
@@ -60,23 +66,23 @@ template <typename T>
 __global__ void __launch_bounds__(NT) stats_kernel(const T* __restrict__ x, double* __restrict__ sums,
                                                    int64_t groups, int64_t rpg, int C) {
     __shared__ float s1[RL][CPB + 1], s2[RL][CPB + 1];
-    const int cl = (threadIdx.x % (CPB / 4)) * 4;
-    const int rl = threadIdx.x / (CPB / 4);
+    const int cl = (threadIdx.x % (CPB / V)) * V;
+    const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.x * CPB + cl;
     const int64_t g = blockIdx.z;
     const int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK;
     const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
-    float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    float a[V] = {0, 0, 0, 0, 0, 0, 0, 0}, b[V] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < C) {
         for (int64_t r = r0 + rl; r < r1; r += RL) {
-            float v[4];
+            float v[V];
             ld4<T>(x + (g * rpg + r) * C, c, C, v);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { a[j] += v[j]; b[j] = fmaf(v[j], v[j], b[j]); }
+            for (int j = 0; j < V; ++j) { a[j] += v[j]; b[j] = fmaf(v[j], v[j], b[j]); }
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s1[rl][cl + j] = a[j]; s2[rl][cl + j] = b[j]; }
+    for (int j = 0; j < V; ++j) { s1[rl][cl + j] = a[j]; s2[rl][cl + j] = b[j]; }
     __syncthreads();
     if (threadIdx.x < CPB) {
         const int cc = blockIdx.x * CPB + threadIdx.x;
@@ -121,19 +127,19 @@ template <typename T>
 __global__ void __launch_bounds__(NT) apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, T* __restrict__ a,
                                                    int64_t rows, int64_t rpg, int C, int act, float slope) {
-    const int cl = (threadIdx.x % (CPB / 4)) * 4;
-    const int rl = threadIdx.x / (CPB / 4);
+    const int cl = (threadIdx.x % (CPB / V)) * V;
+    const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.y * CPB + cl;
     if (c >= C) return;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
     const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rows);
     for (int64_t r = r0 + rl; r < r1; r += RL) {
         const int64_t g = r / rpg;
-        float v[4], sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0};
+        float v[V], sc[V] = {1, 1, 1, 1, 1, 1, 1, 1}, sh[V] = {0, 0, 0, 0, 0, 0, 0, 0};
         ld4<T>(x + r * C, c, C, v);
         if (scale) { ld4<float>(scale + g * C, c, C, sc); ld4<float>(shift + g * C, c, C, sh); }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+        for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
         st4<T>(a + r * C, c, C, v);
     }
 }
@@ -148,23 +154,23 @@ __global__ void __launch_bounds__(NT) bwd_reduce_kernel(const T* __restrict__ x,
                                                         double* __restrict__ sums, T* __restrict__ dxo,
                                                         int64_t groups, int64_t rpg, int C, int act, float slope) {
     __shared__ float s1[RL][CPB + 1], s2[RL][CPB + 1];
-    const int cl = (threadIdx.x % (CPB / 4)) * 4;
-    const int rl = threadIdx.x / (CPB / 4);
+    const int cl = (threadIdx.x % (CPB / V)) * V;
+    const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.x * CPB + cl;
     const int64_t g = blockIdx.z;
     const int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK;
     const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
-    float a[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};
+    float a[V] = {0, 0, 0, 0, 0, 0, 0, 0}, b[V] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < C) {
-        float sc[4] = {1, 1, 1, 1}, sh[4] = {0, 0, 0, 0}, mu[4] = {0, 0, 0, 0}, is[4] = {0, 0, 0, 0};
+        float sc[V] = {1, 1, 1, 1, 1, 1, 1, 1}, sh[V] = {0, 0, 0, 0, 0, 0, 0, 0}, mu[V] = {0, 0, 0, 0, 0, 0, 0, 0}, is[V] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (scale) { ld4<float>(scale + g * C, c, C, sc); ld4<float>(shift + g * C, c, C, sh); }
         if (mean) { ld4<float>(mean + g * C, c, C, mu); ld4<float>(invstd + g * C, c, C, is); }
         for (int64_t r = r0 + rl; r < r1; r += RL) {
-            float v[4], d[4];
+            float v[V], d[V];
             ld4<T>(x + (g * rpg + r) * C, c, C, v);
             ld4<T>(da + (g * rpg + r) * C, c, C, d);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < V; ++j) {
                 d[j] *= act_grad(fmaf(v[j], sc[j], sh[j]), act, slope);
                 a[j] += d[j];
                 b[j] = fmaf(d[j], (v[j] - mu[j]) * is[j], b[j]);
@@ -173,7 +179,7 @@ __global__ void __launch_bounds__(NT) bwd_reduce_kernel(const T* __restrict__ x,
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { s1[rl][cl + j] = a[j]; s2[rl][cl + j] = b[j]; }
+    for (int j = 0; j < V; ++j) { s1[rl][cl + j] = a[j]; s2[rl][cl + j] = b[j]; }
     __syncthreads();
     if (threadIdx.x < CPB) {
         const int cc = blockIdx.x * CPB + threadIdx.x;
@@ -196,8 +202,8 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
                                                        const double* __restrict__ sums, T* __restrict__ dx,
                                                        float* dgamma, float* dbeta, int64_t groups, int64_t rpg,
                                                        int C, int act, float slope) {
-    const int cl = (threadIdx.x % (CPB / 4)) * 4;
-    const int rl = threadIdx.x / (CPB / 4);
+    const int cl = (threadIdx.x % (CPB / V)) * V;
+    const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.y * CPB + cl;
     if (c >= C) return;
     const int64_t rows = groups * rpg;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
     const float inv_m = 1.f / (float)rpg;
     if (blockIdx.x == 0 && rl == 0 && groups == 1) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < V; ++j)
             if (c + j < C) {
                 if (dbeta) dbeta[c + j] = (float)sums[c + j];
                 if (dgamma) dgamma[c + j] = (float)sums[C + c + j];
@@ -214,20 +220,20 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
     }
     for (int64_t r = r0 + rl; r < r1; r += RL) {
         const int64_t g = r / rpg;
-        float sc[4], sh[4], mu[4], is[4], m1[4], m2[4], v[4], d[4];
+        float sc[V], sh[V], mu[V], is[V], m1[V], m2[V], v[V], d[V];
         ld4<float>(scale + g * C, c, C, sc);
         ld4<float>(shift + g * C, c, C, sh);
         ld4<float>(mean + g * C, c, C, mu);
         ld4<float>(invstd + g * C, c, C, is);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < V; ++j) {
             m1[j] = (c + j < C) ? (float)sums[g * C + c + j] * inv_m : 0.f;
             m2[j] = (c + j < C) ? (float)sums[(groups + g) * C + c + j] * inv_m : 0.f;
         }
         ld4<T>(x + r * C, c, C, v);
         ld4<T>(da + r * C, c, C, d);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < V; ++j) {
             const float dd = d[j] * act_grad(fmaf(v[j], sc[j], sh[j]), act, slope);
             const float xh = (v[j] - mu[j]) * is[j];
             d[j] = sc[j] * (dd - m1[j] - xh * m2[j]);

@@ -269,6 +269,90 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWgrad p) {
         }
 }
 
+// Dense KHxKW window specialisation (the 5x5 layers of models/networks.py): tap (ky,kx) of wide pixel x reads
+// the staged band at row rr*s + ky', column x*s + kx' (ky' = ky for dir=+1, KH-1-ky for dir=-1), so the five
+// row pointers live in registers and the kx offsets are immediates: one LDS (warp broadcast) + one FMA per tap.
+template <typename T, int CT, int DIR, int KH, int KW>
+__global__ void __launch_bounds__(256) thin_wgrad_dense_kernel(const ThinWgrad p) {
+    extern __shared__ float sh[];
+    const T* __restrict__ wide = (const T*)p.wide;
+    const T* __restrict__ thin = (const T*)p.thin;
+    const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+    const int rr = threadIdx.x >> 6;
+    const int band_rows = (THIN_ROWS - 1) * p.s + KH;
+    const int band_cols = (p.ww - 1) * p.s + KW;
+    const int bands_per_img = (p.hw + THIN_ROWS - 1) / THIN_ROWS;
+    const int nbands = p.n * bands_per_img;
+    float acc[KH][KW][CT];
+#pragma unroll
+    for (int a = 0; a < KH; ++a)
+#pragma unroll
+        for (int b = 0; b < KW; ++b)
+#pragma unroll
+            for (int g = 0; g < CT; ++g) acc[a][b][g] = 0.f;
+    const float* rowp[KH];
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky) rowp[ky] = sh + (rr * p.s + (DIR > 0 ? ky : KH - 1 - ky)) * band_cols * CT;
+    const int xstep = p.s * CT;
+
+    for (int band = blockIdx.x; band < nbands; band += gridDim.x) {
+        const int img = band / bands_per_img;
+        const int y0 = (band - img * bands_per_img) * THIN_ROWS;
+        __syncthreads();
+        for (int i = threadIdx.x; i < band_rows * band_cols * CT; i += blockDim.x) {
+            const int g = i % CT;
+            const int col = (i / CT) % band_cols;
+            const int row = i / (CT * band_cols);
+            const int ty = y0 * p.s + p.tymin + row, tx = p.txmin + col;
+            float v = 0.f;
+            if (ty >= 0 && ty < p.ht && tx >= 0 && tx < p.wt)
+                v = Cvt<T>::ld(thin + (((int64_t)img * p.ht + ty) * p.wt + tx) * p.Ct + g);
+            sh[i] = v;
+        }
+        __syncthreads();
+        const int y = y0 + rr;
+        if (y < p.hw && c < p.Cw) {
+            const T* wrow = wide + (((int64_t)img * p.hw + y) * p.ww) * p.Cw + c;
+#pragma unroll 4
+            for (int x = 0; x < p.ww; ++x) {
+                const float w = Cvt<T>::ld(wrow + (int64_t)x * p.Cw);
+#pragma unroll
+                for (int ky = 0; ky < KH; ++ky) {
+                    const float* b = rowp[ky] + x * xstep;
+#pragma unroll
+                    for (int kx = 0; kx < KW; ++kx)
+#pragma unroll
+                        for (int g = 0; g < CT; ++g)
+                            acc[ky][kx][g] = fmaf(w, b[(DIR > 0 ? kx : KW - 1 - kx) * CT + g], acc[ky][kx][g]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    float* red = sh;
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KW; ++kx)
+#pragma unroll
+            for (int g = 0; g < CT; ++g) {
+                red[rr * 64 + (threadIdx.x & 63)] = acc[ky][kx][g];
+                __syncthreads();
+                if (rr == 0 && c < p.Cw) {
+                    const float v = red[threadIdx.x] + red[64 + threadIdx.x] + red[128 + threadIdx.x] + red[192 + threadIdx.x];
+                    atomicAdd(p.out + (int64_t)p.taps.widx[ky * KW + kx] * p.so_t + (int64_t)c * p.so_w + (int64_t)g * p.so_th, v);
+                }
+                __syncthreads();
+            }
+}
+
+bool taps_dense(const TapList& t, int kh, int kw) {
+    if (t.ntaps != kh * kw) return false;
+    for (int i = 0; i < t.ntaps; ++i)
+        if (t.ty[i] != t.ty[0] + i / kw || t.tx[i] != t.tx[0] + i % kw) return false;
+    return true;
+}
+
 template <typename T>
 int launch_thin(const ThinWgrad& tp, cudaStream_t s) {
     const int band_rows = (THIN_ROWS - 1) * tp.s + (tp.tymax - tp.tymin) + 1;
@@ -278,6 +362,14 @@ int launch_thin(const ThinWgrad& tp, cudaStream_t s) {
     if (smem > 48 * 1024) return VP_EUNSUPPORTED;
     const int nbands = tp.n * ((tp.hw + THIN_ROWS - 1) / THIN_ROWS);
     dim3 grid((unsigned)(nbands < 148 * 8 ? nbands : 148 * 8), (unsigned)((tp.Cw + 63) / 64));
+    if (taps_dense(tp.taps, 5, 5) && tp.Ct <= 3) {
+#define VP_THIN_DENSE(CT, DIR) thin_wgrad_dense_kernel<T, CT, DIR, 5, 5><<<grid, 256, smem, s>>>(tp)
+        if (tp.dir > 0) { if (tp.Ct == 1) VP_THIN_DENSE(1, 1); else if (tp.Ct == 2) VP_THIN_DENSE(2, 1); else VP_THIN_DENSE(3, 1); }
+        else { if (tp.Ct == 1) VP_THIN_DENSE(1, -1); else if (tp.Ct == 2) VP_THIN_DENSE(2, -1); else VP_THIN_DENSE(3, -1); }
+#undef VP_THIN_DENSE
+        VP_CHECK_LAUNCH("thin_wgrad_dense");
+        return VP_OK;
+    }
     switch (tp.Ct) {
         case 1: thin_wgrad_kernel<T, 1><<<grid, 256, smem, s>>>(tp); break;
         case 2: thin_wgrad_kernel<T, 2><<<grid, 256, smem, s>>>(tp); break;
@@ -318,11 +410,98 @@ int try_thin_wgrad(const TapWgrad& p, cudaStream_t s) {
     return launch_thin<bf16>(tp, s);
 }
 
+// ---- thin-K tap GEMM: the input has <= 4 channels (first-layer forward, last-layer data gradient) ------
+// One thread = one output pixel x 8 output channels (a 16-byte store); the weights [tap][k][N] sit in shared
+// memory as fp32, the few input scalars per tap are warp-broadcast loads.  Purely store-bound.
+template <typename T, typename TD, int CT>
+__global__ void __launch_bounds__(256) thin_fwd_kernel(const TapGemm p) {
+    extern __shared__ float wsm[];   // [ntaps][CT][N]
+    const T* __restrict__ A = (const T*)p.A;
+    const T* __restrict__ W = (const T*)p.Wp;
+    const int nt = p.taps.ntaps;
+    for (int i = threadIdx.x; i < nt * CT * p.N; i += blockDim.x) {
+        const int n = i % p.N;
+        const int k = (i / p.N) % CT;
+        const int t = i / (p.N * CT);
+        wsm[i] = Cvt<T>::ld(W + ((int64_t)p.taps.widx[t] * p.N + n) * p.K + k);
+    }
+    __syncthreads();
+    const int groups = p.N >> 3;
+    const int64_t total = (int64_t)p.n * p.gh * p.gw * groups;
+    TD* __restrict__ D = (TD*)p.D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g8 = (int)(i % groups) * 8;
+        int64_t m = i / groups;
+        const int gx = (int)(m % p.gw); m /= p.gw;
+        const int gy = (int)(m % p.gh);
+        const int n = (int)(m / p.gh);
+        const int oy = gy * p.ds + p.doy, ox = gx * p.ds + p.dox;
+        if (oy >= p.hd || ox >= p.wd) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = p.bias ? p.bias[g8 + j] : 0.f;
+        for (int t = 0; t < nt; ++t) {
+            const int iy = gy * p.as + p.taps.ty[t], ix = gx * p.as + p.taps.tx[t];
+            if (iy < 0 || iy >= p.ha || ix < 0 || ix >= p.wa) continue;
+            const T* arow = A + (((int64_t)n * p.ha + iy) * p.wa + ix) * p.K;
+#pragma unroll
+            for (int k = 0; k < CT; ++k) {
+                const float a = Cvt<T>::ld(arow + k);
+                const float4 w0 = *reinterpret_cast<const float4*>(wsm + (t * CT + k) * p.N + g8);
+                const float4 w1 = *reinterpret_cast<const float4*>(wsm + (t * CT + k) * p.N + g8 + 4);
+                acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
+                acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+            }
+        }
+        TD* out = D + (((int64_t)n * p.hd + oy) * p.wd + ox) * p.N + g8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = act_fwd(acc[j], p.act, p.slope);
+        if (sizeof(TD) == 2) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(out) = pk;
+        } else {
+            float* o = reinterpret_cast<float*>(out);
+            *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
+    }
+}
+
+int try_thin_fwd(const TapGemm& p, cudaStream_t s) {
+    if (p.K > 4 || p.K < 1 || (p.N & 7) != 0 || p.N > 256 || ((uintptr_t)p.D & 15)) return VP_EUNSUPPORTED;
+    const size_t smem = sizeof(float) * (size_t)p.taps.ntaps * p.K * p.N;
+    if (smem > 48 * 1024 || smem == 0) return VP_EUNSUPPORTED;
+    const int64_t total = (int64_t)p.n * p.gh * p.gw * (p.N >> 3);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    const bool f32 = p.out_dtype == VP_F32;
+#define VP_THIN_FWD(CT)                                                                              \
+    if (f32) thin_fwd_kernel<bf16, float, CT><<<(unsigned)blocks, 256, smem, s>>>(p);                 \
+    else thin_fwd_kernel<bf16, bf16, CT><<<(unsigned)blocks, 256, smem, s>>>(p)
+    switch (p.K) {
+        case 1: VP_THIN_FWD(1); break;
+        case 2: VP_THIN_FWD(2); break;
+        case 3: VP_THIN_FWD(3); break;
+        default: VP_THIN_FWD(4); break;
+    }
+#undef VP_THIN_FWD
+    VP_CHECK_LAUNCH("thin_fwd");
+    return VP_OK;
+}
+
 }  // namespace
 
 int launch_tapgemm_simt(const TapGemm& p, int dtype, cudaStream_t s) {
     const int64_t M = (int64_t)p.n * p.gh * p.gw;
     if (M == 0 || p.N == 0) return VP_OK;
+    if (dtype == VP_BF16) {
+        const int rc = try_thin_fwd(p, s);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((p.N + BN - 1) / BN));
     if (dtype == VP_F32 && p.out_dtype == VP_F32) tapgemm_simt_kernel<float, float><<<grid, NT, 0, s>>>(p);
     else if (dtype == VP_F32) tapgemm_simt_kernel<float, bf16><<<grid, NT, 0, s>>>(p);
