@@ -107,6 +107,10 @@ int conv_like(const VpConvGeom& g, bool gather, const void* A, int ha, int wa, i
         gather_taps(g, p.taps);
         return run_tapgemm(p, dtype, engine, s);
     }
+    // scatter form: s*s output-parity phases; the tcgen05 engine takes up to 4 of them in one persistent launch
+    TapGemm phases[4];
+    int np = 0;
+    const bool batchable = g.stride * g.stride <= 4 && engine != VP_ENGINE_SIMT && dtype == VP_BF16;
     for (int py = 0; py < g.stride; ++py)
         for (int px = 0; px < g.stride; ++px) {
             if (py >= hd || px >= wd) continue;
@@ -114,9 +118,18 @@ int conv_like(const VpConvGeom& g, bool gather, const void* A, int ha, int wa, i
             p.gw = ceil_div(wd - px, g.stride);
             p.as = 1; p.ds = g.stride; p.doy = py; p.dox = px;
             scatter_taps(g, py, px, p.taps);
+            if (batchable) { phases[np++] = p; continue; }
             const int rc = run_tapgemm(p, dtype, engine, s);
             if (rc) return rc;
         }
+    if (batchable && np > 0) {
+        const int rc = launch_tapgemm_tc_multi(phases, np, s);
+        if (rc != VP_EUNSUPPORTED || engine == VP_ENGINE_TC) return rc;
+        for (int i = 0; i < np; ++i) {
+            const int r2 = launch_tapgemm_simt(phases[i], dtype, s);
+            if (r2) return r2;
+        }
+    }
     return VP_OK;
 }
 

@@ -127,6 +127,8 @@ int launch_tapgemm_simt(const TapGemm& p, int dtype, cudaStream_t s);
 int launch_tapwgrad_simt(const TapWgrad& p, int dtype, cudaStream_t s);
 // tcgen05 engine: returns VP_EUNSUPPORTED when the shape is not eligible
 int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s);
+// all output-parity phases of one layer in a single persistent launch (phases share everything but grid/offset/taps)
+int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s);
 int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s);
 bool tc_available();
 

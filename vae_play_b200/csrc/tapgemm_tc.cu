@@ -14,6 +14,9 @@
 // Pipelines: smem full/empty mbarriers between TMA and MMA, one "accumulator ready" mbarrier MMA -> epilogue.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace vp {
@@ -21,7 +24,8 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = 128 bytes = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // wgrad kernel: TMA, MMA, 4 epilogue warps
+constexpr int kFwdThreads = 224;       // fwd/dgrad kernel: + a second TMA producer warp (B operand)
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,19 +136,30 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+constexpr int kMaxPhases = 4;
+
+struct TcPhase {
+    int gh, gw;            // iteration grid of this phase
+    int doy, dox;          // output offset (scatter form)
+    int tiles_w, tiles_h;  // bricks along gx, gy
+    int tile_begin;        // first M-tile index of this phase in the launch-wide tile list
+    TapList taps;
+};
+
 struct TcParams {
     void* D;
     const float* bias;
     int n, hd, wd, N;
-    int gh, gw;
-    int as, ds, doy, dox;
+    int as, ds;
     int act;
     float slope;
     int out_f32;
-    int kblocks;          // K / 64
-    int bt, ht, wt;       // tile brick, bt*ht*wt == 128
-    int tiles_w, tiles_h; // bricks along gx, gy (batch bricks are the remainder of blockIdx.x)
-    TapList taps;
+    int kblocks;           // K / 64
+    int bt, ht, wt;        // tile brick, bt*ht*wt == 128
+    int ntiles_n;          // N tiles
+    int total_tiles;       // sum over phases of M-tiles, times ntiles_n
+    int nphases;
+    TcPhase ph[kMaxPhases];
 };
 
 template <int BN, int STAGES>
@@ -152,33 +167,47 @@ struct SmemLayout {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kBarOffset = STAGES * kStageBytes;
-    static constexpr int kTotal = kBarOffset + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                              const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+struct TileCoord { int phase, n0, gy0, gx0, col0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int q, int BN) {
+    TileCoord c;
+    const int nt = q % p.ntiles_n;
+    int mt = q / p.ntiles_n;
+    int ph = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxPhases; ++i)
+        if (i < p.nphases && mt >= p.ph[i].tile_begin) ph = i;
+    mt -= p.ph[ph].tile_begin;
+    const int tw = mt % p.ph[ph].tiles_w; mt /= p.ph[ph].tiles_w;
+    const int th = mt % p.ph[ph].tiles_h; mt /= p.ph[ph].tiles_h;
+    c.phase = ph; c.n0 = mt * p.bt; c.gy0 = th * p.ht; c.gx0 = tw * p.wt; c.col0 = nt * BN;
+    return c;
+}
+
+// Persistent, warp-specialised tap GEMM: grid = min(#tiles, #SMs); every CTA walks tiles q = blockIdx.x + i*gridDim.x
+// (all output-parity phases of a transposed conv / strided dgrad are in ONE launch).  The smem ring runs across
+// tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i
+// overlaps the TMA/MMA main loop of tile i+1.
+template <int BN, int STAGES, int CTAS_PER_SM>
+__global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ TcParams p) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte alignment of every tile
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SW128 tiles: 1024-byte aligned
     uint64_t* full = (uint64_t*)(smem + L::kBarOffset);
     uint64_t* empty = full + STAGES;
-    uint64_t* acc_ready = empty + STAGES;
-    uint32_t* tmem_slot = (uint32_t*)(acc_ready + 1);
+    uint64_t* acc_full = empty + STAGES;     // [2]
+    uint64_t* acc_empty = acc_full + 2;      // [2]
+    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    constexpr int kTmemCols = BN < 32 ? 32 : BN;
-
-    // tile -> brick origin
-    int tile = blockIdx.x;
-    const int tw = tile % p.tiles_w; tile /= p.tiles_w;
-    const int th = tile % p.tiles_h; tile /= p.tiles_h;
-    const int n0 = tile * p.bt;
-    const int gy0 = th * p.ht, gx0 = tw * p.wt;
-    const int col0 = blockIdx.y * BN;
-    const int iters = p.taps.ntaps * p.kblocks;
+    constexpr int kAccCols = BN < 32 ? 32 : BN;          // columns per accumulator buffer
+    constexpr int kTmemCols = 2 * kAccCols;              // power of two >= 64
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -186,8 +215,9 @@ __global__ void __launch_bounds__(kThreads) tapgemm_tc_kernel(const __grid_const
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-            mbar_init(acc_ready, 1);
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }   // full: A and B producers
+            mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+            mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);      // one arrive per epilogue warp
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -200,110 +230,134 @@ __global__ void __launch_bounds__(kThreads) tapgemm_tc_kernel(const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
-        // ===== TMA producer =====
+    if (warp == 0 || warp == 6) {
+        // ===== TMA producers: warp 0 streams the A bricks, warp 6 the weight panels (two issuing threads) =====
+        const bool is_a = warp == 0;
         if (elect_one()) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                const int t = it / p.kblocks;
-                const int kb = it - t * p.kblocks;
-                uint8_t* sa = smem + s * L::kStageBytes;
-                uint8_t* sb = sa + kABytes;
-                mbar_expect_tx(&full[s], L::kStageBytes);
-                tma_load_4d(sa, &mapA, &full[s], kb * kBlockK, gx0 * p.as + p.taps.tx[t], gy0 * p.as + p.taps.ty[t], n0);
-                tma_load_3d(sb, &mapB, &full[s], kb * kBlockK, col0, p.taps.widx[t]);
+            uint32_t g = 0;   // global k-iteration counter (ring position)
+            for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x) {
+                const TileCoord tc = decode_tile(p, q, BN);
+                const TcPhase& ph = p.ph[tc.phase];
+                const int iters = ph.taps.ntaps * p.kblocks;
+                for (int it = 0; it < iters; ++it, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
+                    const int t = it / p.kblocks;
+                    const int kb = it - t * p.kblocks;
+                    uint8_t* sa = smem + s * L::kStageBytes;
+                    if (is_a) {
+                        mbar_expect_tx(&full[s], kABytes);
+                        tma_load_4d(sa, &mapA, &full[s], kb * kBlockK, tc.gx0 * p.as + ph.taps.tx[t], tc.gy0 * p.as + ph.taps.ty[t], tc.n0);
+                    } else {
+                        mbar_expect_tx(&full[s], L::kBBytes);
+                        tma_load_3d(sa + kABytes, &mapB, &full[s], kb * kBlockK, tc.col0, ph.taps.widx[t]);
+                    }
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         constexpr uint32_t idesc = idesc_bf16_f32(kBlockM, BN < 16 ? 16 : BN);
         if (elect_one()) {
-            for (int it = 0; it < iters; ++it) {
-                const int s = it % STAGES;
-                const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            uint32_t g = 0, i = 0;
+            for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
+                const TileCoord tc = decode_tile(p, q, BN);
+                const int iters = p.ph[tc.phase].taps.ntaps * p.kblocks;
+                const uint32_t buf = i & 1, use = i >> 1;
+                mbar_wait(&acc_empty[buf], (use & 1) ^ 1);          // epilogue has drained this TMEM buffer
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
-                const uint32_t sb = sa + kABytes;
-                const uint64_t adesc = smem_desc_k_sw128(sa);
-                const uint64_t bdesc = smem_desc_k_sw128(sb);
+                const uint32_t tmem_d = tmem_base + buf * kAccCols;
+                for (int it = 0; it < iters; ++it, ++g) {
+                    const int s = g % STAGES;
+                    mbar_wait(&full[s], (g / STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
+                    const uint64_t adesc = smem_desc_k_sw128(sa);
+                    const uint64_t bdesc = smem_desc_k_sw128(sa + kABytes);
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-                    tc_mma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K per UMMA_K=16: +2 in the (addr >> 4) field
+                        tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    tc_commit(&empty[s]);
                 }
-                tc_commit(&empty[s]);          // frees the smem slot when these MMAs have read it
+                tc_commit(&acc_full[buf]);
             }
-            tc_commit(acc_ready);              // accumulator complete
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         // ===== epilogue: warps 2..5; warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
         const int lane_base = (warp & 3) * 32;
         const int r = lane_base + lane;                       // row of the tile = TMEM lane
         const int bw = r % p.wt;
         const int bh = (r / p.wt) % p.ht;
         const int bb = r / (p.wt * p.ht);
-        const int n = n0 + bb, gy = gy0 + bh, gx = gx0 + bw;
-        const int oy = gy * p.ds + p.doy, ox = gx * p.ds + p.dox;
-        const bool row_ok = n < p.n && gy < p.gh && gx < p.gw && oy < p.hd && ox < p.wd;
-        const int64_t row_off = (((int64_t)n * p.hd + oy) * p.wd + ox) * p.N;
-        mbar_wait(acc_ready, 0);
-        tc_fence_after();
-        constexpr int CH = BN >= 32 ? 32 : 16;
+        uint32_t i = 0;
+        for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
+            const TileCoord tc = decode_tile(p, q, BN);
+            const TcPhase& ph = p.ph[tc.phase];
+            const int n = tc.n0 + bb, gy = tc.gy0 + bh, gx = tc.gx0 + bw;
+            const int oy = gy * p.ds + ph.doy, ox = gx * p.ds + ph.dox;
+            const bool row_ok = n < p.n && gy < ph.gh && gx < ph.gw && oy < p.hd && ox < p.wd;
+            const int64_t row_off = (((int64_t)n * p.hd + oy) * p.wd + ox) * p.N;
+            const uint32_t buf = i & 1, use = i >> 1;
+            mbar_wait(&acc_full[buf], use & 1);
+            tc_fence_after();
+            constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += CH) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c;
-            if (CH == 32) tmem_ld32(taddr, v);
-            else tmem_ld16(taddr, v);
-            tmem_ld_wait();
-            if (row_ok) {
-                const int cbase = col0 + c;
-                if (p.out_f32) {
-                    float* out = (float*)p.D + row_off + cbase;
+            for (int c = 0; c < BN; c += CH) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + buf * kAccCols + ((uint32_t)lane_base << 16) + (uint32_t)c;
+                if (CH == 32) tmem_ld32(taddr, v);
+                else tmem_ld16(taddr, v);
+                tmem_ld_wait();
+                if (row_ok) {
+                    const int cbase = tc.col0 + c;
+                    if (p.out_f32) {
+                        float* out = (float*)p.D + row_off + cbase;
 #pragma unroll
-                    for (int j = 0; j < CH; j += 4) {
-                        float f[4];
+                        for (int j = 0; j < CH; j += 4) {
+                            float f[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float x = __uint_as_float(v[j + q]);
-                            if (p.bias && cbase + j + q < p.N) x += p.bias[cbase + j + q];
-                            f[q] = act_fwd(x, p.act, p.slope);
+                            for (int qq = 0; qq < 4; ++qq) {
+                                float x = __uint_as_float(v[j + qq]);
+                                if (p.bias && cbase + j + qq < p.N) x += p.bias[cbase + j + qq];
+                                f[qq] = act_fwd(x, p.act, p.slope);
+                            }
+                            if (cbase + j + 3 < p.N && (p.N & 3) == 0) {
+                                *reinterpret_cast<float4*>(out + j) = make_float4(f[0], f[1], f[2], f[3]);
+                            } else {
+#pragma unroll
+                                for (int qq = 0; qq < 4; ++qq) if (cbase + j + qq < p.N) out[j + qq] = f[qq];
+                            }
                         }
-                        if (cbase + j + 3 < p.N && (p.N & 3) == 0) {
-                            *reinterpret_cast<float4*>(out + j) = make_float4(f[0], f[1], f[2], f[3]);
-                        } else {
+                    } else {
+                        bf16* out = (bf16*)p.D + row_off + cbase;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) if (cbase + j + q < p.N) out[j + q] = f[q];
-                        }
-                    }
-                } else {
-                    bf16* out = (bf16*)p.D + row_off + cbase;
+                        for (int j = 0; j < CH; j += 8) {
+                            float f[8];
 #pragma unroll
-                    for (int j = 0; j < CH; j += 8) {
-                        float f[8];
+                            for (int qq = 0; qq < 8; ++qq) {
+                                float x = __uint_as_float(v[j + qq]);
+                                if (p.bias && cbase + j + qq < p.N) x += p.bias[cbase + j + qq];
+                                f[qq] = act_fwd(x, p.act, p.slope);
+                            }
+                            if (cbase + j + 7 < p.N && (p.N & 7) == 0) {
+                                uint4 pk;
+                                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                                *reinterpret_cast<uint4*>(out + j) = pk;
+                            } else {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            float x = __uint_as_float(v[j + q]);
-                            if (p.bias && cbase + j + q < p.N) x += p.bias[cbase + j + q];
-                            f[q] = act_fwd(x, p.act, p.slope);
-                        }
-                        if (cbase + j + 7 < p.N && (p.N & 7) == 0) {
-                            uint4 pk;
-                            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                            *reinterpret_cast<uint4*>(out + j) = pk;
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q) if (cbase + j + q < p.N) out[j + q] = __float2bfloat16_rn(f[q]);
+                                for (int qq = 0; qq < 8; ++qq) if (cbase + j + qq < p.N) out[j + qq] = __float2bfloat16_rn(f[qq]);
+                            }
                         }
                     }
                 }
             }
+            // this warp's TMEM reads are complete (wait::ld above): hand the buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
         }
     }
     // teardown: everyone is done with TMEM before the allocating warp frees it
@@ -337,19 +391,39 @@ EncodeTiledFn get_encode() {
 int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
-template <int BN, int STAGES>
-int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp, dim3 grid, cudaStream_t s) {
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+template <int BN, int STAGES, int CTAS>
+int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES>;
     constexpr int smem_bytes = L::kTotal + 1024;  // + alignment slack
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) { set_error("tapgemm_tc: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = true;
     }
-    tapgemm_tc_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, s>>>(mA, mB, tp);
+    const int slots = num_sms() * CTAS;
+    const int grid = tp.total_tiles < slots ? tp.total_tiles : slots;
+    tapgemm_tc_kernel<BN, STAGES, CTAS><<<grid, kFwdThreads, smem_bytes, s>>>(mA, mB, tp);
     VP_CHECK_LAUNCH("tapgemm_tc");
     return VP_OK;
+}
+
+// experiment switch (tools/run_layer.py): VP_TC_VARIANT=1 -> one CTA per SM with deep rings and BN=256 tiles
+int tc_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VP_TC_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
 }
 
 }  // namespace
@@ -366,30 +440,49 @@ bool tc_available() {
     return cached == 1;
 }
 
-int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) {
+// All phases share A, Wp, D, K, N, as, ds, bias, act; they differ in (gh, gw, doy, dox, taps).
+int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) {
+    const TapGemm& p = phases[0];
     // ---- eligibility -----------------------------------------------------------------------------------
     if (!tc_available()) { set_error("tcgen05 engine: needs an sm_100 device and cuTensorMapEncodeTiled"); return VP_EUNSUPPORTED; }
-    if (p.K % kBlockK != 0 || p.taps.ntaps < 1 || p.N < 1) { set_error("tcgen05 engine: K=%d must be a multiple of 64", p.K); return VP_EUNSUPPORTED; }
+    if (nphases < 1 || nphases > kMaxPhases) { set_error("tcgen05 engine: %d phases", nphases); return VP_EUNSUPPORTED; }
+    if (p.K % kBlockK != 0 || p.N < 1) { set_error("tcgen05 engine: K=%d must be a multiple of 64", p.K); return VP_EUNSUPPORTED; }
+    for (int i = 0; i < nphases; ++i)
+        if (phases[i].taps.ntaps < 1) { set_error("tcgen05 engine: phase without taps"); return VP_EUNSUPPORTED; }
     if (((uintptr_t)p.A & 15) || ((uintptr_t)p.Wp & 15) || ((uintptr_t)p.D & 15)) { set_error("tcgen05 engine: 16-byte alignment"); return VP_EUNSUPPORTED; }
     if (p.as < 1 || p.as > 8) { set_error("tcgen05 engine: gather stride %d", p.as); return VP_EUNSUPPORTED; }
-    const int64_t M = (int64_t)p.n * p.gh * p.gw;
-    if (M <= 0) return VP_OK;
+    if (p.n <= 0) return VP_OK;
     EncodeTiledFn encode = get_encode();
 
-    // ---- tile brick ------------------------------------------------------------------------------------
+    // ---- tile brick (from the largest phase grid) ----------------------------------------------------------
+    int gh = 0, gw = 0;
+    for (int i = 0; i < nphases; ++i) { gh = phases[i].gh > gh ? phases[i].gh : gh; gw = phases[i].gw > gw ? phases[i].gw : gw; }
+    if (gh <= 0 || gw <= 0) return VP_OK;
     TcParams tp;
-    int wt = pow2_floor(p.gw < kBlockM ? p.gw : kBlockM);
+    memset(&tp, 0, sizeof(tp));
+    int wt = pow2_floor(gw < kBlockM ? gw : kBlockM);
     if (wt * p.as > 256) wt = pow2_floor(256 / p.as);
-    int ht = pow2_ceil(p.gh);
+    int ht = pow2_ceil(gh);
     if (ht > kBlockM / wt) ht = kBlockM / wt;
     if (ht * p.as > 256) ht = pow2_floor(256 / p.as);
-    int bt = kBlockM / (wt * ht);
+    const int bt = kBlockM / (wt * ht);
     tp.bt = bt; tp.ht = ht; tp.wt = wt;
-    tp.tiles_w = (p.gw + wt - 1) / wt;
-    tp.tiles_h = (p.gh + ht - 1) / ht;
     const int tiles_b = (p.n + bt - 1) / bt;
-    const int64_t mtiles = (int64_t)tp.tiles_w * tp.tiles_h * tiles_b;
-    if (mtiles > 0x7fffffff) { set_error("tcgen05 engine: too many tiles"); return VP_EUNSUPPORTED; }
+    const bool one_cta = tc_variant() == 1;
+    const int BN = (one_cta && p.N % 256 == 0) ? 256 : (p.N % 128 == 0) ? 128 : (p.N >= 64 ? 64 : (p.N > 16 ? 32 : 16));
+    tp.ntiles_n = (p.N + BN - 1) / BN;
+    int64_t mtiles = 0;
+    for (int i = 0; i < nphases; ++i) {
+        TcPhase& ph = tp.ph[i];
+        ph.gh = phases[i].gh; ph.gw = phases[i].gw; ph.doy = phases[i].doy; ph.dox = phases[i].dox; ph.taps = phases[i].taps;
+        ph.tiles_w = (ph.gw + wt - 1) / wt;
+        ph.tiles_h = (ph.gh + ht - 1) / ht;
+        ph.tile_begin = (int)mtiles;
+        mtiles += (int64_t)ph.tiles_w * ph.tiles_h * tiles_b;
+    }
+    if (mtiles * tp.ntiles_n > 0x7fffffff) { set_error("tcgen05 engine: too many tiles"); return VP_EUNSUPPORTED; }
+    tp.total_tiles = (int)(mtiles * tp.ntiles_n);
+    tp.nphases = nphases;
 
     // ---- tensor maps -----------------------------------------------------------------------------------
     CUtensorMap mA, mB;
@@ -403,10 +496,9 @@ int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return VP_EUNSUPPORTED; }
     }
-    const int BN = (p.N % 128 == 0) ? 128 : (p.N >= 64 ? 64 : (p.N > 16 ? 32 : 16));
     {
-        cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.N, (cuuint64_t)kMaxTaps};
         // the tap extent is only an upper bound for the descriptor; taps actually addressed are < the packed count
+        cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.N, (cuuint64_t)kMaxTaps};
         cuuint64_t strides[2] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.N * p.K * 2};
         cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)BN, 1};
         cuuint32_t estr[3] = {1, 1, 1};
@@ -416,17 +508,29 @@ int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) {
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return VP_EUNSUPPORTED; }
     }
-    tp.D = p.D; tp.bias = p.bias; tp.n = p.n; tp.hd = p.hd; tp.wd = p.wd; tp.N = p.N; tp.gh = p.gh; tp.gw = p.gw;
-    tp.as = p.as; tp.ds = p.ds; tp.doy = p.doy; tp.dox = p.dox; tp.act = p.act; tp.slope = p.slope;
-    tp.out_f32 = (p.out_dtype == VP_F32); tp.kblocks = p.K / kBlockK; tp.taps = p.taps;
-    dim3 grid((unsigned)mtiles, (unsigned)((p.N + BN - 1) / BN));
+    tp.D = p.D; tp.bias = p.bias; tp.n = p.n; tp.hd = p.hd; tp.wd = p.wd; tp.N = p.N;
+    tp.as = p.as; tp.ds = p.ds; tp.act = p.act; tp.slope = p.slope;
+    tp.out_f32 = (p.out_dtype == VP_F32); tp.kblocks = p.K / kBlockK;
+    if (one_cta) {
+        switch (BN) {
+            case 256: return launch_cfg<256, 4, 1>(mA, mB, tp, s);
+            case 128: return launch_cfg<128, 6, 1>(mA, mB, tp, s);
+            case 64: return launch_cfg<64, 8, 1>(mA, mB, tp, s);
+            case 32: return launch_cfg<32, 8, 1>(mA, mB, tp, s);
+            default: return launch_cfg<16, 8, 1>(mA, mB, tp, s);
+        }
+    }
+    // default: two persistent CTAs per SM (two TMA issue streams, two epilogues in flight), <= 113 KB smem and
+    // <= 256 TMEM columns each
     switch (BN) {
-        case 128: return launch_cfg<128, 3>(mA, mB, tp, grid, s);
-        case 64: return launch_cfg<64, 4>(mA, mB, tp, grid, s);
-        case 32: return launch_cfg<32, 4>(mA, mB, tp, grid, s);
-        default: return launch_cfg<16, 4>(mA, mB, tp, grid, s);
+        case 128: return launch_cfg<128, 3, 2>(mA, mB, tp, s);
+        case 64: return launch_cfg<64, 4, 2>(mA, mB, tp, s);
+        case 32: return launch_cfg<32, 5, 2>(mA, mB, tp, s);
+        default: return launch_cfg<16, 5, 2>(mA, mB, tp, s);
     }
 }
+
+int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) { return launch_tapgemm_tc_multi(&p, 1, s); }
 
 // =====================================================================================================
 // wgrad:  dWp[widx_t][gc][ac] += sum_{pixels} G[pix][gc] * A[pix (+) tap_t][ac]
