@@ -12,84 +12,119 @@ constexpr int CPB = 64;              // channels per block (8 threads x 8)
 constexpr int RL = NT / (CPB / V);   // 32 row lanes
 constexpr int ROWS_PER_BLOCK = 512;
 
-template <typename T> __device__ __forceinline__ void ld4(const T* p, int c, int C, float v[V]);
-template <> __device__ __forceinline__ void ld4<float>(const float* p, int c, int C, float v[V]) {
-    if (c + V - 1 < C && ((C & 3) == 0)) {
-        const float4 t0 = *reinterpret_cast<const float4*>(p + c);
-        const float4 t1 = *reinterpret_cast<const float4*>(p + c + 4);
-        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
-    } else {
+template <typename T, int VV> struct Vec;
+template <int VV> struct Vec<float, VV> {
+    static __device__ __forceinline__ void ld(const float* p, int c, int C, float* v) {
+        if (c + VV - 1 < C && ((C & 3) == 0)) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = (c + j < C) ? p[c + j] : 0.f;
-    }
-}
-template <> __device__ __forceinline__ void ld4<bf16>(const bf16* p, int c, int C, float v[V]) {
-    if (c + V - 1 < C && ((C & 7) == 0)) {
-        const uint4 t = *reinterpret_cast<const uint4*>(p + c);
-        const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+            for (int q = 0; q < VV / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(p + c + 4 * q);
+                v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            }
+        } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            v[2 * j] = __uint_as_float(w[j] << 16);
-            v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+            for (int j = 0; j < VV; ++j) v[j] = (c + j < C) ? p[c + j] : 0.f;
         }
-    } else {
-#pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = (c + j < C) ? __bfloat162float(p[c + j]) : 0.f;
     }
-}
-template <typename T> __device__ __forceinline__ void st4(T* p, int c, int C, const float v[V]);
-template <> __device__ __forceinline__ void st4<float>(float* p, int c, int C, const float v[V]) {
-    if (c + V - 1 < C && ((C & 3) == 0)) {
-        *reinterpret_cast<float4*>(p + c) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(p + c + 4) = make_float4(v[4], v[5], v[6], v[7]);
-    } else {
+    static __device__ __forceinline__ void st(float* p, int c, int C, const float* v) {
+        if (c + VV - 1 < C && ((C & 3) == 0)) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) if (c + j < C) p[c + j] = v[j];
-    }
-}
-template <> __device__ __forceinline__ void st4<bf16>(bf16* p, int c, int C, const float v[V]) {
-    if (c + V - 1 < C && ((C & 7) == 0)) {
-        uint4 t;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
-        t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
-        t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(p + c) = t;
-    } else {
+            for (int q = 0; q < VV / 4; ++q)
+                *reinterpret_cast<float4*>(p + c + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) if (c + j < C) p[c + j] = __float2bfloat16_rn(v[j]);
+            for (int j = 0; j < VV; ++j) if (c + j < C) p[c + j] = v[j];
+        }
     }
-}
+};
+template <int VV> struct Vec<bf16, VV> {
+    static __device__ __forceinline__ void ld(const bf16* p, int c, int C, float* v) {
+        if (c + VV - 1 < C && ((C & (VV - 1)) == 0)) {
+            uint32_t w[VV / 2];
+            if (VV == 8) {
+                const uint4 t = *reinterpret_cast<const uint4*>(p + c);
+                w[0] = t.x; w[1] = t.y; w[VV / 2 - 2] = t.z; w[VV / 2 - 1] = t.w;
+            } else {
+                const uint2 t = *reinterpret_cast<const uint2*>(p + c);
+                w[0] = t.x; w[1] = t.y;
+            }
+#pragma unroll
+            for (int j = 0; j < VV / 2; ++j) {
+                v[2 * j] = __uint_as_float(w[j] << 16);
+                v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < VV; ++j) v[j] = (c + j < C) ? __bfloat162float(p[c + j]) : 0.f;
+        }
+    }
+    static __device__ __forceinline__ void st(bf16* p, int c, int C, const float* v) {
+        if (c + VV - 1 < C && ((C & (VV - 1)) == 0)) {
+            uint32_t w[VV / 2];
+#pragma unroll
+            for (int j = 0; j < VV / 2; ++j) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            if (VV == 8) *reinterpret_cast<uint4*>(p + c) = make_uint4(w[0], w[1], w[VV / 2 - 2], w[VV / 2 - 1]);
+            else *reinterpret_cast<uint2*>(p + c) = make_uint2(w[0], w[1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < VV; ++j) if (c + j < C) p[c + j] = __float2bfloat16_rn(v[j]);
+        }
+    }
+};
+template <typename T> __device__ __forceinline__ void ld4(const T* p, int c, int C, float* v) { Vec<T, V>::ld(p, c, C, v); }
+template <typename T> __device__ __forceinline__ void st4(T* p, int c, int C, const float* v) { Vec<T, V>::st(p, c, C, v); }
+
+constexpr int UNR = 4;   // rows in flight per thread (16-byte loads issued back to back before use)
+
+// Reduction kernels use 4 channels per thread (8-byte bf16 loads) to stay at <= 64 registers: four 256-thread
+// blocks per SM with 4 rows in flight per thread keeps ~64 KB of loads outstanding per SM.
+constexpr int VR = 4;
 
 // grid: (channel tiles, row slabs per group, groups)
 template <typename T>
-__global__ void __launch_bounds__(NT) stats_kernel(const T* __restrict__ x, double* __restrict__ sums,
-                                                   int64_t groups, int64_t rpg, int C) {
-    __shared__ float s1[RL][CPB + 1], s2[RL][CPB + 1];
-    const int cl = (threadIdx.x % (CPB / V)) * V;
-    const int rl = threadIdx.x / (CPB / V);
-    const int c = blockIdx.x * CPB + cl;
+__global__ void __launch_bounds__(NT, 4) stats_kernel(const T* __restrict__ x, double* __restrict__ sums,
+                                                      int64_t groups, int64_t rpg, int C, int tpr) {
+    // tpr = threads per row (power of two <= 16): narrow tensors (C = 1, 3, ...) put more threads on the row axis
+    __shared__ float s1[NT * VR], s2[NT * VR];
+    const int cpb = tpr * VR;            // channels per block
+    const int rlanes = NT / tpr;         // row lanes
+    const int cl = (threadIdx.x % tpr) * VR;
+    const int rl = threadIdx.x / tpr;
+    const int c = blockIdx.x * cpb + cl;
     const int64_t g = blockIdx.z;
-    const int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK;
-    const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
-    float a[V] = {0, 0, 0, 0, 0, 0, 0, 0}, b[V] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (c < C) {
-        for (int64_t r = r0 + rl; r < r1; r += RL) {
-            float v[V];
-            ld4<T>(x + (g * rpg + r) * C, c, C, v);
+    float a[VR] = {0, 0, 0, 0}, b[VR] = {0, 0, 0, 0};
+    // each block walks several row slabs: few blocks => few same-address double atomics at the end
+    for (int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK; r0 < rpg && c < C; r0 += (int64_t)gridDim.y * ROWS_PER_BLOCK) {
+        const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
+        const T* base = x + g * rpg * C;
+        for (int64_t r = r0 + rl; r < r1; r += (int64_t)rlanes * UNR) {
+            float v[UNR][VR];
 #pragma unroll
-            for (int j = 0; j < V; ++j) { a[j] += v[j]; b[j] = fmaf(v[j], v[j], b[j]); }
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t rr = r + (int64_t)u * rlanes;
+                if (rr < r1) Vec<T, VR>::ld(base + rr * C, c, C, v[u]);
+                else {
+#pragma unroll
+                    for (int j = 0; j < VR; ++j) v[u][j] = 0.f;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < UNR; ++u)
+#pragma unroll
+                for (int j = 0; j < VR; ++j) { a[j] += v[u][j]; b[j] = fmaf(v[u][j], v[u][j], b[j]); }
         }
     }
 #pragma unroll
-    for (int j = 0; j < V; ++j) { s1[rl][cl + j] = a[j]; s2[rl][cl + j] = b[j]; }
+    for (int j = 0; j < VR; ++j) { s1[rl * cpb + cl + j] = a[j]; s2[rl * cpb + cl + j] = b[j]; }
     __syncthreads();
-    if (threadIdx.x < CPB) {
-        const int cc = blockIdx.x * CPB + threadIdx.x;
+    if ((int)threadIdx.x < cpb) {
+        const int cc = blockIdx.x * cpb + threadIdx.x;
         if (cc < C) {
             double t1 = 0, t2 = 0;
-#pragma unroll
-            for (int i = 0; i < RL; ++i) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+            for (int i = 0; i < rlanes; ++i) { t1 += s1[i * cpb + threadIdx.x]; t2 += s2[i * cpb + threadIdx.x]; }
             atomicAdd(sums + g * C + cc, t1);
             atomicAdd(sums + (groups + g) * C + cc, t2);
         }
@@ -122,77 +157,104 @@ __global__ void finalize_kernel(const double* __restrict__ sums, const float* __
     }
 }
 
-// grid: (row slabs over all rows, channel tiles)
+// grid: (row slabs per group, channel tiles, groups): per-channel parameters are loaded once per thread
 template <typename T>
 __global__ void __launch_bounds__(NT) apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, T* __restrict__ a,
-                                                   int64_t rows, int64_t rpg, int C, int act, float slope) {
+                                                   int64_t rpg, int C, int act, float slope) {
     const int cl = (threadIdx.x % (CPB / V)) * V;
     const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.y * CPB + cl;
     if (c >= C) return;
+    const int64_t g = blockIdx.z;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
-    const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rows);
-    for (int64_t r = r0 + rl; r < r1; r += RL) {
-        const int64_t g = r / rpg;
-        float v[V], sc[V] = {1, 1, 1, 1, 1, 1, 1, 1}, sh[V] = {0, 0, 0, 0, 0, 0, 0, 0};
-        ld4<T>(x + r * C, c, C, v);
-        if (scale) { ld4<float>(scale + g * C, c, C, sc); ld4<float>(shift + g * C, c, C, sh); }
+    const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
+    float sc[V] = {1, 1, 1, 1, 1, 1, 1, 1}, sh[V] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (scale) { ld4<float>(scale + g * C, c, C, sc); ld4<float>(shift + g * C, c, C, sh); }
+    const T* xb = x + g * rpg * C;
+    T* ab = a + g * rpg * C;
+    for (int64_t r = r0 + rl; r < r1; r += RL * UNR) {
+        float v[UNR][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
-        st4<T>(a + r * C, c, C, v);
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t rr = r + (int64_t)u * RL;
+            if (rr < r1) ld4<T>(xb + rr * C, c, C, v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int64_t rr = r + (int64_t)u * RL;
+            if (rr < r1) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) v[u][j] = act_fwd(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+                st4<T>(ab + rr * C, c, C, v[u]);
+            }
+        }
     }
 }
 
 // pass 1 of backward: d = da*act'(pre), sums of d and d*xhat.  grid like stats_kernel.
 template <typename T>
-__global__ void __launch_bounds__(NT) bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ da,
-                                                        const float* __restrict__ mean,
-                                                        const float* __restrict__ invstd,
-                                                        const float* __restrict__ scale,
-                                                        const float* __restrict__ shift,
-                                                        double* __restrict__ sums, T* __restrict__ dxo,
-                                                        int64_t groups, int64_t rpg, int C, int act, float slope) {
-    __shared__ float s1[RL][CPB + 1], s2[RL][CPB + 1];
-    const int cl = (threadIdx.x % (CPB / V)) * V;
-    const int rl = threadIdx.x / (CPB / V);
-    const int c = blockIdx.x * CPB + cl;
+__global__ void __launch_bounds__(NT, 3) bwd_reduce_kernel(const T* __restrict__ x, const T* __restrict__ da,
+                                                           const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           double* __restrict__ sums, T* __restrict__ dxo,
+                                                           int64_t groups, int64_t rpg, int C, int act, float slope, int tpr) {
+    __shared__ float s1[NT * VR], s2[NT * VR];
+    const int cpb = tpr * VR;
+    const int rlanes = NT / tpr;
+    const int cl = (threadIdx.x % tpr) * VR;
+    const int rl = threadIdx.x / tpr;
+    const int c = blockIdx.x * cpb + cl;
     const int64_t g = blockIdx.z;
-    const int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK;
-    const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
-    float a[V] = {0, 0, 0, 0, 0, 0, 0, 0}, b[V] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float a[VR] = {0, 0, 0, 0}, b[VR] = {0, 0, 0, 0};
+    float sc[VR] = {1, 1, 1, 1}, sh[VR] = {0, 0, 0, 0}, mu[VR] = {0, 0, 0, 0}, is[VR] = {0, 0, 0, 0};
     if (c < C) {
-        float sc[V] = {1, 1, 1, 1, 1, 1, 1, 1}, sh[V] = {0, 0, 0, 0, 0, 0, 0, 0}, mu[V] = {0, 0, 0, 0, 0, 0, 0, 0}, is[V] = {0, 0, 0, 0, 0, 0, 0, 0};
-        if (scale) { ld4<float>(scale + g * C, c, C, sc); ld4<float>(shift + g * C, c, C, sh); }
-        if (mean) { ld4<float>(mean + g * C, c, C, mu); ld4<float>(invstd + g * C, c, C, is); }
-        for (int64_t r = r0 + rl; r < r1; r += RL) {
-            float v[V], d[V];
-            ld4<T>(x + (g * rpg + r) * C, c, C, v);
-            ld4<T>(da + (g * rpg + r) * C, c, C, d);
+        if (scale) { Vec<float, VR>::ld(scale + g * C, c, C, sc); Vec<float, VR>::ld(shift + g * C, c, C, sh); }
+        if (mean) { Vec<float, VR>::ld(mean + g * C, c, C, mu); Vec<float, VR>::ld(invstd + g * C, c, C, is); }
+    }
+    for (int64_t r0 = (int64_t)blockIdx.y * ROWS_PER_BLOCK; r0 < rpg && c < C; r0 += (int64_t)gridDim.y * ROWS_PER_BLOCK) {
+        const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
+        const T* xb = x + g * rpg * C;
+        const T* db = da + g * rpg * C;
+        for (int64_t r = r0 + rl; r < r1; r += (int64_t)rlanes * UNR) {
+            float v[UNR][VR], d[UNR][VR];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                d[j] *= act_grad(fmaf(v[j], sc[j], sh[j]), act, slope);
-                a[j] += d[j];
-                b[j] = fmaf(d[j], (v[j] - mu[j]) * is[j], b[j]);
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t rr = r + (int64_t)u * rlanes;
+                if (rr < r1) { Vec<T, VR>::ld(xb + rr * C, c, C, v[u]); Vec<T, VR>::ld(db + rr * C, c, C, d[u]); }
             }
-            if (dxo) st4<T>(dxo + (g * rpg + r) * C, c, C, d);
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+                const int64_t rr = r + (int64_t)u * rlanes;
+                if (rr < r1) {
+#pragma unroll
+                    for (int j = 0; j < VR; ++j) {
+                        d[u][j] *= act_grad(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+                        a[j] += d[u][j];
+                        b[j] = fmaf(d[u][j], (v[u][j] - mu[j]) * is[j], b[j]);
+                    }
+                    if (dxo) Vec<T, VR>::st(dxo + (g * rpg + rr) * C, c, C, d[u]);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int j = 0; j < V; ++j) { s1[rl][cl + j] = a[j]; s2[rl][cl + j] = b[j]; }
+    for (int j = 0; j < VR; ++j) { s1[rl * cpb + cl + j] = a[j]; s2[rl * cpb + cl + j] = b[j]; }
     __syncthreads();
-    if (threadIdx.x < CPB) {
-        const int cc = blockIdx.x * CPB + threadIdx.x;
+    if ((int)threadIdx.x < cpb) {
+        const int cc = blockIdx.x * cpb + threadIdx.x;
         if (cc < C) {
             double t1 = 0, t2 = 0;
-#pragma unroll
-            for (int i = 0; i < RL; ++i) { t1 += s1[i][threadIdx.x]; t2 += s2[i][threadIdx.x]; }
+            for (int i = 0; i < rlanes; ++i) { t1 += s1[i * cpb + threadIdx.x]; t2 += s2[i * cpb + threadIdx.x]; }
             atomicAdd(sums + g * C + cc, t1);
             if (mean) atomicAdd(sums + (groups + g) * C + cc, t2);
         }
     }
 }
 
+// pass 2: grid (row slabs per group, channel tiles, groups)
 template <typename T>
 __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ da,
                                                        const float* __restrict__ mean,
@@ -206,10 +268,20 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
     const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.y * CPB + cl;
     if (c >= C) return;
-    const int64_t rows = groups * rpg;
+    const int64_t g = blockIdx.z;
     const int64_t r0 = (int64_t)blockIdx.x * ROWS_PER_BLOCK;
-    const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rows);
+    const int64_t r1 = min(r0 + ROWS_PER_BLOCK, rpg);
     const float inv_m = 1.f / (float)rpg;
+    float sc[V], sh[V], mu[V], is[V], m1[V], m2[V];
+    ld4<float>(scale + g * C, c, C, sc);
+    ld4<float>(shift + g * C, c, C, sh);
+    ld4<float>(mean + g * C, c, C, mu);
+    ld4<float>(invstd + g * C, c, C, is);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        m1[j] = (c + j < C) ? (float)sums[g * C + c + j] * inv_m : 0.f;
+        m2[j] = (c + j < C) ? (float)sums[(groups + g) * C + c + j] * inv_m : 0.f;
+    }
     if (blockIdx.x == 0 && rl == 0 && groups == 1) {
 #pragma unroll
         for (int j = 0; j < V; ++j)
@@ -218,27 +290,29 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
                 if (dgamma) dgamma[c + j] = (float)sums[C + c + j];
             }
     }
-    for (int64_t r = r0 + rl; r < r1; r += RL) {
-        const int64_t g = r / rpg;
-        float sc[V], sh[V], mu[V], is[V], m1[V], m2[V], v[V], d[V];
-        ld4<float>(scale + g * C, c, C, sc);
-        ld4<float>(shift + g * C, c, C, sh);
-        ld4<float>(mean + g * C, c, C, mu);
-        ld4<float>(invstd + g * C, c, C, is);
+    const T* xb = x + g * rpg * C;
+    const T* db = da + g * rpg * C;
+    T* ob = dx + g * rpg * C;
+    for (int64_t r = r0 + rl; r < r1; r += RL * (UNR / 2)) {
+        float v[UNR / 2][V], d[UNR / 2][V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            m1[j] = (c + j < C) ? (float)sums[g * C + c + j] * inv_m : 0.f;
-            m2[j] = (c + j < C) ? (float)sums[(groups + g) * C + c + j] * inv_m : 0.f;
+        for (int u = 0; u < UNR / 2; ++u) {
+            const int64_t rr = r + (int64_t)u * RL;
+            if (rr < r1) { ld4<T>(xb + rr * C, c, C, v[u]); ld4<T>(db + rr * C, c, C, d[u]); }
         }
-        ld4<T>(x + r * C, c, C, v);
-        ld4<T>(da + r * C, c, C, d);
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const float dd = d[j] * act_grad(fmaf(v[j], sc[j], sh[j]), act, slope);
-            const float xh = (v[j] - mu[j]) * is[j];
-            d[j] = sc[j] * (dd - m1[j] - xh * m2[j]);
+        for (int u = 0; u < UNR / 2; ++u) {
+            const int64_t rr = r + (int64_t)u * RL;
+            if (rr < r1) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float dd = d[u][j] * act_grad(fmaf(v[u][j], sc[j], sh[j]), act, slope);
+                    const float xh = (v[u][j] - mu[j]) * is[j];
+                    d[u][j] = sc[j] * (dd - m1[j] - xh * m2[j]);
+                }
+                st4<T>(ob + rr * C, c, C, d[u]);
+            }
         }
-        st4<T>(dx + r * C, c, C, d);
     }
 }
 
@@ -252,14 +326,31 @@ __global__ void colsum_finish_kernel(const double* __restrict__ s, float* __rest
 
 using namespace vp;
 
+// threads per row of the reduction kernels: enough 4-channel threads to cover C, at most 16 (64 channels per block)
+static int threads_per_row(int c) {
+    int t = 1;
+    while (t < 16 && t * VR < c) t *= 2;
+    return t;
+}
+
+// number of row-slab blocks of the reduction kernels: about 4 CTAs per SM in total
+static unsigned slab_blocks(int64_t rpg, int ctiles, int64_t groups) {
+    const int64_t slabs = (rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+    int64_t cap = (148 * 4) / ((int64_t)ctiles * groups);
+    if (cap < 1) cap = 1;
+    return (unsigned)(slabs < cap ? slabs : cap);
+}
+
 extern "C" int vp_norm_stats(const void* x, double* sums, int dtype, int64_t groups, int64_t rpg, int c,
                              void* stream) {
     VP_CHECK_ARG(x && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_stats: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_stats: too many groups");
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
-    dim3 grid((c + CPB - 1) / CPB, (unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (unsigned)groups);
-    if (dtype == VP_F32) stats_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, sums, groups, rpg, c);
-    else stats_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, sums, groups, rpg, c);
+    const int tpr = threads_per_row(c);
+    const int ctiles = (c + tpr * VR - 1) / (tpr * VR);
+    dim3 grid(ctiles, slab_blocks(rpg, ctiles, groups), (unsigned)groups);
+    if (dtype == VP_F32) stats_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, sums, groups, rpg, c, tpr);
+    else stats_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, sums, groups, rpg, c, tpr);
     VP_CHECK_LAUNCH("vp_norm_stats");
     return VP_OK;
 }
@@ -279,12 +370,12 @@ extern "C" int vp_norm_finalize(const double* sums, const float* gamma, const fl
 extern "C" int vp_norm_apply_act(const void* x, const float* scale, const float* shift, void* a, int dtype,
                                  int64_t groups, int64_t rpg, int c, int act, float slope, void* stream) {
     VP_CHECK_ARG(x && a && groups > 0 && rpg > 0 && c > 0, "vp_norm_apply_act: bad arguments");
-    const int64_t rows = groups * rpg;
-    dim3 grid((unsigned)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB);
+    VP_CHECK_ARG(groups <= 65535, "vp_norm_apply_act: too many groups");
+    dim3 grid((unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB, (unsigned)groups);
     if (dtype == VP_F32)
-        apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, scale, shift, (float*)a, rows, rpg, c, act, slope);
+        apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, scale, shift, (float*)a, rpg, c, act, slope);
     else
-        apply_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, scale, shift, (bf16*)a, rows, rpg, c, act, slope);
+        apply_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, scale, shift, (bf16*)a, rpg, c, act, slope);
     VP_CHECK_LAUNCH("vp_norm_apply_act");
     return VP_OK;
 }
@@ -295,11 +386,13 @@ extern "C" int vp_norm_bwd_reduce(const void* x, const void* da, const float* me
     VP_CHECK_ARG(x && da && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_bwd_reduce: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_bwd_reduce: too many groups");
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
-    dim3 grid((c + CPB - 1) / CPB, (unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (unsigned)groups);
+    const int tpr = threads_per_row(c);
+    const int ctiles = (c + tpr * VR - 1) / (tpr * VR);
+    dim3 grid(ctiles, slab_blocks(rpg, ctiles, groups), (unsigned)groups);
     if (dtype == VP_F32)
-        bwd_reduce_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dxo, groups, rpg, c, act, slope);
+        bwd_reduce_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dxo, groups, rpg, c, act, slope, tpr);
     else
-        bwd_reduce_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, sums, (bf16*)dxo, groups, rpg, c, act, slope);
+        bwd_reduce_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, sums, (bf16*)dxo, groups, rpg, c, act, slope, tpr);
     VP_CHECK_LAUNCH("vp_norm_bwd_reduce");
     return VP_OK;
 }
@@ -310,8 +403,8 @@ extern "C" int vp_norm_bwd_apply(const void* x, const void* da, const float* mea
                                  int act, float slope, void* stream) {
     VP_CHECK_ARG(x && da && mean && invstd && scale && shift && sums && dx && groups > 0 && rpg > 0 && c > 0,
                  "vp_norm_bwd_apply: bad arguments");
-    const int64_t rows = groups * rpg;
-    dim3 grid((unsigned)((rows + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB);
+    VP_CHECK_ARG(groups <= 65535, "vp_norm_bwd_apply: too many groups");
+    dim3 grid((unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB, (unsigned)groups);
     if (dtype == VP_F32)
         bwd_apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dx, dgamma, dbeta, groups, rpg, c, act, slope);
     else

@@ -413,6 +413,8 @@ int try_thin_wgrad(const TapWgrad& p, cudaStream_t s) {
 // ---- thin-K tap GEMM: the input has <= 4 channels (first-layer forward, last-layer data gradient) ------
 // One thread = one output pixel x 8 output channels (a 16-byte store); the weights [tap][k][N] sit in shared
 // memory as fp32, the few input scalars per tap are warp-broadcast loads.  Purely store-bound.
+constexpr int THIN_PX = 4;   // output pixels (consecutive gx) per thread: each weight fetch from smem feeds 4 pixels
+
 template <typename T, typename TD, int CT>
 __global__ void __launch_bounds__(256) thin_fwd_kernel(const TapGemm p) {
     extern __shared__ float wsm[];   // [ntaps][CT][N]
@@ -427,46 +429,66 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(const TapGemm p) {
     }
     __syncthreads();
     const int groups = p.N >> 3;
-    const int64_t total = (int64_t)p.n * p.gh * p.gw * groups;
+    const int xq = (p.gw + THIN_PX - 1) / THIN_PX;
+    const int64_t total = (int64_t)p.n * p.gh * xq * groups;
     TD* __restrict__ D = (TD*)p.D;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int g8 = (int)(i % groups) * 8;
         int64_t m = i / groups;
-        const int gx = (int)(m % p.gw); m /= p.gw;
+        const int gx0 = (int)(m % xq) * THIN_PX; m /= xq;
         const int gy = (int)(m % p.gh);
         const int n = (int)(m / p.gh);
-        const int oy = gy * p.ds + p.doy, ox = gx * p.ds + p.dox;
-        if (oy >= p.hd || ox >= p.wd) continue;
-        float acc[8];
+        const int oy = gy * p.ds + p.doy;
+        if (oy >= p.hd) continue;
+        float acc[THIN_PX][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = p.bias ? p.bias[g8 + j] : 0.f;
+        for (int q = 0; q < THIN_PX; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = p.bias ? p.bias[g8 + j] : 0.f;
         for (int t = 0; t < nt; ++t) {
-            const int iy = gy * p.as + p.taps.ty[t], ix = gx * p.as + p.taps.tx[t];
-            if (iy < 0 || iy >= p.ha || ix < 0 || ix >= p.wa) continue;
-            const T* arow = A + (((int64_t)n * p.ha + iy) * p.wa + ix) * p.K;
+            const int iy = gy * p.as + p.taps.ty[t];
+            if (iy < 0 || iy >= p.ha) continue;
+            const T* arow = A + ((int64_t)n * p.ha + iy) * p.wa * p.K;
 #pragma unroll
             for (int k = 0; k < CT; ++k) {
-                const float a = Cvt<T>::ld(arow + k);
+                float a[THIN_PX];
+#pragma unroll
+                for (int q = 0; q < THIN_PX; ++q) {
+                    const int ix = (gx0 + q) * p.as + p.taps.tx[t];
+                    a[q] = (ix >= 0 && ix < p.wa) ? Cvt<T>::ld(arow + (int64_t)ix * p.K + k) : 0.f;
+                }
                 const float4 w0 = *reinterpret_cast<const float4*>(wsm + (t * CT + k) * p.N + g8);
                 const float4 w1 = *reinterpret_cast<const float4*>(wsm + (t * CT + k) * p.N + g8 + 4);
-                acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]); acc[3] = fmaf(a, w0.w, acc[3]);
-                acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]); acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+#pragma unroll
+                for (int q = 0; q < THIN_PX; ++q) {
+                    acc[q][0] = fmaf(a[q], w0.x, acc[q][0]); acc[q][1] = fmaf(a[q], w0.y, acc[q][1]);
+                    acc[q][2] = fmaf(a[q], w0.z, acc[q][2]); acc[q][3] = fmaf(a[q], w0.w, acc[q][3]);
+                    acc[q][4] = fmaf(a[q], w1.x, acc[q][4]); acc[q][5] = fmaf(a[q], w1.y, acc[q][5]);
+                    acc[q][6] = fmaf(a[q], w1.z, acc[q][6]); acc[q][7] = fmaf(a[q], w1.w, acc[q][7]);
+                }
             }
         }
-        TD* out = D + (((int64_t)n * p.hd + oy) * p.wd + ox) * p.N + g8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = act_fwd(acc[j], p.act, p.slope);
-        if (sizeof(TD) == 2) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[0], acc[1]), h1 = __floats2bfloat162_rn(acc[2], acc[3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[4], acc[5]), h3 = __floats2bfloat162_rn(acc[6], acc[7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(out) = pk;
-        } else {
-            float* o = reinterpret_cast<float*>(out);
-            *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        for (int q = 0; q < THIN_PX; ++q) {
+            const int gx = gx0 + q;
+            const int ox = gx * p.ds + p.dox;
+            if (gx >= p.gw || ox >= p.wd) continue;
+            TD* out = D + (((int64_t)n * p.hd + oy) * p.wd + ox) * p.N + g8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = act_fwd(acc[q][j], p.act, p.slope);
+            if (sizeof(TD) == 2) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                *reinterpret_cast<uint4*>(out) = pk;
+            } else {
+                float* o = reinterpret_cast<float*>(out);
+                *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(o + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            }
         }
     }
 }
@@ -475,7 +497,7 @@ int try_thin_fwd(const TapGemm& p, cudaStream_t s) {
     if (p.K > 4 || p.K < 1 || (p.N & 7) != 0 || p.N > 256 || ((uintptr_t)p.D & 15)) return VP_EUNSUPPORTED;
     const size_t smem = sizeof(float) * (size_t)p.taps.ntaps * p.K * p.N;
     if (smem > 48 * 1024 || smem == 0) return VP_EUNSUPPORTED;
-    const int64_t total = (int64_t)p.n * p.gh * p.gw * (p.N >> 3);
+    const int64_t total = (int64_t)p.n * p.gh * ((p.gw + THIN_PX - 1) / THIN_PX) * (p.N >> 3);
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     const bool f32 = p.out_dtype == VP_F32;

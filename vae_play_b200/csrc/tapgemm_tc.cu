@@ -571,7 +571,7 @@ struct TcWgradParams {
 };
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads) tapwgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG,
+__global__ void __launch_bounds__(kFwdThreads) tapwgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG,
                                                                const __grid_constant__ CUtensorMap mapA,
                                                                const TcWgradParams p) {
     constexpr int kGBytes = 2 * kBoxBytes;            // 128 gc
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kThreads) tapwgrad_tc_kernel(const __grid_cons
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+            for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }   // full: G and A producers
             mbar_init(acc_ready, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
@@ -616,7 +616,9 @@ __global__ void __launch_bounds__(kThreads) tapwgrad_tc_kernel(const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == 0 || warp == 6) {
+        // two TMA issuing threads: warp 0 streams the G (grid-side) boxes, warp 6 the shifted A boxes
+        const bool is_g = warp == 0;
         if (elect_one()) {
             for (int it = 0; it < iters; ++it) {
                 const int s = it % STAGES;
@@ -628,12 +630,16 @@ __global__ void __launch_bounds__(kThreads) tapwgrad_tc_kernel(const __grid_cons
                 const int n0 = b * p.bt, gy0 = th * p.ht, gx0 = tw * p.wt;
                 uint8_t* sg = smem + s * kStage;
                 uint8_t* sa = sg + kGBytes;
-                mbar_expect_tx(&full[s], kStage);
-                tma_load_4d(sg, &mapG, &full[s], m0, gx0, gy0, n0);
-                tma_load_4d(sg + kBoxBytes, &mapG, &full[s], m0 + 64, gx0, gy0, n0);
+                if (is_g) {
+                    mbar_expect_tx(&full[s], kGBytes);
+                    tma_load_4d(sg, &mapG, &full[s], m0, gx0, gy0, n0);
+                    tma_load_4d(sg + kBoxBytes, &mapG, &full[s], m0 + 64, gx0, gy0, n0);
+                } else {
+                    mbar_expect_tx(&full[s], kAStage);
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                    tma_load_4d(sa + j * kBoxBytes, &mapA, &full[s], c0 + 64 * j, gx0 * p.as + tx, gy0 * p.as + ty, n0);
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_4d(sa + j * kBoxBytes, &mapA, &full[s], c0 + 64 * j, gx0 * p.as + tx, gy0 * p.as + ty, n0);
+                }
             }
         }
     } else if (warp == 1) {
@@ -656,7 +662,7 @@ __global__ void __launch_bounds__(kThreads) tapwgrad_tc_kernel(const __grid_cons
             }
             tc_commit(acc_ready);
         }
-    } else {
+    } else if (warp >= 2 && warp <= 5) {
         const int lane_base = (warp & 3) * 32;
         const int gc = m0 + lane_base + lane;
         mbar_wait(acc_ready, 0);
@@ -691,7 +697,7 @@ int launch_wgrad_cfg(const CUtensorMap& mG, const CUtensorMap& mA, const TcWgrad
         if (e != cudaSuccess) { set_error("tapwgrad_tc: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = true;
     }
-    tapwgrad_tc_kernel<BN, STAGES><<<grid, kThreads, smem_bytes, s>>>(mG, mA, tp);
+    tapwgrad_tc_kernel<BN, STAGES><<<grid, kFwdThreads, smem_bytes, s>>>(mG, mA, tp);
     VP_CHECK_LAUNCH("tapwgrad_tc");
     return VP_OK;
 }
