@@ -21,10 +21,16 @@ import torch.distributed as dist
 
 
 class GradBuckets:
-    def __init__(self, params: List[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0, group=None):
+    def __init__(self, params: List[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0, group=None,
+                 overlap: bool = True):
+        """overlap=True: each bucket's all-reduce is issued from the gradient hook as soon as the bucket is
+        complete (overlaps the rest of backward).  overlap=False: hooks only place gradients into the buckets and
+        ``allreduce()`` issues all collectives afterwards -- used when forward+backward is replayed as a CUDA
+        graph (the collectives stay outside the captured region)."""
         self.params = [p for p in params if p.requires_grad]
         self.world = world_size
         self.group = group
+        self.overlap = overlap
         cap = int(bucket_mb * (1 << 20) / 4)
         # reverse registration order ~ the order gradients become ready in backward
         order = list(reversed(self.params))
@@ -71,16 +77,16 @@ class GradBuckets:
             p.grad = view
         b = self.buckets[bi]
         b["ready"] += 1
-        if b["ready"] == len(b["params"]) and self.world > 1:
+        if b["ready"] == len(b["params"]) and self.world > 1 and self.overlap:
             b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
-    def allreduce(self):
+    def allreduce(self, check_missing: bool = True):
         """Finish the step's exchange: launch whatever is still pending, wait for everything."""
         for b in self.buckets:
             if self.world > 1 and b["handle"] is None:
                 # some parameter of this bucket received no gradient this step: its slot must not carry stale data
                 for p in b["params"]:
-                    if p.grad is None:
+                    if check_missing and p.grad is None:
                         self.slot[id(p)][1].zero_()
                 b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         for b in self.buckets:
