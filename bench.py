@@ -49,7 +49,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -237,7 +237,7 @@ def run_ours(args):
         sampler.start()          # nvidia-smi needs ~0.3 s to produce its first sample: start before the warm-up
     # untimed warm-up: W steps as asked, plus a fixed number of extra steps (same on every rank: the step
     # contains collectives) so that the clock sampler is live and the SM clocks have ramped up
-    for _ in range(max(args.warmup, 3) + 60):
+    for _ in range(max(args.warmup, 3) + args.extra_warmup):
         step(x_dev)
     barrier()
     if rank == 0:
@@ -353,6 +353,7 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=16)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extra-warmup", type=int, default=60, help="additional untimed steps so clocks ramp up and the sampler is live")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

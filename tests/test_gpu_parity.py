@@ -561,3 +561,33 @@ def test_thin_channel_fwd_and_dgrad(vp, cin, cout, stride, hw, b):
         dx = layer.dgrad(dy, w, tuple(x.shape), out_dtype=torch.float32)
         want = torch.nn.grad.conv2d_input((b, cin, hw, hw), wq, dy.double().permute(0, 3, 1, 2), stride=stride, padding=2)
         close(npy(dx), npy(want.permute(0, 2, 3, 1)), 1e-5, "thin dgrad")
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,S", [("conv", 64, 128, 5, 1), ("conv", 3, 64, 5, 1), ("convT", 128, 64, 5, 1),
+                                                ("conv", 40, 96, 3, 1), ("flatten_in", 64, 96, 1, 8), ("flatten_out", 32, 64, 1, 8),
+                                                ("linear", 96, 40, 1, 1)])
+def test_pack_unpack_bit_exact(vp, kind, cin, cout, k, S):
+    """Weight packing is index shuffling: bit-exact against the host emulation, and unpack inverts it."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    from tests.test_host_cpu import _emulate_pack
+    if kind == "conv":
+        layer, shape = VF.TapLayer("conv", cin, cout, k=k, stride=1, pad=k // 2), (cout, cin, k, k)
+    elif kind == "convT":
+        layer, shape = VF.TapLayer("convT", cin, cout, k=k, stride=2, pad=2, out_pad=1), (cin, cout, k, k)
+    elif kind == "flatten_in":
+        layer, shape = VF.TapLayer("flatten_in", cin, cout, spatial=S), (cout, cin * S * S)
+    elif kind == "flatten_out":
+        layer, shape = VF.TapLayer("flatten_out", cin, cout, spatial=S), (cout * S * S, cin)
+    else:
+        layer, shape = VF.TapLayer("linear", cin, cout), (cout, cin)
+    w = torch.randn(*shape, device="cuda")
+    for which in ("fwd", "dgrad"):
+        p = getattr(layer, "p_" + which)
+        wp = torch.empty(p.taps * p.n * p.k, dtype=torch.float32, device="cuda")
+        _lib.call("vp_pack_weight", VF._ptr(w), VF._ptr(wp), 0, p.taps, p.n, p.k, p.sn, p.sk, p.st, VF._stream())
+        want = _emulate_pack(w.cpu().numpy(), p)
+        assert np.array_equal(wp.cpu().numpy().reshape(want.shape), want), (kind, which)
+        back = torch.zeros_like(w)
+        _lib.call("vp_unpack_wgrad", VF._ptr(wp), VF._ptr(back), p.taps, p.n, p.k, p.sn, p.sk, p.st, VF._stream())
+        assert torch.equal(back, w), (kind, which)

@@ -278,6 +278,42 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
     for (int t = 0; t < taps; ++t) Cvt<T>::st(wp + ((int64_t)t * N + n) * K + k, src[t * st]);
 }
 
+// Tiled variants for the torch conv layouts (taps contiguous in the source, stride_t == 1): a 32(k) x T tile goes
+// through shared memory so that both the fp32 side (contiguous along t) and the packed side (contiguous along k)
+// are accessed in full segments.  grid = (K/32, N).
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N,
+                                                                int K, int64_t sn, int64_t sk) {
+    extern __shared__ float tile[];   // [32][taps+1]
+    const int n = blockIdx.y, k0 = blockIdx.x * 32;
+    const int ld = taps + 1;
+    for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
+        const int kk = i / taps, tt = i - kk * taps;
+        tile[kk * ld + tt] = (k0 + kk < K) ? w[n * sn + (int64_t)(k0 + kk) * sk + tt] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
+        const int tt = i >> 5, kk = i & 31;
+        if (k0 + kk < K) Cvt<T>::st(wp + ((int64_t)tt * N + n) * K + k0 + kk, tile[kk * ld + tt]);
+    }
+}
+
+__global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int taps,
+                                                                 int N, int K, int64_t sn, int64_t sk) {
+    extern __shared__ float tile[];
+    const int n = blockIdx.y, k0 = blockIdx.x * 32;
+    const int ld = taps + 1;
+    for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
+        const int tt = i >> 5, kk = i & 31;
+        tile[kk * ld + tt] = (k0 + kk < K) ? dwp[((int64_t)tt * N + n) * K + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * taps; i += blockDim.x) {
+        const int kk = i / taps, tt = i - kk * taps;
+        if (k0 + kk < K) dw[n * sn + (int64_t)(k0 + kk) * sk + tt] = tile[kk * ld + tt];
+    }
+}
+
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int taps,
                                                            int N, int K, int64_t sn, int64_t sk, int64_t st) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -441,6 +477,14 @@ extern "C" int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void*
 extern "C" int vp_pack_weight(const float* w, void* wp, int dtype, int taps, int n, int k, int64_t sn, int64_t sk,
                               int64_t st, void* stream) {
     VP_CHECK_ARG(w && wp && taps > 0 && n > 0 && k > 0, "vp_pack_weight: bad arguments");
+    if (st == 1 && taps >= 4 && k >= 32 && n <= 65535) {
+        dim3 grid((k + 31) / 32, n);
+        const size_t smem = sizeof(float) * 32 * (taps + 1);
+        if (dtype == VP_F32) pack_weight_tiled_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (float*)wp, taps, n, k, sn, sk);
+        else pack_weight_tiled_kernel<bf16><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wp, taps, n, k, sn, sk);
+        VP_CHECK_LAUNCH("vp_pack_weight(tiled)");
+        return VP_OK;
+    }
     const unsigned g = (unsigned)(((int64_t)n * k + 255) / 256);
     if (dtype == VP_F32) pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(w, (float*)wp, taps, n, k, sn, sk, st);
     else pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, taps, n, k, sn, sk, st);
@@ -451,6 +495,13 @@ extern "C" int vp_pack_weight(const float* w, void* wp, int dtype, int taps, int
 extern "C" int vp_unpack_wgrad(const float* dwp, float* dw, int taps, int n, int k, int64_t sn, int64_t sk, int64_t st,
                                void* stream) {
     VP_CHECK_ARG(dwp && dw && taps > 0 && n > 0 && k > 0, "vp_unpack_wgrad: bad arguments");
+    if (st == 1 && taps >= 4 && k >= 32 && n <= 65535) {
+        dim3 grid((k + 31) / 32, n);
+        const size_t smem = sizeof(float) * 32 * (taps + 1);
+        unpack_wgrad_tiled_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dwp, dw, taps, n, k, sn, sk);
+        VP_CHECK_LAUNCH("vp_unpack_wgrad(tiled)");
+        return VP_OK;
+    }
     const unsigned g = (unsigned)(((int64_t)n * k + 255) / 256);
     unpack_wgrad_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(dwp, dw, taps, n, k, sn, sk, st);
     VP_CHECK_LAUNCH("vp_unpack_wgrad");

@@ -324,6 +324,11 @@ __global__ void colsum_finish_kernel(const double* __restrict__ s, float* __rest
 }  // namespace
 }  // namespace vp
 
+namespace vp {
+int norm_stream(int mode, int dtype, const void* x, const void* da, void* out, const float* mean, const float* invstd,
+                const float* scale, const float* shift, double* sums, float* dgamma, float* dbeta, int64_t rows, int c, int act,
+                float slope, cudaStream_t s);
+}
 using namespace vp;
 
 // threads per row of the reduction kernels: enough 4-channel threads to cover C, at most 16 (64 channels per block)
@@ -346,6 +351,11 @@ extern "C" int vp_norm_stats(const void* x, double* sums, int dtype, int64_t gro
     VP_CHECK_ARG(x && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_stats: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_stats: too many groups");
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
+    if (groups == 1) {
+        const int rc = norm_stream(0, dtype, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, nullptr, nullptr, rpg, c, 0,
+                                   0.f, (cudaStream_t)stream);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     const int tpr = threads_per_row(c);
     const int ctiles = (c + tpr * VR - 1) / (tpr * VR);
     dim3 grid(ctiles, slab_blocks(rpg, ctiles, groups), (unsigned)groups);
@@ -371,6 +381,11 @@ extern "C" int vp_norm_apply_act(const void* x, const float* scale, const float*
                                  int64_t groups, int64_t rpg, int c, int act, float slope, void* stream) {
     VP_CHECK_ARG(x && a && groups > 0 && rpg > 0 && c > 0, "vp_norm_apply_act: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_apply_act: too many groups");
+    if (groups == 1) {
+        const int rc = norm_stream(1, dtype, x, nullptr, a, nullptr, nullptr, scale, shift, nullptr, nullptr, nullptr, rpg, c, act, slope,
+                                   (cudaStream_t)stream);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     dim3 grid((unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB, (unsigned)groups);
     if (dtype == VP_F32)
         apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, scale, shift, (float*)a, rpg, c, act, slope);
@@ -386,6 +401,11 @@ extern "C" int vp_norm_bwd_reduce(const void* x, const void* da, const float* me
     VP_CHECK_ARG(x && da && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_bwd_reduce: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_bwd_reduce: too many groups");
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
+    if (groups == 1) {
+        const int rc = norm_stream(2, dtype, x, da, dxo, mean, invstd, scale, shift, sums, nullptr, nullptr, rpg, c, act, slope,
+                                   (cudaStream_t)stream);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     const int tpr = threads_per_row(c);
     const int ctiles = (c + tpr * VR - 1) / (tpr * VR);
     dim3 grid(ctiles, slab_blocks(rpg, ctiles, groups), (unsigned)groups);
@@ -404,6 +424,11 @@ extern "C" int vp_norm_bwd_apply(const void* x, const void* da, const float* mea
     VP_CHECK_ARG(x && da && mean && invstd && scale && shift && sums && dx && groups > 0 && rpg > 0 && c > 0,
                  "vp_norm_bwd_apply: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_bwd_apply: too many groups");
+    if (groups == 1) {
+        const int rc = norm_stream(3, dtype, x, da, dx, mean, invstd, scale, shift, const_cast<double*>(sums), dgamma, dbeta, rpg, c, act,
+                                   slope, (cudaStream_t)stream);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     dim3 grid((unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB, (unsigned)groups);
     if (dtype == VP_F32)
         bwd_apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dx, dgamma, dbeta, groups, rpg, c, act, slope);
