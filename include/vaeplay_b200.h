@@ -166,6 +166,9 @@ int vp_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
 /* sum += a (fp32, n elements): gradient accumulation helper */
 int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
 
+/* debug: tcgen05 operand-window probe (tools/probe_umma.py); x bf16 [256][64], ident bf16 [64][64], out fp32 [128][64] */
+int vp_debug_umma_probe(const void* x, const void* ident, float* out, int off_rows, int sbo_rows, int base_offset, void* stream);
+
 /* number of kernels this library has launched in this process (the bench's gpu_launches claim) */
 uint64_t vp_launch_count(void);
 

@@ -18,8 +18,41 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vp {
+
+// ---- host-side helpers shared by the tcgen05 launchers (declared in tc_common.cuh) ----
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -28,113 +61,7 @@ constexpr int kThreads = 192;          // wgrad kernel: TMA, MMA, 4 epilogue war
 constexpr int kFwdThreads = 224;       // fwd/dgrad kernel: + a second TMA producer warp (B operand)
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// Bounded wait: a pipeline bug must surface as a trapped kernel (launch error), never as a hung GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}"
-            : "=r"(done)
-            : "r"(addr), "r"(parity)
-            : "memory");
-        if (done) return;
-    }
-    printf("vaeplay_b200: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
-    __trap();
-}
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "elect.sync _|p, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(pred));
-    return pred != 0;
-}
-__device__ __forceinline__ void tma_load_4d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
-            smem_u32(smem)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-            smem_u32(smem)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// 32 lanes x 32 columns of fp32: thread i of the warp receives columns [col, col+32) of TMEM lane (lane_base + i)
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), start address advanced by
-// 32 B per UMMA_K=16 step.  Bits: [0,14) addr>>4, [16,30) LBO>>4 (unused for swizzled K-major), [32,46) SBO>>4,
-// [46,48) version=1 (Blackwell), [61,64) layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-// kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
-__host__ __device__ constexpr uint32_t idesc_bf16_f32(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
+using namespace tc;
 
 constexpr int kMaxPhases = 4;
 
@@ -308,51 +235,7 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                 if (CH == 32) tmem_ld32(taddr, v);
                 else tmem_ld16(taddr, v);
                 tmem_ld_wait();
-                if (row_ok) {
-                    const int cbase = tc.col0 + c;
-                    if (p.out_f32) {
-                        float* out = (float*)p.D + row_off + cbase;
-#pragma unroll
-                        for (int j = 0; j < CH; j += 4) {
-                            float f[4];
-#pragma unroll
-                            for (int qq = 0; qq < 4; ++qq) {
-                                float x = __uint_as_float(v[j + qq]);
-                                if (p.bias && cbase + j + qq < p.N) x += p.bias[cbase + j + qq];
-                                f[qq] = act_fwd(x, p.act, p.slope);
-                            }
-                            if (cbase + j + 3 < p.N && (p.N & 3) == 0) {
-                                *reinterpret_cast<float4*>(out + j) = make_float4(f[0], f[1], f[2], f[3]);
-                            } else {
-#pragma unroll
-                                for (int qq = 0; qq < 4; ++qq) if (cbase + j + qq < p.N) out[j + qq] = f[qq];
-                            }
-                        }
-                    } else {
-                        bf16* out = (bf16*)p.D + row_off + cbase;
-#pragma unroll
-                        for (int j = 0; j < CH; j += 8) {
-                            float f[8];
-#pragma unroll
-                            for (int qq = 0; qq < 8; ++qq) {
-                                float x = __uint_as_float(v[j + qq]);
-                                if (p.bias && cbase + j + qq < p.N) x += p.bias[cbase + j + qq];
-                                f[qq] = act_fwd(x, p.act, p.slope);
-                            }
-                            if (cbase + j + 7 < p.N && (p.N & 7) == 0) {
-                                uint4 pk;
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
-                                pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                                pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                                *reinterpret_cast<uint4*>(out + j) = pk;
-                            } else {
-#pragma unroll
-                                for (int qq = 0; qq < 8; ++qq) if (cbase + j + qq < p.N) out[j + qq] = __float2bfloat16_rn(f[qq]);
-                            }
-                        }
-                    }
-                }
+                if (row_ok) store_chunk<CH>(v, p.D, row_off, tc.col0 + c, p.N, p.bias, p.act, p.slope, p.out_f32 != 0);
             }
             // this warp's TMEM reads are complete (wait::ld above): hand the buffer back to the MMA warp
             tc_fence_before();
@@ -370,38 +253,6 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)sym;
-    }
-    return fn;
-}
-
-int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
-int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
-
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 template <int BN, int STAGES, int CTAS>
 int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES>;
@@ -443,6 +294,11 @@ bool tc_available() {
 // All phases share A, Wp, D, K, N, as, ds, bias, act; they differ in (gh, gw, doy, dox, taps).
 int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) {
     const TapGemm& p = phases[0];
+    // stride-1 tap sets go to the windowed (halo re-use) kernel first; VP_TC_VARIANT=2 disables it (A/B measurements)
+    if (tc_variant() != 2) {
+        const int rc = launch_tapgemm_win(phases, nphases, s);
+        if (rc != VP_EUNSUPPORTED) return rc;
+    }
     // ---- eligibility -----------------------------------------------------------------------------------
     if (!tc_available()) { set_error("tcgen05 engine: needs an sm_100 device and cuTensorMapEncodeTiled"); return VP_EUNSUPPORTED; }
     if (nphases < 1 || nphases > kMaxPhases) { set_error("tcgen05 engine: %d phases", nphases); return VP_EUNSUPPORTED; }
@@ -759,3 +615,90 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
 }
 
 }  // namespace vp
+
+// =====================================================================================================
+// Hardware-semantics probe (debug entry point, used by tools/probe_umma.py): does tcgen05.mma accept a K-major
+// SW128 A operand whose start address is NOT 1024-byte aligned (a window into a larger TMA-written tile), with an
+// arbitrary stride between 8-row groups (SBO)?  D[m][n] should equal X[off + (m/8)*sbo_rows + m%8][n] for B = I.
+// =====================================================================================================
+namespace vp {
+namespace {
+__global__ void __launch_bounds__(128) umma_probe_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapI,
+                                                         float* out, int off_rows, int sbo_rows, int base_offset) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sx = smem;                 // 256 rows x 128 B
+    uint8_t* si = smem + 256 * 128;     // 64 rows x 128 B (identity)
+    uint64_t* bar = (uint64_t*)(si + 64 * 128);
+    uint64_t* done = bar + 1;
+    uint32_t* slot = (uint32_t*)(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+        if (lane == 0) { mbar_init(bar, 1); mbar_init(done, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(64) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, 256 * 128 + 64 * 128);
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(sx)),
+                     "l"(&mapX), "r"(smem_u32(bar)), "r"(0), "r"(0) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(si)),
+                     "l"(&mapI), "r"(smem_u32(bar)), "r"(0), "r"(0) : "memory");
+        mbar_wait(bar, 0);
+        tc_fence_after();
+        uint64_t adesc = 0;
+        const uint32_t sa = smem_u32(sx) + off_rows * 128;
+        adesc |= (uint64_t)((sa & 0x3FFFF) >> 4);
+        adesc |= (uint64_t)1 << 16;
+        adesc |= (uint64_t)((sbo_rows * 128) >> 4) << 32;
+        adesc |= (uint64_t)1 << 46;
+        adesc |= (uint64_t)(base_offset & 7) << 49;
+        adesc |= (uint64_t)2 << 61;
+        const uint64_t bdesc = smem_desc_k_sw128(smem_u32(si));
+        constexpr uint32_t idesc = idesc_bf16_f32(128, 64);
+        for (int k = 0; k < 4; ++k) tc_mma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, k != 0);
+        tc_commit(done);
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    for (int c = 0; c < 64; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c, v);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) out[(warp * 32 + lane) * 64 + c + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { tc_fence_after(); asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64) : "memory"); }
+}
+}  // namespace
+}  // namespace vp
+
+// x: bf16 [256][64]; ident: bf16 [64][64]; out: fp32 [128][64]
+extern "C" int vp_debug_umma_probe(const void* x, const void* ident, float* out, int off_rows, int sbo_rows, int base_offset, void* stream) {
+    using namespace vp;
+    if (!tc_available()) { set_error("probe: no tcgen05 device"); return VP_EUNSUPPORTED; }
+    EncodeTiledFn encode = get_encode();
+    CUtensorMap mX, mI;
+    cuuint32_t estr[2] = {1, 1};
+    {
+        cuuint64_t dims[2] = {64, 256}; cuuint64_t strides[1] = {128}; cuuint32_t box[2] = {64, 256};
+        if (encode(&mX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return VP_ECUDA;
+    }
+    {
+        cuuint64_t dims[2] = {64, 64}; cuuint64_t strides[1] = {128}; cuuint32_t box[2] = {64, 64};
+        if (encode(&mI, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ident), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return VP_ECUDA;
+    }
+    const int smem = 256 * 128 + 64 * 128 + 64 + 1024;
+    cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mX, mI, out, off_rows, sbo_rows, base_offset);
+    VP_CHECK_LAUNCH("umma_probe");
+    return VP_OK;
+}
