@@ -166,6 +166,12 @@ int vp_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
 /* sum += a (fp32, n elements): gradient accumulation helper */
 int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
 
+/* ---- optimiser: torch.optim.RMSprop (train.py:136-140; alpha .99, eps 1e-8, no momentum, not centered) as ONE
+ * multi-tensor kernel over fp32 masters:  sq = alpha*sq + (1-alpha)*g*g;  p -= lr * g / (sqrt(sq) + eps).
+ * params/grads/sq: host arrays of `count` device pointers, numel: host array of element counts. */
+int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* sq, const int64_t* numel, int count,
+                    float lr, float alpha, float eps, float weight_decay, void* stream);
+
 /* debug: tcgen05 operand-window probe (tools/probe_umma.py); x bf16 [256][64], ident bf16 [64][64], out fp32 [128][64] */
 int vp_debug_umma_probe(const void* x, const void* ident, float* out, int off_rows, int sbo_rows, int base_offset, void* stream);
 

@@ -591,3 +591,26 @@ def test_pack_unpack_bit_exact(vp, kind, cin, cout, k, S):
         back = torch.zeros_like(w)
         _lib.call("vp_unpack_wgrad", VF._ptr(wp), VF._ptr(back), p.taps, p.n, p.k, p.sn, p.sk, p.st, VF._stream())
         assert torch.equal(back, w), (kind, which)
+
+
+def test_fused_rmsprop_matches_torch(vp):
+    """FusedRMSprop == torch.optim.RMSprop (the reference's optimiser, train.py:136-140) step for step."""
+    from vae_play_b200.optim import FusedRMSprop
+    torch.manual_seed(0)
+    shapes = [(64, 1, 5, 5), (128,), (1024, 16384), (3,), (256, 128, 5, 5), (7, 13)]
+    pa = [torch.randn(*s, device="cuda").requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa = FusedRMSprop(pa, lr=1e-4)
+    ob = torch.optim.RMSprop(pb, lr=1e-4)
+    for step in range(3):
+        for x, y in zip(pa, pb):
+            g = torch.randn_like(x) * (0.1 + step)
+            x.grad = g.clone()
+            y.grad = g.clone()
+        v0 = pa[0]._version
+        oa.step()
+        ob.step()
+        assert pa[0]._version > v0
+        for x, y in zip(pa, pb):
+            close(npy(x), npy(y), 1e-6, "rmsprop param")
+            close(npy(oa.state[x]["square_avg"]), npy(ob.state[y]["square_avg"]), 1e-6, "rmsprop state")

@@ -522,3 +522,66 @@ extern "C" int vp_fill_from(const float* g, float scale, float* out, int64_t n, 
     VP_CHECK_LAUNCH("vp_fill_from");
     return VP_OK;
 }
+
+// ---- multi-tensor RMSprop ---------------------------------------------------------------------------------------
+namespace vp {
+namespace {
+constexpr int kOptMax = 64;
+struct OptTable {
+    float* p[kOptMax];
+    const float* g[kOptMax];
+    float* sq[kOptMax];
+    int64_t n[kOptMax];
+};
+__global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd) {
+    const int ti = blockIdx.y;
+    float* __restrict__ p = t.p[ti];
+    const float* __restrict__ g = t.g[ti];
+    float* __restrict__ sq = t.sq[ti];
+    const int64_t n = t.n[ti];
+    const int64_t n4 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)sq) & 15) == 0 ? n / 4 : 0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 pv = reinterpret_cast<float4*>(p)[i];
+        const float4 gv0 = reinterpret_cast<const float4*>(g)[i];
+        float4 sv = reinterpret_cast<float4*>(sq)[i];
+        float pe[4] = {pv.x, pv.y, pv.z, pv.w}, ge[4] = {gv0.x, gv0.y, gv0.z, gv0.w}, se[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gg = ge[j] + wd * pe[j];
+            se[j] = alpha * se[j] + (1.f - alpha) * gg * gg;
+            pe[j] -= lr * (gg / (sqrtf(se[j]) + eps));
+        }
+        reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+        reinterpret_cast<float4*>(sq)[i] = make_float4(se[0], se[1], se[2], se[3]);
+    }
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float gg = g[i] + wd * p[i];
+        const float s2 = alpha * sq[i] + (1.f - alpha) * gg * gg;
+        sq[i] = s2;
+        p[i] -= lr * (gg / (sqrtf(s2) + eps));
+    }
+}
+}  // namespace
+}  // namespace vp
+
+extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* sq, const int64_t* numel, int count, float lr,
+                               float alpha, float eps, float weight_decay, void* stream) {
+    VP_CHECK_ARG(params && grads && sq && numel && count >= 0, "vp_rmsprop_step: bad arguments");
+    for (int base = 0; base < count; base += kOptMax) {
+        OptTable t;
+        const int m = count - base < kOptMax ? count - base : kOptMax;
+        int64_t nmax = 0;
+        for (int i = 0; i < m; ++i) {
+            t.p[i] = (float*)params[base + i]; t.g[i] = (const float*)grads[base + i]; t.sq[i] = (float*)sq[base + i];
+            t.n[i] = numel[base + i];
+            nmax = numel[base + i] > nmax ? numel[base + i] : nmax;
+        }
+        int64_t bx = (nmax / 4 + 255) / 256;
+        if (bx > 148 * 2) bx = 148 * 2;
+        if (bx < 1) bx = 1;
+        rmsprop_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, lr, alpha, eps, weight_decay);
+        VP_CHECK_LAUNCH("vp_rmsprop_step");
+    }
+    return VP_OK;
+}

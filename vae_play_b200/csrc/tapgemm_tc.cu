@@ -530,9 +530,18 @@ __global__ void __launch_bounds__(kFwdThreads) tapwgrad_tc_kernel(const __grid_c
             tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
             tmem_ld_wait();
             if (gc < p.GC) {
+                if (c0 + c + 32 <= p.AC) {
+                    // whole chunk inside the tensor: 8 vector reductions (red.global.add.v4.f32), no per-element predicates
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (c0 + c + j < p.AC) atomicAdd(out + c + j, __uint_as_float(v[j]));
+                    for (int j = 0; j < 32; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + j), "f"(__uint_as_float(v[j])),
+                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                     : "memory");
+                } else {
+#pragma unroll 4
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + c + j < p.AC) atomicAdd(out + c + j, __uint_as_float(v[j]));
+                }
             }
         }
     }
