@@ -166,6 +166,18 @@ int vp_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
 /* sum += a (fp32, n elements): gradient accumulation helper */
 int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
 
+/* ---- thin layers on the tensor cores: im2col + zero-padded weight panels ------------------------------------
+ * A layer with <= 4 input (or output) channels has a reduction of only cin*taps elements: instead of running it on
+ * CUDA cores, its taps are gathered into the channel axis so that it becomes a 1x1 layer with K = 64 or 128.
+ * dst[n,gy,gx, c*taps + t] = src[n, gy*stride + ty[t], gx*stride + tx[t], c]  (0 outside src and for padding columns);
+ * host_ty / host_tx: HOST arrays of `taps` offsets. */
+int vp_im2col(const void* src, void* dst, int dtype, int n, int hs, int ws, int cs, int gh, int gw, int stride, int taps,
+              const int8_t* host_ty, const int8_t* host_tx, int dst_cols, void* stream);
+/* dst[r][c] = c < cols ? (dtype) src[r*cols + c] : 0, dst row length dst_cols  (fp32 -> dtype) */
+int vp_pad_rows(const float* src, void* dst, int dtype, int64_t rows, int cols, int dst_cols, void* stream);
+/* dst[r*cols + c] = src[r*src_cols + c]  (fp32 -> fp32): drops the padding columns of a weight-gradient panel */
+int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_cols, void* stream);
+
 /* ---- optimiser: torch.optim.RMSprop (train.py:136-140; alpha .99, eps 1e-8, no momentum, not centered) as ONE
  * multi-tensor kernel over fp32 masters:  sq = alpha*sq + (1-alpha)*g*g;  p -= lr * g / (sqrt(sq) + eps).
  * params/grads/sq: host arrays of `count` device pointers, numel: host array of element counts. */

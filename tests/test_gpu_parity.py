@@ -612,5 +612,5 @@ def test_fused_rmsprop_matches_torch(vp):
         ob.step()
         assert pa[0]._version > v0
         for x, y in zip(pa, pb):
-            close(npy(x), npy(y), 1e-6, "rmsprop param")
-            close(npy(oa.state[x]["square_avg"]), npy(ob.state[y]["square_avg"]), 1e-6, "rmsprop state")
+            close(npy(x), npy(y), 1e-5, "rmsprop param")
+            close(npy(oa.state[x]["square_avg"]), npy(ob.state[y]["square_avg"]), 1e-5, "rmsprop state")

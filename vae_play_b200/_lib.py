@@ -58,6 +58,9 @@ SIGNATURES = {
     "vp_sum_into": [_p, _i64, _f, _p, _p],
     "vp_fill_from": [_p, _f, _p, _i64, _p],
     "vp_debug_umma_probe": [_p, _p, _p, _i, _i, _i, _p],
+    "vp_im2col": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
+    "vp_pad_rows": [_p, _p, _i, _i64, _i, _i, _p],
+    "vp_unpad_rows": [_p, _p, _i64, _i, _i, _p],
     "vp_rmsprop_step": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
 }
 PLAIN = {"vp_last_error": (C.c_char_p, []), "vp_abi_version": (_i, []), "vp_device_arch": (_i, []),

@@ -585,3 +585,91 @@ extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, vo
     }
     return VP_OK;
 }
+
+// ---- im2col for thin layers -----------------------------------------------------------------------------------------
+namespace vp {
+namespace {
+struct Im2colTaps { int8_t ty[kMaxTaps], tx[kMaxTaps]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int hs, int ws, int cs, int gh,
+                                                     int gw, int stride, int taps, const __grid_constant__ Im2colTaps tt, int dst_cols) {
+    // one thread = one destination pixel x 8 consecutive columns (16-byte store for bf16)
+    const int groups = dst_cols >> 3;
+    const int64_t total = (int64_t)n * gh * gw * groups;
+    const int valid = cs * taps;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g8 = (int)(i % groups) * 8;
+        int64_t m = i / groups;
+        const int gx = (int)(m % gw); m /= gw;
+        const int gy = (int)(m % gh);
+        const int img = (int)(m / gh);
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int col = g8 + j;
+            float x = 0.f;
+            if (col < valid) {
+                const int c = col / taps, t = col - c * taps;
+                const int sy = gy * stride + tt.ty[t], sx = gx * stride + tt.tx[t];
+                if (sy >= 0 && sy < hs && sx >= 0 && sx < ws) x = Cvt<T>::ld(src + (((int64_t)img * hs + sy) * ws + sx) * cs + c);
+            }
+            v[j] = x;
+        }
+        T* out = dst + (((int64_t)img * gh + gy) * gw + gx) * dst_cols + g8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Cvt<T>::st(out + j, v[j]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t rows, int cols, int dst_cols) {
+    const int64_t total = rows * dst_cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / dst_cols;
+        const int c = (int)(i - r * dst_cols);
+        Cvt<T>::st(dst + i, c < cols ? src[r * cols + c] : 0.f);
+    }
+}
+
+__global__ void __launch_bounds__(256) unpad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int cols,
+                                                         int src_cols) {
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols;
+        dst[i] = src[r * src_cols + (i - r * cols)];
+    }
+}
+}  // namespace
+}  // namespace vp
+
+extern "C" int vp_im2col(const void* src, void* dst, int dtype, int n, int hs, int ws, int cs, int gh, int gw, int stride, int taps,
+                         const int8_t* host_ty, const int8_t* host_tx, int dst_cols, void* stream) {
+    VP_CHECK_ARG(src && dst && host_ty && host_tx && n > 0 && hs > 0 && ws > 0 && cs > 0 && gh > 0 && gw > 0 && stride > 0,
+                 "vp_im2col: bad arguments");
+    VP_CHECK_ARG(taps > 0 && taps <= kMaxTaps && dst_cols % 8 == 0 && cs * taps <= dst_cols, "vp_im2col: taps/columns");
+    Im2colTaps tt;
+    for (int t = 0; t < taps; ++t) { tt.ty[t] = host_ty[t]; tt.tx[t] = host_tx[t]; }
+    const int64_t total = (int64_t)n * gh * gw * (dst_cols >> 3);
+    const unsigned g = grid_for(total);
+    if (dtype == VP_F32) im2col_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, n, hs, ws, cs, gh, gw, stride, taps, tt, dst_cols);
+    else im2col_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, n, hs, ws, cs, gh, gw, stride, taps, tt, dst_cols);
+    VP_CHECK_LAUNCH("vp_im2col");
+    return VP_OK;
+}
+
+extern "C" int vp_pad_rows(const float* src, void* dst, int dtype, int64_t rows, int cols, int dst_cols, void* stream) {
+    VP_CHECK_ARG(src && dst && rows > 0 && cols > 0 && dst_cols >= cols, "vp_pad_rows: bad arguments");
+    const unsigned g = grid_for(rows * dst_cols);
+    if (dtype == VP_F32) pad_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(src, (float*)dst, rows, cols, dst_cols);
+    else pad_rows_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, rows, cols, dst_cols);
+    VP_CHECK_LAUNCH("vp_pad_rows");
+    return VP_OK;
+}
+
+extern "C" int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_cols, void* stream) {
+    VP_CHECK_ARG(src && dst && rows > 0 && cols > 0 && src_cols >= cols, "vp_unpad_rows: bad arguments");
+    unpad_rows_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, cols, src_cols);
+    VP_CHECK_LAUNCH("vp_unpad_rows");
+    return VP_OK;
+}
