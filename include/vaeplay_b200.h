@@ -178,6 +178,20 @@ int vp_pad_rows(const float* src, void* dst, int dtype, int64_t rows, int cols, 
 /* dst[r*cols + c] = src[r*src_cols + c]  (fp32 -> fp32): drops the padding columns of a weight-gradient panel */
 int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_cols, void* stream);
 
+/* ---- thin layers on tcgen05, straight from the fp32 master weight ------------------------------------------------
+ * Convolutions with a single channel on one side: the first EncoderBlock conv (models/networks.py:14 with
+ * channel_in = 1), the decoder's output conv (models/networks.py:101) and their gradients.  x / dy / y are bf16
+ * channels-last (y / dx in `out_dtype`); `w` is the nn.Conv2d weight itself, fp32 [co][ci][kh][kw], and `dw` its
+ * gradient in the same layout (zeroed by the call): no packed panels.  VP_EUNSUPPORTED when the shape is not thin.
+ *   fwd:   ci == 1 (stride <= 3, kernel <= 8x8; co a multiple of 32, <= 128)   or   co*kh*kw <= 32 at stride 1 (kernel
+ *          <= 5x5, ci a multiple of 64, <= 256)
+ *   dgrad: co == 1 at stride 1 (ci a multiple of 32, <= 128)
+ *   wgrad: ci == 1 (co a multiple of 64)   or   co == 1 at stride 1 (ci a multiple of 64) */
+int vp_thin_conv_fwd(const VpConvGeom* g, const void* x, const float* w, const float* bias, void* y, int out_dtype,
+                     int act, float slope, void* stream);
+int vp_thin_conv_dgrad(const VpConvGeom* g, const void* dy, const float* w, void* dx, int out_dtype, void* stream);
+int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, void* stream);
+
 /* ---- optimiser: torch.optim.RMSprop (train.py:136-140; alpha .99, eps 1e-8, no momentum, not centered) as ONE
  * multi-tensor kernel over fp32 masters:  sq = alpha*sq + (1-alpha)*g*g;  p -= lr * g / (sqrt(sq) + eps).
  * params/grads/sq: host arrays of `count` device pointers, numel: host array of element counts. */

@@ -563,6 +563,48 @@ def test_thin_channel_fwd_and_dgrad(vp, cin, cout, stride, hw, b):
         close(npy(dx), npy(want.permute(0, 2, 3, 1)), 1e-5, "thin dgrad")
 
 
+@pytest.mark.parametrize("cin,cout,k,stride,hw,b", [(1, 64, 5, 2, 64, 5), (1, 64, 7, 3, 40, 3), (1, 32, 5, 1, 21, 2), (1, 128, 3, 1, 17, 2),
+                                                      (64, 1, 5, 1, 64, 5), (128, 1, 5, 1, 19, 3), (64, 2, 3, 1, 33, 2), (64, 1, 3, 1, 9, 2)])
+def test_thin_tc_kernels(vp, cin, cout, k, stride, hw, b):
+    """tcgen05 thin-layer kernels (operands built in shared memory from the fp32 master weight) against float64 torch:
+    forward with bias + sigmoid, data gradient and weight gradient, ragged grids and both thin sides."""
+    import torch.nn.functional as F
+    import vae_play_b200.functional as VF
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    pad = (k - 1) // 2
+    g = torch.Generator(device="cuda").manual_seed(11)
+    layer = VF.TapLayer("conv", cin, cout, k=k, stride=stride, pad=pad)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.1
+    wq = w.to(torch.bfloat16).double()
+    x = torch.randn(b, hw, hw, cin, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    ho = (hw + 2 * pad - k) // stride + 1
+    dy = torch.randn(b, ho, ho, cout, device="cuda", generator=g).to(torch.bfloat16)
+    xd, dyd = x.double().permute(0, 3, 1, 2), dy.double().permute(0, 3, 1, 2)
+    n0 = vp._lib.launch_count()
+    assert layer._thin("fwd", torch.bfloat16, w)
+    y = layer.fwd(x, w, bias, "sigmoid", out_dtype=torch.float32)
+    want = torch.sigmoid(F.conv2d(xd, wq, bias.double(), stride=stride, padding=pad)).permute(0, 2, 3, 1)
+    close(npy(y), npy(want), 1e-5, "thin tc fwd")
+    y16 = layer.fwd(x, w, None)
+    want = F.conv2d(xd, wq, None, stride=stride, padding=pad).permute(0, 2, 3, 1)
+    close(npy(y16), npy(want), 6e-3, "thin tc fwd bf16")
+    assert vp._lib.launch_count() - n0 == 2          # one kernel each: no packing passes
+    if layer._thin("dgrad", torch.bfloat16, w):
+        dx = layer.dgrad(dy, w, tuple(x.shape), out_dtype=torch.float32)
+        want = torch.nn.grad.conv2d_input((b, cin, hw, hw), wq, dyd, stride=stride, padding=pad)
+        close(npy(dx), npy(want.permute(0, 2, 3, 1)), 1e-5, "thin tc dgrad")
+    else:
+        assert cin == 1 or cout > 1
+    if layer._thin("wgrad", torch.bfloat16, w):
+        dw = layer.wgrad(x, dy, w)
+        want = torch.nn.grad.conv2d_weight(xd, w.shape, dyd, stride=stride, padding=pad)
+        close(npy(dw), npy(want), 1e-5, "thin tc wgrad")
+    else:
+        assert (cout % 64 != 0 and cin == 1) or cout > 1
+
+
 @pytest.mark.parametrize("kind,cin,cout,k,S", [("conv", 64, 128, 5, 1), ("conv", 3, 64, 5, 1), ("convT", 128, 64, 5, 1),
                                                 ("conv", 40, 96, 3, 1), ("flatten_in", 64, 96, 1, 8), ("flatten_out", 32, 64, 1, 8),
                                                 ("linear", 96, 40, 1, 1)])

@@ -10,7 +10,7 @@ iters = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 B = 256
 vp.set_precision("bf16")
 cfg = {"ct3": ("convT", 128, 64, 32), "ct2": ("convT", 256, 128, 16), "ct1": ("convT", 256, 256, 8),
-       "enc2": ("conv", 64, 128, 32), "enc3": ("conv", 128, 256, 16), "out": ("conv1", 64, 1, 64)}
+       "enc2": ("conv", 64, 128, 32), "enc3": ("conv", 128, 256, 16), "out": ("conv1", 64, 1, 64), "enc1": ("conv", 1, 64, 64)}
 name = which.split("_")[0]
 kind, cin, cout, hw = cfg[name]
 if kind == "convT":

@@ -61,6 +61,9 @@ SIGNATURES = {
     "vp_im2col": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "vp_pad_rows": [_p, _p, _i, _i64, _i, _i, _p],
     "vp_unpad_rows": [_p, _p, _i64, _i, _i, _p],
+    "vp_thin_conv_fwd": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
+    "vp_thin_conv_dgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
+    "vp_thin_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
     "vp_rmsprop_step": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
 }
 PLAIN = {"vp_last_error": (C.c_char_p, []), "vp_abi_version": (_i, []), "vp_device_arch": (_i, []),

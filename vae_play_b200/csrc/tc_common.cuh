@@ -68,6 +68,16 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// TMA store of a shared-memory tile (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map), "r"(smem_u32(smem)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -175,6 +185,37 @@ __device__ __forceinline__ void store_chunk(const uint32_t* v, void* D, int64_t 
                 }
             }
         }
+    }
+}
+
+// ---- accumulator chunk -> per-warp staging tile for a TMA store ---------------------------------------------------
+// A warp owns 32 consecutive rows of the output tile; per 64-column group it writes them as a [32 rows][128 B]
+// SWIZZLE_128B tile (1024-byte aligned; chunk j of row r at ((j ^ (r & 7)) << 4): conflict-free 16-byte stores) which ONE
+// cp.async.bulk.tensor store then moves to global memory as full 128-byte lines.  (Per-thread 16-byte global stores at
+// a 128-byte row stride cost one L1 wavefront per row and capped the epilogue at ~1 TB/s.)
+// v: 32 fp32 columns [cbase, cbase+32) of row `lane`.
+__device__ __forceinline__ void stage_chunk32(uint8_t* stile, int lane, int cbase, const uint32_t* v, const float* bias, int act, float slope) {
+    const int j0 = (cbase & 63) >> 3;
+    uint8_t* row = stile + lane * 128;
+    const bool plain = (bias == nullptr) && (act == VP_ACT_NONE);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = __uint_as_float(v[j * 8 + e]);
+            if (!plain) {
+                if (bias) x += bias[cbase + j * 8 + e];
+                x = act_fwd(x, act, slope);
+            }
+            f[e] = x;
+        }
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(row + (((j0 + j) ^ (lane & 7)) << 4)) = pk;
     }
 }
 

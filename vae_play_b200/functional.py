@@ -165,11 +165,31 @@ class TapLayer:
         self._cache[which] = (key, wp)
         return wp
 
+    # ---- thin layers (<= 2 channels on one side): tcgen05 kernels that read the fp32 master weight directly ----
+    def _thin(self, which, dt, weight):
+        if self.kind != "conv" or dt != torch.bfloat16 or _STATE["engine"] == _lib.ENGINE_SIMT or not weight.is_contiguous():
+            return False
+        T, ci, co, s = self.k * self.k, self.cin, self.cout, self.stride
+        thin_in = ci == 1 and self.k <= 8 and s <= 3
+        if which == "fwd":
+            return (thin_in and co % 32 == 0 and co <= 128) or (s == 1 and self.k <= 5 and co * T <= 32 and ci % 64 == 0 and ci <= 256)
+        thin_out = co == 1 and s == 1 and self.k <= 8
+        if which == "dgrad":
+            return thin_out and ci % 32 == 0 and ci <= 128
+        return (thin_in and co % 64 == 0) or (thin_out and ci % 64 == 0)
+
     # ---- the three contractions --------------------------------------------------------------------
     def fwd(self, x, weight, bias, act="none", slope=0.0, out_dtype=None):
         n, h, w, _ = x.shape
         dt = x.dtype
         out_dtype = out_dtype or dt
+        if self._thin("fwd", dt, weight):
+            shp = self.out_shape(n, h, w)
+            y = torch.empty(shp, dtype=out_dtype, device=x.device)
+            g = self._geom(n, h, w, self.cin, shp[1], shp[2], self.cout, self.k, self.stride, self.pad, 0)
+            _lib.call("vp_thin_conv_fwd", C.byref(g), _ptr(x), _ptr(weight.detach()), _ptr(bias), _ptr(y), _code(out_dtype),
+                      ACT[act], float(slope), _stream())
+            return y
         wp = self._packed(weight.detach(), "fwd", dt)
         shp = self.out_shape(n, h, w)
         y = torch.empty(shp, dtype=out_dtype, device=x.device)
@@ -187,6 +207,11 @@ class TapLayer:
         n, h, w, _ = x_shape
         dt = dy.dtype
         out_dtype = out_dtype or dt
+        if self._thin("dgrad", dt, weight):
+            dx = torch.empty(x_shape, dtype=out_dtype, device=dy.device)
+            g = self._geom(n, h, w, self.cin, dy.shape[1], dy.shape[2], self.cout, self.k, self.stride, self.pad, 0)
+            _lib.call("vp_thin_conv_dgrad", C.byref(g), _ptr(dy), _ptr(weight.detach()), _ptr(dx), _code(out_dtype), _stream())
+            return dx
         wp = self._packed(weight.detach(), "dgrad", dt)
         dx = torch.empty(x_shape, dtype=out_dtype, device=dy.device)
         if self.kind == "flatten_in":
@@ -209,6 +234,11 @@ class TapLayer:
     def wgrad(self, x, dy, weight):
         n, h, w, _ = x.shape
         dt = x.dtype
+        if self._thin("wgrad", dt, weight):
+            dw = _grad_target(weight)
+            g = self._geom(n, h, w, self.cin, dy.shape[1], dy.shape[2], self.cout, self.k, self.stride, self.pad, 0)
+            _lib.call("vp_thin_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), _stream())
+            return dw
         p: Pack = self.p_wgrad
         dwp = torch.empty(p.taps * p.n * p.k, dtype=torch.float32, device=x.device)
         if self.kind == "flatten_out":
