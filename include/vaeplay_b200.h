@@ -178,6 +178,19 @@ int vp_pad_rows(const float* src, void* dst, int dtype, int64_t rows, int cols, 
 /* dst[r*cols + c] = src[r*src_cols + c]  (fp32 -> fp32): drops the padding columns of a weight-gradient panel */
 int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_cols, void* stream);
 
+/* ---- contractions on the module's own weight (no packed panels) -----------------------------------------------------
+ * w_cl: bf16 copy of the layer's weight in channels-last element order, i.e. exactly the bytes of the nn.Parameter when it is
+ * kept in torch.channels_last memory format: nn.Conv2d [co][kh][kw][ci], nn.ConvTranspose2d [ci][kh][kw][co], nn.Linear
+ * [out][in].  The TMA reads it in place, as a K-major or an MN-major tcgen05 operand depending on the direction.
+ * dw_cl: fp32 gradient in the same element order, zeroed by the call.  bf16 activations, tcgen05 engine only:
+ * VP_EUNSUPPORTED when the shape is not eligible (reduction channels not a multiple of 64, ...). */
+int vp_conv_fwd_cl(const VpConvGeom* g, const void* x, const void* w_cl, const float* bias, void* y, int out_dtype,
+                   int act, float slope, void* stream);
+int vp_conv_dgrad_cl(const VpConvGeom* g, const void* dy, const void* w_cl, void* dx, int out_dtype, void* stream);
+int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, void* stream);
+/* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
+int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
+
 /* ---- thin layers on tcgen05, straight from the fp32 master weight ------------------------------------------------
  * Convolutions with a single channel on one side: the first EncoderBlock conv (models/networks.py:14 with
  * channel_in = 1), the decoder's output conv (models/networks.py:101) and their gradients.  x / dy / y are bf16

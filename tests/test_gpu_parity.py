@@ -385,8 +385,8 @@ def test_vae_step_vs_oracle(vp, mode, img, cin, b, seed):
 # size-independent properties at the benchmark size (B=256, 64x64): adjointness of fwd/dgrad/wgrad,
 # normalisation invariants, loss identities
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("kind,cin,cout,hw", [("conv", 64, 128, 32), ("convT", 256, 128, 16), ("conv", 1, 64, 64),
-                                              ("flatten_in", 256, 1024, 8), ("flatten_out", 128, 256, 1)])
+@pytest.mark.parametrize("kind,cin,cout,hw", [("conv", 64, 128, 32), ("convT", 256, 128, 16), ("conv", 1, 64, 64), ("conv_out", 64, 1, 64),
+                                              ("linear", 16384, 1024, 1), ("linear", 128, 16384, 1)])
 def test_adjoint_identities_full_size(vp, mode, kind, cin, cout, hw):
     import vae_play_b200.functional as VF
     torch.manual_seed(3)
@@ -398,12 +398,14 @@ def test_adjoint_identities_full_size(vp, mode, kind, cin, cout, hw):
     elif kind == "convT":
         layer = VF.TapLayer("convT", cin, cout, k=5, stride=2, pad=2, out_pad=1)
         w = torch.randn(cin, cout, 5, 5, device="cuda") * 0.05
-    elif kind == "flatten_in":
-        layer = VF.TapLayer("flatten_in", cin, cout, spatial=8)
-        w = torch.randn(cout, cin * 64, device="cuda") * 0.05
+    elif kind == "conv_out":
+        layer = VF.TapLayer("conv", cin, cout, k=5, stride=1, pad=2)
+        w = torch.randn(cout, cin, 5, 5, device="cuda") * 0.05
     else:
-        layer = VF.TapLayer("flatten_out", cin, cout, spatial=8)
-        w = torch.randn(cout * 64, cin, device="cuda") * 0.05
+        layer = VF.TapLayer("linear", cin, cout)
+        w = torch.randn(cout, cin, device="cuda") * 0.05
+    if w.dim() == 4 and cin % 64 == 0 and cout % 64 == 0:
+        w = w.contiguous(memory_format=torch.channels_last)      # the in-place (no packing) route in bf16 mode
     x = torch.randn(B, hw, hw, cin, device="cuda").to(dt)
     y = layer.fwd(x, w, None)
     dy = torch.randn(y.shape, device="cuda").to(dt)
@@ -461,8 +463,11 @@ TC_SHAPES = [
     # kind, cin, cout, hw, batch
     ("conv", 64, 128, 32, 4), ("conv", 128, 256, 16, 4), ("conv", 64, 128, 32, 3),
     ("convT", 256, 256, 8, 4), ("convT", 256, 128, 16, 2), ("convT", 128, 64, 32, 2),
-    ("flatten_in", 256, 1024, 8, 16), ("flatten_out", 128, 256, 1, 16), ("linear", 1024, 256, 1, 40),
+    ("linear", 16384, 1024, 1, 16), ("linear", 128, 16384, 1, 16), ("linear", 1024, 256, 1, 40),
     ("conv_s1", 64, 1, 64, 2), ("conv_s1", 64, 3, 32, 2), ("conv_k3", 64, 96, 20, 3),
+    # channels-last weights: forward / dgrad / wgrad on the module's own weight (K-major and MN-major operands), no packing
+    ("conv_cl", 64, 128, 32, 4), ("conv_cl", 128, 256, 16, 3), ("convT_cl", 256, 256, 8, 4), ("convT_cl", 256, 128, 16, 2),
+    ("convT_cl", 128, 64, 32, 2), ("conv_s1_cl", 64, 128, 24, 2), ("conv_k3_cl", 128, 64, 20, 3),
 ]
 
 
@@ -470,6 +475,9 @@ def _tc_layer(kind, cin, cout):
     import vae_play_b200.functional as VF
     g = torch.Generator(device="cuda").manual_seed(11)
     r = lambda *s: torch.randn(*s, device="cuda", generator=g) * 0.05
+    if kind.endswith("_cl"):
+        layer, w = _tc_layer(kind[:-3], cin, cout)
+        return layer, w.contiguous(memory_format=torch.channels_last)
     if kind == "conv":
         return VF.TapLayer("conv", cin, cout, k=5, stride=2, pad=2), r(cout, cin, 5, 5)
     if kind == "conv_s1":
@@ -478,10 +486,6 @@ def _tc_layer(kind, cin, cout):
         return VF.TapLayer("conv", cin, cout, k=3, stride=1, pad=1), r(cout, cin, 3, 3)
     if kind == "convT":
         return VF.TapLayer("convT", cin, cout, k=5, stride=2, pad=2, out_pad=1), r(cin, cout, 5, 5)
-    if kind == "flatten_in":
-        return VF.TapLayer("flatten_in", cin, cout, spatial=8), r(cout, cin * 64)
-    if kind == "flatten_out":
-        return VF.TapLayer("flatten_out", cin, cout, spatial=8), r(cout * 64, cin)
     return VF.TapLayer("linear", cin, cout), r(cout, cin)
 
 
@@ -606,8 +610,7 @@ def test_thin_tc_kernels(vp, cin, cout, k, stride, hw, b):
 
 
 @pytest.mark.parametrize("kind,cin,cout,k,S", [("conv", 64, 128, 5, 1), ("conv", 3, 64, 5, 1), ("convT", 128, 64, 5, 1),
-                                                ("conv", 40, 96, 3, 1), ("flatten_in", 64, 96, 1, 8), ("flatten_out", 32, 64, 1, 8),
-                                                ("linear", 96, 40, 1, 1)])
+                                                ("conv", 40, 96, 3, 1), ("linear", 96, 40, 1, 1)])
 def test_pack_unpack_bit_exact(vp, kind, cin, cout, k, S):
     """Weight packing is index shuffling: bit-exact against the host emulation, and unpack inverts it."""
     import vae_play_b200.functional as VF
@@ -617,15 +620,11 @@ def test_pack_unpack_bit_exact(vp, kind, cin, cout, k, S):
         layer, shape = VF.TapLayer("conv", cin, cout, k=k, stride=1, pad=k // 2), (cout, cin, k, k)
     elif kind == "convT":
         layer, shape = VF.TapLayer("convT", cin, cout, k=k, stride=2, pad=2, out_pad=1), (cin, cout, k, k)
-    elif kind == "flatten_in":
-        layer, shape = VF.TapLayer("flatten_in", cin, cout, spatial=S), (cout, cin * S * S)
-    elif kind == "flatten_out":
-        layer, shape = VF.TapLayer("flatten_out", cin, cout, spatial=S), (cout * S * S, cin)
     else:
         layer, shape = VF.TapLayer("linear", cin, cout), (cout, cin)
     w = torch.randn(*shape, device="cuda")
     for which in ("fwd", "dgrad"):
-        p = getattr(layer, "p_" + which)
+        p = layer._recipe(which, w)
         wp = torch.empty(p.taps * p.n * p.k, dtype=torch.float32, device="cuda")
         _lib.call("vp_pack_weight", VF._ptr(w), VF._ptr(wp), 0, p.taps, p.n, p.k, p.sn, p.sk, p.st, VF._stream())
         want = _emulate_pack(w.cpu().numpy(), p)

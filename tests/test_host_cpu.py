@@ -63,6 +63,7 @@ def test_init_parameters_matches_reference_scale():
 
 
 def _emulate_pack(w, p):
+    """w: flat storage of the weight (physical element order)."""
     w = np.asarray(w).ravel()
     out = np.empty((p.taps, p.n, p.k), w.dtype)
     for t in range(p.taps):
@@ -71,44 +72,52 @@ def _emulate_pack(w, p):
     return out
 
 
-def test_pack_recipes():
+def _storage(w):
+    return torch.as_strided(w, (w.numel(),), (1,)).numpy()
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_pack_recipes(channels_last):
+    """Pack recipes are derived from the weight's strides: the same panels come out of a torch-contiguous and of a
+    channels-last weight."""
     from vae_play_b200.functional import TapLayer
-    rs = np.random.RandomState(0)
+    torch.manual_seed(0)
+    fmt = torch.channels_last if channels_last else torch.contiguous_format
     # conv: Wp[t][co][ci] = w[co][ci][ky][kx]
-    w = rs.randn(6, 4, 3, 3)
+    w = torch.randn(6, 4, 3, 3, dtype=torch.float64).contiguous(memory_format=fmt)
     L = TapLayer("conv", 4, 6, k=3, stride=1, pad=1)
-    assert np.array_equal(_emulate_pack(w, L.p_fwd), w.reshape(6, 4, 9).transpose(2, 0, 1))
-    assert np.array_equal(_emulate_pack(w, L.p_dgrad), w.reshape(6, 4, 9).transpose(2, 1, 0))
+    ref = w.numpy().reshape(6, 4, 9)
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("fwd", w)), ref.transpose(2, 0, 1))
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("dgrad", w)), ref.transpose(2, 1, 0))
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("wgrad", w)), ref.transpose(2, 0, 1))
     # convT: weight [ci][co][ky][kx]
-    w = rs.randn(4, 6, 3, 3)
+    w = torch.randn(4, 6, 3, 3, dtype=torch.float64).contiguous(memory_format=fmt)
     L = TapLayer("convT", 4, 6, k=3, stride=2, pad=1, out_pad=1)
-    assert np.array_equal(_emulate_pack(w, L.p_fwd), w.reshape(4, 6, 9).transpose(2, 1, 0))
-    assert np.array_equal(_emulate_pack(w, L.p_dgrad), w.reshape(4, 6, 9).transpose(2, 0, 1))
-    # flatten_in: Linear weight [out, C*S*S] with NCHW flatten  ->  taps over the SxS map
-    C_, S, out = 3, 2, 5
-    w = rs.randn(out, C_ * S * S)
-    L = TapLayer("flatten_in", C_, out, spatial=S)
-    assert np.array_equal(_emulate_pack(w, L.p_fwd), w.reshape(out, C_, S * S).transpose(2, 0, 1))
-    # dgrad packing [T][C][out] read as a plain [T*C, out] matrix maps dh -> channels-last dx
-    wp = _emulate_pack(w, L.p_dgrad).reshape(S * S * C_, out)
-    dh = rs.randn(2, out)
-    dx_cl = dh @ wp.T                                     # [B, (t, c)]
-    dx_ref = (dh @ w).reshape(2, C_, S * S).transpose(0, 2, 1).reshape(2, -1)
-    assert np.allclose(dx_cl, dx_ref)
-    # flatten_out: Linear weight [C*S*S, z], output viewed [B,C,S,S]
-    z = 4
-    w = rs.randn(C_ * S * S, z)
-    L = TapLayer("flatten_out", z, C_, spatial=S)
-    wp = _emulate_pack(w, L.p_fwd).reshape(S * S * C_, z)
-    zz = rs.randn(2, z)
-    y_cl = zz @ wp.T
-    y_ref = (zz @ w.T).reshape(2, C_, S * S).transpose(0, 2, 1).reshape(2, -1)
-    assert np.allclose(y_cl, y_ref)
-    wpd = _emulate_pack(w, L.p_dgrad)                    # [T][z][C]
-    dy_cl = rs.randn(2, S * S, C_)
-    dz = np.einsum("btc,tkc->bk", dy_cl, wpd)
-    dz_ref = dy_cl.transpose(0, 2, 1).reshape(2, -1) @ w
-    assert np.allclose(dz, dz_ref)
+    ref = w.numpy().reshape(4, 6, 9)
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("fwd", w)), ref.transpose(2, 1, 0))
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("dgrad", w)), ref.transpose(2, 0, 1))
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("wgrad", w)), ref.transpose(2, 0, 1))
+    # linear: weight [out][in]
+    w = torch.randn(5, 7, dtype=torch.float64)
+    L = TapLayer("linear", 7, 5)
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("fwd", w))[0], w.numpy())
+    assert np.array_equal(_emulate_pack(_storage(w), L._recipe("dgrad", w))[0], w.numpy().T)
+
+
+def test_weights_channels_last_keeps_state_dict():
+    """Conv weights are kept in channels-last memory order: shapes, values and state_dict keys are unchanged and a
+    checkpoint written from them loads into a plain contiguous module."""
+    from vae_play_b200.models.networks import DecoderBlock, EncoderBlock
+    torch.manual_seed(0)
+    blk, ref = EncoderBlock(64, 128), torch.nn.Conv2d(64, 128, 5, padding=2, stride=2, bias=False)
+    assert blk.conv.weight.shape == ref.weight.shape
+    assert blk.conv.weight.is_contiguous(memory_format=torch.channels_last) and not blk.conv.weight.is_contiguous()
+    ref.load_state_dict({"weight": blk.state_dict()["conv.weight"]})
+    assert torch.equal(ref.weight, blk.conv.weight)
+    blk.load_state_dict({**blk.state_dict(), "conv.weight": ref.weight.detach() * 2})
+    assert blk.conv.weight.is_contiguous(memory_format=torch.channels_last) and torch.equal(blk.conv.weight, ref.weight * 2)
+    assert DecoderBlock(128, 64).conv.weight.is_contiguous(memory_format=torch.channels_last)
+    assert EncoderBlock(1, 64).conv.weight.is_contiguous()          # single-channel layers stay torch-contiguous (thin kernels)
 
 
 def test_philox_policy_matches_oracle():

@@ -61,6 +61,10 @@ SIGNATURES = {
     "vp_im2col": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "vp_pad_rows": [_p, _p, _i, _i64, _i, _i, _p],
     "vp_unpad_rows": [_p, _p, _i64, _i, _i, _p],
+    "vp_conv_fwd_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
+    "vp_conv_dgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
+    "vp_conv_wgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
+    "vp_transpose_bt": [_p, _p, _i, _i, _i, _i, _p],
     "vp_thin_conv_fwd": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
     "vp_thin_conv_dgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
     "vp_thin_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _p],

@@ -94,11 +94,17 @@ int run_tapgemm(const TapGemm& p, int dtype, int engine, cudaStream_t s) {
 
 // forward == true : small side is the input (A), large side the output (conv fwd / convT dgrad -> gather;
 //                                                                       convT fwd / conv dgrad -> scatter)
+// wlay: 0 = packed panels Wp[tap][N][K]; 1 = the module's weight in channels-last order [d0][kh][kw][d1] read in place, with
+// (N, K) = (d0, d1) -> K-major operand; 2 = same with (N, K) = (d1, d0) -> MN-major operand
 int conv_like(const VpConvGeom& g, bool gather, const void* A, int ha, int wa, int K, void* D, int hd, int wd, int N,
-              const void* wp, const float* bias, int act, float slope, int dtype, int out_dtype, int engine, cudaStream_t s) {
+              const void* wp, const float* bias, int act, float slope, int dtype, int out_dtype, int engine, cudaStream_t s, int wlay = 0) {
     TapGemm p;
     memset(&p, 0, sizeof(p));
     p.out_dtype = out_dtype;
+    const int64_t T = (int64_t)g.kh * g.kw;
+    if (wlay == 0) { p.w_st = (int64_t)N * K; p.w_sn = K; p.w_sk = 1; }
+    else if (wlay == 1) { p.w_st = K; p.w_sn = T * K; p.w_sk = 1; }
+    else { p.w_st = N; p.w_sn = 1; p.w_sk = T * N; }
     p.A = A; p.Wp = wp; p.D = D; p.bias = bias;
     p.n = g.n; p.ha = ha; p.wa = wa; p.K = K; p.hd = hd; p.wd = wd; p.N = N;
     p.act = act; p.slope = slope;
@@ -170,15 +176,10 @@ extern "C" int vp_conv_dgrad(const VpConvGeom* g, const void* dy, const void* wp
                      dtype, out_dtype, engine, (cudaStream_t)stream);
 }
 
-extern "C" int vp_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dwp, int dtype, int engine,
-                             void* stream) {
-    if (!check_geom(g, "vp_conv_wgrad")) return VP_EINVAL;
-    VP_CHECK_ARG(x && dy && dwp, "vp_conv_wgrad: null pointer");
-    VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_conv_wgrad: bad dtype %d", dtype);
-    cudaStream_t s = (cudaStream_t)stream;
-    TapWgrad p;
+namespace {
+void fill_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, bool channels_last, TapWgrad& p) {
     memset(&p, 0, sizeof(p));
-    p.n = g->n; p.as = g->stride; p.dWp = dwp;
+    p.n = g->n; p.as = g->stride; p.dWp = dw;
     gather_taps(*g, p.taps);
     if (!g->transposed) {
         p.G = dy; p.gh = g->ho; p.gw = g->wo; p.GC = g->co;
@@ -187,6 +188,47 @@ extern "C" int vp_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy,
         p.G = x; p.gh = g->hi; p.gw = g->wi; p.GC = g->ci;
         p.A = dy; p.ha = g->ho; p.wa = g->wo; p.AC = g->co;
     }
+    if (channels_last) { p.o_st = p.AC; p.o_sg = (int64_t)p.taps.ntaps * p.AC; }     // [GC][kh][kw][AC]
+    else { p.o_st = (int64_t)p.GC * p.AC; p.o_sg = p.AC; }                            // [taps][GC][AC]
+}
+}  // namespace
+
+/* ---- the same contractions with the weight read / the gradient written IN PLACE (no packed panels) ----------------
+ * w_cl: the bf16 copy of the module's weight in channels-last element order: nn.Conv2d [co][kh][kw][ci], nn.ConvTranspose2d
+ * [ci][kh][kw][co], nn.Linear [out][in].  dw_cl: fp32 gradient in the same element order (zeroed by the call). */
+extern "C" int vp_conv_fwd_cl(const VpConvGeom* g, const void* x, const void* w_cl, const float* bias, void* y, int out_dtype, int act,
+                              float slope, void* stream) {
+    if (!check_geom(g, "vp_conv_fwd_cl")) return VP_EINVAL;
+    VP_CHECK_ARG(x && w_cl && y, "vp_conv_fwd_cl: null pointer");
+    return conv_like(*g, !g->transposed, x, g->hi, g->wi, g->ci, y, g->ho, g->wo, g->co, w_cl, bias, act, slope, VP_BF16, out_dtype,
+                     VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 2 : 1);
+}
+
+extern "C" int vp_conv_dgrad_cl(const VpConvGeom* g, const void* dy, const void* w_cl, void* dx, int out_dtype, void* stream) {
+    if (!check_geom(g, "vp_conv_dgrad_cl")) return VP_EINVAL;
+    VP_CHECK_ARG(dy && w_cl && dx, "vp_conv_dgrad_cl: null pointer");
+    return conv_like(*g, g->transposed != 0, dy, g->ho, g->wo, g->co, dx, g->hi, g->wi, g->ci, w_cl, nullptr, VP_ACT_NONE, 0.f, VP_BF16,
+                     out_dtype, VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 1 : 2);
+}
+
+extern "C" int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, void* stream) {
+    if (!check_geom(g, "vp_conv_wgrad_cl")) return VP_EINVAL;
+    VP_CHECK_ARG(x && dy && dw_cl, "vp_conv_wgrad_cl: null pointer");
+    cudaStream_t s = (cudaStream_t)stream;
+    TapWgrad p;
+    fill_wgrad(g, x, dy, dw_cl, true, p);
+    cudaMemsetAsync(dw_cl, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    return launch_tapwgrad_tc(p, s);
+}
+
+extern "C" int vp_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dwp, int dtype, int engine,
+                             void* stream) {
+    if (!check_geom(g, "vp_conv_wgrad")) return VP_EINVAL;
+    VP_CHECK_ARG(x && dy && dwp, "vp_conv_wgrad: null pointer");
+    VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_conv_wgrad: bad dtype %d", dtype);
+    cudaStream_t s = (cudaStream_t)stream;
+    TapWgrad p;
+    fill_wgrad(g, x, dy, dwp, false, p);
     cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     if (engine != VP_ENGINE_SIMT && dtype == VP_BF16) {
         const int rc = launch_tapwgrad_tc(p, s);

@@ -109,6 +109,10 @@ struct TapGemm {
     int act;
     float slope;
     int out_dtype;  // dtype of D (VP_F32 / VP_BF16); A and Wp are in the call's dtype
+    // weight addressing (tcgen05 engine): element (tap, n, k) at Wp[tap*w_st + n*w_sn + k*w_sk].  Packed panels: w_st = N*K,
+    // w_sn = K, w_sk = 1.  One of w_sn / w_sk must be 1: w_sk == 1 is a K-major operand, w_sn == 1 an MN-major one
+    // (the module's own channels-last weight read without any re-packing).
+    int64_t w_st, w_sn, w_sk;
     TapList taps;
 };
 
@@ -116,7 +120,8 @@ struct TapGemm {
 struct TapWgrad {
     const void* G;  // [n, gh, gw, GC]
     const void* A;  // [n, ha, wa, AC]
-    float* dWp;     // [taps][GC][AC]
+    float* dWp;     // [taps][GC][AC] (packed) or any layout with AC contiguous: element (tap, gc, ac) at tap*o_st + gc*o_sg + ac
+    int64_t o_st, o_sg;
     int n, gh, gw, GC;
     int ha, wa, AC;
     int as;

@@ -673,3 +673,35 @@ extern "C" int vp_unpad_rows(const float* src, float* dst, int64_t rows, int col
     VP_CHECK_LAUNCH("vp_unpad_rows");
     return VP_OK;
 }
+
+// ---- batched transpose (same dtype): dst[b][c][r] = src[b][r][c] ---------------------------------------------------------
+// The NCHW-flatten Linear layers (models/networks.py:65,74-75 and :88,110) see the 8x8 map in (c, y, x) order while the
+// activations are channels-last: a [B][64][C] <-> [B][C][64] transpose on either side lets them run as plain Linear layers
+// on the module's own weight.
+namespace vp {
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_bt_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols) {
+    __shared__ T tile[32][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const T* s = src + (int64_t)b * rows * cols;
+    T* d = dst + (int64_t)b * rows * cols;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < rows && c0 + tx < cols) tile[i][tx] = s[(int64_t)(r0 + i) * cols + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < cols && r0 + tx < rows) d[(int64_t)(c0 + i) * rows + r0 + tx] = tile[tx][i];
+}
+}  // namespace
+}  // namespace vp
+
+extern "C" int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream) {
+    VP_CHECK_ARG(src && dst && batch > 0 && rows > 0 && cols > 0 && batch <= 65535, "vp_transpose_bt: bad arguments");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
+    if (dtype == VP_F32) transpose_bt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, cols);
+    else transpose_bt_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, cols);
+    VP_CHECK_LAUNCH("vp_transpose_bt");
+    return VP_OK;
+}

@@ -38,6 +38,22 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Tensor map of the weight operand of a tap GEMM: element (tap, n, k) at Wp[tap*w_st + n*w_sn + k*w_sk] (bf16).
+// K-major (w_sk == 1): dims {K, N, taps}, box {64, BN, 1}.  MN-major (w_sn == 1): dims {N, K, taps}, box {64, 64, 1}.
+int encode_weight_map(CUtensorMap* m, const TapGemm& p, bool bmn, int BN) {
+    EncodeTiledFn encode = get_encode();
+    const int64_t s1 = bmn ? p.w_sk : p.w_sn;
+    cuuint64_t dims[3] = {(cuuint64_t)(bmn ? p.N : p.K), (cuuint64_t)(bmn ? p.K : p.N), (cuuint64_t)kMaxTaps};
+    cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)p.w_st * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)(bmn ? 64 : BN), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    if ((strides[0] & 15) != 0 || (strides[1] & 15) != 0) return -1;
+    // the tap extent is only an upper bound for the descriptor; taps actually addressed are < the real count
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.Wp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
@@ -64,6 +80,18 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 using namespace tc;
 
 constexpr int kMaxPhases = 4;
+constexpr int kBoxBytes = 64 * 128;  // {64 channels, 64 rows} bf16 box of an MN-major operand
+
+// MN-major SWIZZLE_128B operand: 8-row (K) atoms of 1024 B, LBO = next 64-wide MN group (one box), 16 K rows per MMA = 2048 B
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(kBoxBytes >> 4) << 16;   // LBO: next 64-wide MN group
+    d |= (uint64_t)(1024 >> 4) << 32;        // SBO: next 8 K rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 
 struct TcPhase {
     int gh, gw;            // iteration grid of this phase
@@ -118,7 +146,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int q, int B
 // (all output-parity phases of a transposed conv / strided dgrad are in ONE launch).  The smem ring runs across
 // tile boundaries and the accumulator is double-buffered in TMEM (2 x BN columns), so the epilogue of tile i
 // overlaps the TMA/MMA main loop of tile i+1.
-template <int BN, int STAGES, int CTAS_PER_SM>
+template <int BN, int STAGES, int CTAS_PER_SM, bool BMN>
 __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB,
                                                                  const __grid_constant__ TcParams p) {
@@ -177,14 +205,20 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                         tma_load_4d(sa, &mapA, &full[s], kb * kBlockK, tc.gx0 * p.as + ph.taps.tx[t], tc.gy0 * p.as + ph.taps.ty[t], tc.n0);
                     } else {
                         mbar_expect_tx(&full[s], L::kBBytes);
-                        tma_load_3d(sa + kABytes, &mapB, &full[s], kb * kBlockK, tc.col0, ph.taps.widx[t]);
+                        if constexpr (BMN) {      // weight read in place, N contiguous: 64 (n) x 64 (k) boxes = MN-major atoms
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_3d(sa + kABytes + j * kBoxBytes, &mapB, &full[s], tc.col0 + 64 * j, kb * kBlockK, ph.taps.widx[t]);
+                        } else {
+                            tma_load_3d(sa + kABytes, &mapB, &full[s], kb * kBlockK, tc.col0, ph.taps.widx[t]);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = idesc_bf16_f32(kBlockM, BN < 16 ? 16 : BN);
+        constexpr uint32_t idesc = idesc_bf16_f32(kBlockM, BN < 16 ? 16 : BN) | (BMN ? (1u << 16) : 0u);
         if (elect_one()) {
             uint32_t g = 0, i = 0;
             for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
@@ -200,10 +234,10 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + s * L::kStageBytes);
                     const uint64_t adesc = smem_desc_k_sw128(sa);
-                    const uint64_t bdesc = smem_desc_k_sw128(sa + kABytes);
+                    const uint64_t bdesc = BMN ? smem_desc_mn_sw128(sa + kABytes) : smem_desc_k_sw128(sa + kABytes);
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k)   // +32 bytes along K per UMMA_K=16: +2 in the (addr >> 4) field
-                        tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    for (int k = 0; k < kBlockK / 16; ++k)   // per UMMA_K=16: K-major +32 B (+2 in the addr>>4 field), MN-major +16 rows = 2048 B (+128)
+                        tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * (BMN ? 128 : 2)), idesc, (it | k) != 0);
                     tc_commit(&empty[s]);
                 }
                 tc_commit(&acc_full[buf]);
@@ -253,19 +287,19 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
-template <int BN, int STAGES, int CTAS>
+template <int BN, int STAGES, int CTAS, bool BMN = false>
 int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp, cudaStream_t s) {
     using L = SmemLayout<BN, STAGES>;
     constexpr int smem_bytes = L::kTotal + 1024;  // + alignment slack
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, CTAS, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) { set_error("tapgemm_tc: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = true;
     }
     const int slots = num_sms() * CTAS;
     const int grid = tp.total_tiles < slots ? tp.total_tiles : slots;
-    tapgemm_tc_kernel<BN, STAGES, CTAS><<<grid, kFwdThreads, smem_bytes, s>>>(mA, mB, tp);
+    tapgemm_tc_kernel<BN, STAGES, CTAS, BMN><<<grid, kFwdThreads, smem_bytes, s>>>(mA, mB, tp);
     VP_CHECK_LAUNCH("tapgemm_tc");
     return VP_OK;
 }
@@ -324,7 +358,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     const int bt = kBlockM / (wt * ht);
     tp.bt = bt; tp.ht = ht; tp.wt = wt;
     const int tiles_b = (p.n + bt - 1) / bt;
-    const bool one_cta = tc_variant() == 1;
+    const bool one_cta = tc_variant() == 1 && p.w_sk == 1;
     const int BN = (one_cta && p.N % 256 == 0) ? 256 : (p.N % 128 == 0) ? 128 : (p.N >= 64 ? 64 : (p.N > 16 ? 32 : 16));
     tp.ntiles_n = (p.N + BN - 1) / BN;
     int64_t mtiles = 0;
@@ -352,18 +386,10 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return VP_EUNSUPPORTED; }
     }
-    {
-        // the tap extent is only an upper bound for the descriptor; taps actually addressed are < the packed count
-        cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.N, (cuuint64_t)kMaxTaps};
-        cuuint64_t strides[2] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.N * p.K * 2};
-        cuuint32_t box[3] = {(cuuint32_t)kBlockK, (cuuint32_t)BN, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        if ((strides[1] & 15) != 0) { set_error("tcgen05 engine: weight tap stride not 16-byte aligned"); return VP_EUNSUPPORTED; }
-        CUresult r = encode(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.Wp), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return VP_EUNSUPPORTED; }
-    }
+    const bool bmn = p.w_sn == 1 && p.w_sk != 1;
+    if (!bmn && p.w_sk != 1) { set_error("tcgen05 engine: weight operand must be contiguous along K or along N"); return VP_EUNSUPPORTED; }
+    if (bmn && (p.N % 64 != 0 || BN < 64)) { set_error("tcgen05 engine: MN-major weights need N %% 64 == 0"); return VP_EUNSUPPORTED; }
+    if (encode_weight_map(&mB, p, bmn, BN)) { set_error("tcgen05 engine: cuTensorMapEncodeTiled(B) failed"); return VP_EUNSUPPORTED; }
     tp.D = p.D; tp.bias = p.bias; tp.n = p.n; tp.hd = p.hd; tp.wd = p.wd; tp.N = p.N;
     tp.as = p.as; tp.ds = p.ds; tp.act = p.act; tp.slope = p.slope;
     tp.out_f32 = (p.out_dtype == VP_F32); tp.kblocks = p.K / kBlockK;
@@ -376,6 +402,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
             default: return launch_cfg<16, 8, 1>(mA, mB, tp, s);
         }
     }
+    if (bmn) return BN == 128 ? launch_cfg<128, 3, 2, true>(mA, mB, tp, s) : launch_cfg<64, 4, 2, true>(mA, mB, tp, s);
     // default: two persistent CTAs per SM (two TMA issue streams, two epilogues in flight), <= 113 KB smem and
     // <= 256 TMEM columns each
     switch (BN) {
@@ -400,23 +427,13 @@ int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s) { return launch_tapgemm_
 // =====================================================================================================
 namespace {
 
-constexpr int kBoxBytes = 64 * 128;  // {64 channels, 64 pixels} bf16
-
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
-    d |= (uint64_t)(kBoxBytes >> 4) << 16;   // LBO: next 64-wide MN group
-    d |= (uint64_t)(1024 >> 4) << 32;        // SBO: next 8 K rows
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int m, int n) {
     return idesc_bf16_f32(m, n) | (1u << 15) | (1u << 16);   // A and B MN-major
 }
 
 struct TcWgradParams {
     float* dWp;
+    int64_t o_st, o_sg;        // element (tap, gc, ac) at dWp[tap*o_st + gc*o_sg + ac]
     int GC, AC;
     int as;
     int bt, ht, wt;            // pixel brick, bt*ht*wt == 64
@@ -523,7 +540,7 @@ __global__ void __launch_bounds__(kFwdThreads) tapwgrad_tc_kernel(const __grid_c
         const int gc = m0 + lane_base + lane;
         mbar_wait(acc_ready, 0);
         tc_fence_after();
-        float* out = p.dWp + ((int64_t)p.taps.widx[tap] * p.GC + gc) * p.AC + c0;
+        float* out = p.dWp + (int64_t)p.taps.widx[tap] * p.o_st + (int64_t)gc * p.o_sg + c0;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
@@ -612,7 +629,7 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
     if (nsplit > 65535) nsplit = 65535;
     tp.bricks_per_split = (tp.nbricks + nsplit - 1) / nsplit;
     nsplit = (tp.nbricks + tp.bricks_per_split - 1) / tp.bricks_per_split;
-    tp.dWp = p.dWp; tp.GC = p.GC; tp.AC = p.AC; tp.as = p.as; tp.taps = p.taps;
+    tp.dWp = p.dWp; tp.o_st = p.o_st; tp.o_sg = p.o_sg; tp.GC = p.GC; tp.AC = p.AC; tp.as = p.as; tp.taps = p.taps;
     CUtensorMap mG, mA;
     int r = encode_nhwc(&mG, p.G, p.GC, p.gw, p.gh, p.n, wt, ht, bt, 1);
     if (r) { set_error("tcgen05 wgrad: cuTensorMapEncodeTiled(G) failed (%d)", r); return VP_EUNSUPPORTED; }

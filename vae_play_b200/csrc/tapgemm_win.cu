@@ -68,7 +68,12 @@ __device__ __forceinline__ WTile wdecode(const WinParams& p, int q, int BN) {
     return c;
 }
 
-template <int BN, int BSTAGES>
+// MN-major SWIZZLE_128B weight tile (the module's channels-last weight read in place): 64 (n) x 64 (k) boxes, LBO = one box
+__device__ __forceinline__ uint64_t wdesc_mn_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+template <int BN, int BSTAGES, bool BMN>
 __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB,
                                                                    const __grid_constant__ WinParams p) {
@@ -139,13 +144,19 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
                         const int s = gb % BSTAGES;
                         mbar_wait(&b_empty[s], ((gb / BSTAGES) & 1) ^ 1);
                         mbar_expect_tx(&b_full[s], kBBytes);
-                        tma_load_3d(smem_b + s * kBBytes, &mapB, &b_full[s], kb * 64, t.col0, taps.widx[tp]);
+                        if constexpr (BMN) {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_3d(smem_b + s * kBBytes + j * 8192, &mapB, &b_full[s], t.col0 + 64 * j, kb * 64, taps.widx[tp]);
+                        } else {
+                            tma_load_3d(smem_b + s * kBBytes, &mapB, &b_full[s], kb * 64, t.col0, taps.widx[tp]);
+                        }
                     }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = idesc_bf16_f32(128, BN < 16 ? 16 : BN);
+        constexpr uint32_t idesc = idesc_bf16_f32(128, BN < 16 ? 16 : BN) | (BMN ? (1u << 16) : 0u);
         if (elect_one()) {
             uint32_t ga = 0, gb = 0, i = 0;
             const uint64_t sbo_field = (uint64_t)((p.Wh * 128) >> 4) << 32;
@@ -165,7 +176,7 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
                         const int sb_i = gb % BSTAGES;
                         mbar_wait(&b_full[sb_i], (gb / BSTAGES) & 1);
                         tc_fence_after();
-                        const uint64_t bdesc = smem_desc_k_sw128(smem_u32(smem_b + sb_i * kBBytes));
+                        const uint64_t bdesc = BMN ? wdesc_mn_sw128(smem_u32(smem_b + sb_i * kBBytes)) : smem_desc_k_sw128(smem_u32(smem_b + sb_i * kBBytes));
                         // window of the halo: first row (ty-tymin)*Wh + (tx-txmin); 16 groups of 8 rows, group stride Wh rows
                         const uint32_t woff = (uint32_t)((taps.ty[tp] - p.tymin) * p.Wh + (taps.tx[tp] - p.txmin)) * 128u;
 #pragma unroll
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
                                              ((uint64_t)2 << 61);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                tc_mma_bf16(tmem_d + br * kAccCols, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                tc_mma_bf16(tmem_d + br * kAccCols, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * (BMN ? 128 : 2)), idesc,
                                             (kb | tp | k) != 0);
                         }
                         tc_commit(&b_empty[sb_i]);
@@ -227,18 +238,18 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
     }
 }
 
-template <int BN, int BSTAGES>
+template <int BN, int BSTAGES, bool BMN = false>
 int launch_win(const CUtensorMap& mA, const CUtensorMap& mB, const WinParams& wp, cudaStream_t s) {
     const int smem_bytes = kAStages * 2 * wp.halo_bytes + BSTAGES * BN * 128 + (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024;
     if (smem_bytes > 227 * 1024) { set_error("windowed tap GEMM: %d bytes of shared memory", smem_bytes); return VP_EUNSUPPORTED; }
     static int attr_set = 0;
     if (attr_set < smem_bytes) {
-        cudaError_t e = cudaFuncSetAttribute(tapgemm_win_kernel<BN, BSTAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(tapgemm_win_kernel<BN, BSTAGES, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) { set_error("tapgemm_win: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = smem_bytes;
     }
     const int grid = wp.total_tiles < num_sms() ? wp.total_tiles : num_sms();
-    tapgemm_win_kernel<BN, BSTAGES><<<grid, kWThreads, smem_bytes, s>>>(mA, mB, wp);
+    tapgemm_win_kernel<BN, BSTAGES, BMN><<<grid, kWThreads, smem_bytes, s>>>(mA, mB, wp);
     VP_CHECK_LAUNCH("tapgemm_win");
     return VP_OK;
 }
@@ -297,16 +308,10 @@ int launch_tapgemm_win(const TapGemm* phases, int nphases, cudaStream_t s) {
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
             return VP_EUNSUPPORTED;
     }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)p.K, (cuuint64_t)p.N, (cuuint64_t)kMaxTaps};
-        cuuint64_t strides[2] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.N * p.K * 2};
-        cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
-        cuuint32_t estr[3] = {1, 1, 1};
-        if ((strides[1] & 15) != 0) return VP_EUNSUPPORTED;
-        if (encode(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(p.Wp), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return VP_EUNSUPPORTED;
-    }
+    const bool bmn = p.w_sn == 1 && p.w_sk != 1;
+    if ((!bmn && p.w_sk != 1) || (bmn && (p.N % 64 != 0 || BN < 64))) return VP_EUNSUPPORTED;
+    if (encode_weight_map(&mB, p, bmn, BN)) return VP_EUNSUPPORTED;
+    if (bmn) return BN == 128 ? launch_win<128, 5, true>(mA, mB, wp, s) : launch_win<64, 8, true>(mA, mB, wp, s);
     switch (BN) {
         case 128: return launch_win<128, 5>(mA, mB, wp, s);
         case 64: return launch_win<64, 8>(mA, mB, wp, s);

@@ -10,6 +10,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn get_encode();
+struct TapGemm;
+int encode_weight_map(CUtensorMap* m, const TapGemm& p, bool bmn, int BN);
 int pow2_floor(int v);
 int pow2_ceil(int v);
 int num_sms();

@@ -39,7 +39,7 @@ def _grad_target(weight):
     hit = _GRAD_SINKS.get(weight.data_ptr())
     if hit is not None:
         view, param = hit
-        if param.grad is None and view.shape == weight.shape:
+        if param.grad is None and view.shape == weight.shape and view.stride() == weight.stride():
             return view
     return torch.empty_like(weight, dtype=torch.float32)
 
@@ -100,45 +100,33 @@ class Pack:
     st: int
 
 
-class TapLayer:
-    """One contraction layer: how its forward / dgrad / wgrad map onto vp_conv_{fwd,dgrad,wgrad}.
+def weights_channels_last(module):
+    """Keep the conv weights of ``module`` in torch.channels_last memory format (same shapes, same ``state_dict``):
+    physically [co][kh][kw][ci] (nn.Conv2d) / [ci][kh][kw][co] (nn.ConvTranspose2d), which the TMA reads in place as a
+    tcgen05 operand for forward AND data gradient, and which the weight-gradient kernel writes in place -- no packed
+    copies, no unpack pass.  Only layers the in-place kernels take (both channel counts multiples of 64) are converted."""
+    for m in module.modules():
+        if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d)) and m.in_channels % 64 == 0 and m.out_channels % 64 == 0:
+            m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
+    return module
 
-    kind: 'conv' (nn.Conv2d), 'convT' (nn.ConvTranspose2d), 'linear' (nn.Linear on [B,in]),
-          'flatten_in'  (nn.Linear on the NCHW-flattened SxS map, models/networks.py:65,74-75),
-          'flatten_out' (nn.Linear whose output is viewed as [B,C,S,S], models/networks.py:88,110).
+
+class TapLayer:
+    """One contraction layer: how its forward / dgrad / wgrad map onto the kernel library.
+
+    kind: 'conv' (nn.Conv2d), 'convT' (nn.ConvTranspose2d), 'linear' (nn.Linear on [B,in]).
+    Three routes, chosen per call:
+      * in place  (vp_conv_*_cl):  bf16, both channel counts multiples of 64, weight dense in channels-last order
+      * thin      (vp_thin_conv_*): bf16, a single channel on one side
+      * packed    (vp_conv_*):      everything else, and the fp32 check mode (tap-major panels built by vp_pack_weight)
     """
 
-    def __init__(self, kind, cin, cout, k=1, stride=1, pad=0, out_pad=0, spatial=1):
-        self.kind, self.cin, self.cout = kind, cin, cout
-        self.k, self.stride, self.pad, self.out_pad, self.S = k, stride, pad, out_pad, spatial
-        self._cache = {}
-        T = k * k
-        if kind == "conv":
-            self.p_fwd = Pack(T, cout, cin, cin * T, T, 1)
-            self.p_dgrad = Pack(T, cin, cout, T, cin * T, 1)
-            self.p_wgrad = self.p_fwd
-        elif kind == "convT":
-            self.p_fwd = Pack(T, cout, cin, T, cout * T, 1)
-            self.p_dgrad = Pack(T, cin, cout, cout * T, T, 1)
-            self.p_wgrad = self.p_dgrad
-        elif kind == "linear":
-            self.p_fwd = Pack(1, cout, cin, cin, 1, 1)
-            self.p_dgrad = Pack(1, cin, cout, 1, cin, 1)
-            self.p_wgrad = self.p_fwd
-        elif kind == "flatten_in":
-            # weight [out, C*S*S] == conv weight [out, C, S, S]; cin = C
-            T = spatial * spatial
-            self.p_fwd = Pack(T, cout, cin, cin * T, T, 1)
-            self.p_dgrad = Pack(T, cin, cout, T, cin * T, 1)     # [T][C][out] == plain linear with N' = t*C + c
-            self.p_wgrad = self.p_fwd
-        elif kind == "flatten_out":
-            # weight [C*S*S, z]; cout = C, cin = z
-            T = spatial * spatial
-            self.p_fwd = Pack(T, cout, cin, T * cin, 1, cin)     # [T][C][z] == plain linear with N' = t*C + c
-            self.p_dgrad = Pack(T, cin, cout, 1, T * cin, cin)   # [T][z][C]: 'conv' over the SxS map
-            self.p_wgrad = self.p_dgrad
-        else:
+    def __init__(self, kind, cin, cout, k=1, stride=1, pad=0, out_pad=0):
+        if kind not in ("conv", "convT", "linear"):
             raise ValueError(kind)
+        self.kind, self.cin, self.cout = kind, cin, cout
+        self.k, self.stride, self.pad, self.out_pad = k, stride, pad, out_pad
+        self._cache = {}
 
     # ---- geometry -------------------------------------------------------------------------------
     def out_shape(self, n, h, w):
@@ -147,25 +135,67 @@ class TapLayer:
         if self.kind == "convT":
             return (n, (h - 1) * self.stride - 2 * self.pad + self.k + self.out_pad,
                     (w - 1) * self.stride - 2 * self.pad + self.k + self.out_pad, self.cout)
-        if self.kind in ("linear", "flatten_in"):
-            return (n, 1, 1, self.cout)
-        return (n, self.S, self.S, self.cout)
+        return (n, 1, 1, self.cout)
 
     def _geom(self, n, hi, wi, ci, ho, wo, co, k, stride, pad, transposed):
         return VpConvGeom(n, hi, wi, ci, ho, wo, co, k, k, stride, pad, transposed)
 
+    def _layer_geom(self, n, h, w, ho, wo):
+        return self._geom(n, h, w, self.cin, ho, wo, self.cout, self.k, self.stride, self.pad, int(self.kind == "convT"))
+
+    # ---- packed route ---------------------------------------------------------------------------------
+    def _recipe(self, which, weight) -> Pack:
+        """Pack recipe from the weight's actual strides (torch-contiguous or channels-last)."""
+        T = self.k * self.k
+        if weight.dim() == 2:
+            s_out, s_in, st = weight.stride(0), weight.stride(1), 1
+        else:
+            if weight.stride(2) != weight.shape[3] * weight.stride(3) and weight.shape[2] > 1:
+                raise _lib.VaePlayError("conv weight with non-uniform tap strides")
+            s_out, s_in, st = weight.stride(0), weight.stride(1), weight.stride(3)
+        if self.kind == "convT":
+            s_out, s_in = s_in, s_out       # weight is [cin][cout][kh][kw]
+        if (which == "dgrad") != (self.kind == "convT" and which == "wgrad"):
+            # [T][cin][cout]: dgrad panel; also the wgrad layout of a transposed conv
+            return Pack(T, self.cin, self.cout, s_in, s_out, st)
+        return Pack(T, self.cout, self.cin, s_out, s_in, st)
+
     def _packed(self, weight, which, dtype):
-        key = (which, dtype, weight.data_ptr(), weight._version, _EPOCH[0])
+        key = (which, dtype, weight.data_ptr(), weight._version, _EPOCH[0], weight.stride())
         hit = self._cache.get(which)
         if hit is not None and hit[0] == key:
             return hit[1]
-        p: Pack = getattr(self, "p_" + which)
+        p = self._recipe(which, weight)
         wp = torch.empty(p.taps * p.n * p.k, dtype=dtype, device=weight.device)
         _lib.call("vp_pack_weight", _ptr(weight), _ptr(wp), _code(dtype), p.taps, p.n, p.k, p.sn, p.sk, p.st, _stream())
         self._cache[which] = (key, wp)
         return wp
 
-    # ---- thin layers (<= 2 channels on one side): tcgen05 kernels that read the fp32 master weight directly ----
+    # ---- in-place route ---------------------------------------------------------------------------------
+    def _cl(self, dt, weight):
+        if dt != torch.bfloat16 or _STATE["engine"] == _lib.ENGINE_SIMT or self.cin % 64 or self.cout % 64:
+            return False
+        if weight.dim() == 4:
+            return weight.is_contiguous(memory_format=torch.channels_last)
+        return weight.is_contiguous()
+
+    def _shadow(self, weight):
+        """bf16 copy of the master weight, element for element (same strides)."""
+        hit = self._cache.get("shadow")
+        key = (weight.data_ptr(), weight._version, _EPOCH[0])
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        sh = hit[1] if hit is not None and hit[1].shape == weight.shape and hit[1].stride() == weight.stride() else \
+            torch.empty_like(weight, dtype=torch.bfloat16)
+        _lib.call("vp_cast", _ptr(weight), F32, _ptr(sh), BF16, weight.numel(), _stream())
+        self._cache["shadow"] = (key, sh)
+        return sh
+
+    def shadow_refreshed(self, weight, shadow):
+        """Called by an optimiser that has written the bf16 copy itself."""
+        self._cache["shadow"] = ((weight.data_ptr(), weight._version, _EPOCH[0]), shadow)
+
+    # ---- thin layers (a single channel on one side): tcgen05 kernels that read the fp32 master weight directly ----
     def _thin(self, which, dt, weight):
         if self.kind != "conv" or dt != torch.bfloat16 or _STATE["engine"] == _lib.ENGINE_SIMT or not weight.is_contiguous():
             return False
@@ -183,50 +213,35 @@ class TapLayer:
         n, h, w, _ = x.shape
         dt = x.dtype
         out_dtype = out_dtype or dt
-        if self._thin("fwd", dt, weight):
-            shp = self.out_shape(n, h, w)
-            y = torch.empty(shp, dtype=out_dtype, device=x.device)
-            g = self._geom(n, h, w, self.cin, shp[1], shp[2], self.cout, self.k, self.stride, self.pad, 0)
-            _lib.call("vp_thin_conv_fwd", C.byref(g), _ptr(x), _ptr(weight.detach()), _ptr(bias), _ptr(y), _code(out_dtype),
-                      ACT[act], float(slope), _stream())
-            return y
-        wp = self._packed(weight.detach(), "fwd", dt)
+        weight = weight.detach()
         shp = self.out_shape(n, h, w)
         y = torch.empty(shp, dtype=out_dtype, device=x.device)
-        if self.kind == "flatten_out":
-            g = self._geom(n, 1, 1, self.cin, 1, 1, self.S * self.S * self.cout, 1, 1, 0, 0)
-        elif self.kind == "flatten_in":
-            g = self._geom(n, h, w, self.cin, 1, 1, self.cout, self.S, 1, 0, 0)
+        g = self._layer_geom(n, h, w, shp[1], shp[2])
+        if self._thin("fwd", dt, weight):
+            _lib.call("vp_thin_conv_fwd", C.byref(g), _ptr(x), _ptr(weight), _ptr(bias), _ptr(y), _code(out_dtype),
+                      ACT[act], float(slope), _stream())
+        elif self._cl(dt, weight):
+            _lib.call("vp_conv_fwd_cl", C.byref(g), _ptr(x), _ptr(self._shadow(weight)), _ptr(bias), _ptr(y), _code(out_dtype),
+                      ACT[act], float(slope), _stream())
         else:
-            g = self._geom(n, h, w, self.cin, shp[1], shp[2], self.cout, self.k, self.stride, self.pad, int(self.kind == "convT"))
-        _lib.call("vp_conv_fwd", C.byref(g), _ptr(x), _ptr(wp), _ptr(bias), _ptr(y), _code(dt), _code(out_dtype),
-                  ACT[act], float(slope), _STATE["engine"], _stream())
+            wp = self._packed(weight, "fwd", dt)
+            _lib.call("vp_conv_fwd", C.byref(g), _ptr(x), _ptr(wp), _ptr(bias), _ptr(y), _code(dt), _code(out_dtype),
+                      ACT[act], float(slope), _STATE["engine"], _stream())
         return y
 
     def dgrad(self, dy, weight, x_shape, out_dtype=None):
         n, h, w, _ = x_shape
         dt = dy.dtype
         out_dtype = out_dtype or dt
-        if self._thin("dgrad", dt, weight):
-            dx = torch.empty(x_shape, dtype=out_dtype, device=dy.device)
-            g = self._geom(n, h, w, self.cin, dy.shape[1], dy.shape[2], self.cout, self.k, self.stride, self.pad, 0)
-            _lib.call("vp_thin_conv_dgrad", C.byref(g), _ptr(dy), _ptr(weight.detach()), _ptr(dx), _code(out_dtype), _stream())
-            return dx
-        wp = self._packed(weight.detach(), "dgrad", dt)
+        weight = weight.detach()
         dx = torch.empty(x_shape, dtype=out_dtype, device=dy.device)
-        if self.kind == "flatten_in":
-            # expansion: plain linear [n,out] -> [n, S*S*C] with the permuted packing
-            g = self._geom(n, 1, 1, self.cout, 1, 1, self.S * self.S * self.cin, 1, 1, 0, 0)
-            _lib.call("vp_conv_fwd", C.byref(g), _ptr(dy), _ptr(wp), None, _ptr(dx), _code(dt), _code(out_dtype), 0, 0.0,
-                      _STATE["engine"], _stream())
-        elif self.kind == "flatten_out":
-            # contraction over the SxS map: 'conv' k=S p=0 with A = dy
-            g = self._geom(n, self.S, self.S, self.cout, 1, 1, self.cin, self.S, 1, 0, 0)
-            _lib.call("vp_conv_fwd", C.byref(g), _ptr(dy), _ptr(wp), None, _ptr(dx), _code(dt), _code(out_dtype), 0, 0.0,
-                      _STATE["engine"], _stream())
+        g = self._layer_geom(n, h, w, dy.shape[1], dy.shape[2])
+        if self._thin("dgrad", dt, weight):
+            _lib.call("vp_thin_conv_dgrad", C.byref(g), _ptr(dy), _ptr(weight), _ptr(dx), _code(out_dtype), _stream())
+        elif self._cl(dt, weight):
+            _lib.call("vp_conv_dgrad_cl", C.byref(g), _ptr(dy), _ptr(self._shadow(weight)), _ptr(dx), _code(out_dtype), _stream())
         else:
-            ho, wo = dy.shape[1], dy.shape[2]
-            g = self._geom(n, h, w, self.cin, ho, wo, self.cout, self.k, self.stride, self.pad, int(self.kind == "convT"))
+            wp = self._packed(weight, "dgrad", dt)
             _lib.call("vp_conv_dgrad", C.byref(g), _ptr(dy), _ptr(wp), _ptr(dx), _code(dt), _code(out_dtype),
                       _STATE["engine"], _stream())
         return dx
@@ -234,37 +249,18 @@ class TapLayer:
     def wgrad(self, x, dy, weight):
         n, h, w, _ = x.shape
         dt = x.dtype
-        if self._thin("wgrad", dt, weight):
-            dw = _grad_target(weight)
-            g = self._geom(n, h, w, self.cin, dy.shape[1], dy.shape[2], self.cout, self.k, self.stride, self.pad, 0)
-            _lib.call("vp_thin_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), _stream())
+        g = self._layer_geom(n, h, w, dy.shape[1], dy.shape[2])
+        thin, cl = self._thin("wgrad", dt, weight), self._cl(dt, weight)
+        if thin or cl:
+            dw = _grad_target(weight)       # same strides as the weight: the kernel writes the gradient in place
+            _lib.call("vp_thin_conv_wgrad" if thin else "vp_conv_wgrad_cl", C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), _stream())
             return dw
-        p: Pack = self.p_wgrad
+        p = self._recipe("wgrad", weight)
         dwp = torch.empty(p.taps * p.n * p.k, dtype=torch.float32, device=x.device)
-        if self.kind == "flatten_out":
-            # dW[c*T+t][k] = sum_b dY[b,t,c] z[b,k]: conv-wgrad with the roles x := dY (SxS map), dy := z
-            g = self._geom(n, self.S, self.S, self.cout, 1, 1, self.cin, self.S, 1, 0, 0)
-            _lib.call("vp_conv_wgrad", C.byref(g), _ptr(dy), _ptr(x), _ptr(dwp), _code(dt), _STATE["engine"], _stream())
-        elif self.kind == "flatten_in":
-            g = self._geom(n, h, w, self.cin, 1, 1, self.cout, self.S, 1, 0, 0)
-            _lib.call("vp_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dwp), _code(dt), _STATE["engine"], _stream())
-        else:
-            ho, wo = dy.shape[1], dy.shape[2]
-            g = self._geom(n, h, w, self.cin, ho, wo, self.cout, self.k, self.stride, self.pad, int(self.kind == "convT"))
-            _lib.call("vp_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dwp), _code(dt), _STATE["engine"], _stream())
+        _lib.call("vp_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dwp), _code(dt), _STATE["engine"], _stream())
         dw = _grad_target(weight)
         _lib.call("vp_unpack_wgrad", _ptr(dwp), _ptr(dw), p.taps, p.n, p.k, p.sn, p.sk, p.st, _stream())
         return dw
-
-
-def _permute_vec(v, T, Cn, inverse=False):
-    """feature order c*T+t (torch BatchNorm1d after Linear) <-> t*C+c (our channels-last view)."""
-    out = torch.empty_like(v)
-    if not inverse:
-        _lib.call("vp_pack_weight", _ptr(v), _ptr(out), F32, T, Cn, 1, T, 0, 1, _stream())
-    else:
-        _lib.call("vp_unpack_wgrad", _ptr(v), _ptr(out), T, Cn, 1, T, 0, 1, _stream())
-    return out
 
 
 @dataclass
@@ -272,7 +268,6 @@ class NormCfg:
     kind: Optional[str]  # 'batch' | 'instance' | None
     eps: float = 1e-5
     momentum: float = 0.1
-    perm_T: int = 0       # >0: BatchNorm1d over a flatten_out layer, features permuted with T = S*S
 
 
 class _FusedLayerFn(torch.autograd.Function):
@@ -300,10 +295,7 @@ class _FusedLayerFn(torch.autograd.Function):
             return a, None
         y = layer.fwd(x, weight, bias, "none", 0.0, dt)
         n, h, w, c = y.shape
-        if norm.perm_T:
-            feat = h * w * c  # BatchNorm1d over the flattened (permuted) feature vector
-            groups, rpg, cc = 1, n, feat
-        elif norm.kind == "batch":
+        if norm.kind == "batch":
             groups, rpg, cc = 1, n * h * w, c
         else:
             groups, rpg, cc = n, h * w, c
@@ -311,31 +303,19 @@ class _FusedLayerFn(torch.autograd.Function):
         stats = torch.empty(4, groups * cc, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         g_, b_ = gamma, beta
-        if norm.perm_T and gamma is not None:
-            g_, b_ = _permute_vec(gamma.detach(), norm.perm_T, c), _permute_vec(beta.detach(), norm.perm_T, c)
         if training or norm.kind == "instance":
             sums = torch.empty(2 * groups * cc, dtype=torch.float64, device=dev)
             _lib.call("vp_norm_stats", _ptr(y), _ptr(sums), _code(dt), groups, rpg, cc, _stream())
             rm = rv = None
             if norm.kind == "batch" and bn_module is not None and bn_module.track_running_stats:
                 rm, rv = bn_module.running_mean, bn_module.running_var
-                if norm.perm_T:
-                    rm_p, rv_p = _permute_vec(rm, norm.perm_T, c), _permute_vec(rv, norm.perm_T, c)
-                else:
-                    rm_p, rv_p = rm, rv
-            _lib.call("vp_norm_finalize", _ptr(sums), _ptr(g_), _ptr(b_), _ptr(rm_p if rm is not None else None),
-                      _ptr(rv_p if rm is not None else None), float(norm.momentum), float(norm.eps),
+            _lib.call("vp_norm_finalize", _ptr(sums), _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum), float(norm.eps),
                       _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), groups, rpg, cc, _stream())
             if rm is not None:
-                if norm.perm_T:
-                    rm.copy_(_permute_vec(rm_p, norm.perm_T, c, inverse=True))
-                    rv.copy_(_permute_vec(rv_p, norm.perm_T, c, inverse=True))
                 bn_module.num_batches_tracked += 1
         else:
             # eval-mode BatchNorm: running statistics (not on the training hot path; tiny [C] vectors)
             rm, rv = bn_module.running_mean, bn_module.running_var
-            if norm.perm_T:
-                rm, rv = _permute_vec(rm, norm.perm_T, c), _permute_vec(rv, norm.perm_T, c)
             invstd.copy_(torch.rsqrt(rv + norm.eps))
             mean.copy_(rm)
             scale.copy_(invstd * (g_ if g_ is not None else 1.0))
@@ -407,9 +387,6 @@ class _FusedLayerFn(torch.autograd.Function):
                 _lib.call("vp_norm_bwd_apply", _ptr(y), _ptr(da), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
                           _ptr(sums), _ptr(dy), _ptr(dgamma), _ptr(dbeta), _code(dt), groups, rpg, cc, ACT[act],
                           float(slope), _stream())
-                if norm.perm_T and dgamma is not None:
-                    dgamma = _permute_vec(dgamma, norm.perm_T, c, inverse=True)
-                    dbeta = _permute_vec(dbeta, norm.perm_T, c, inverse=True)
             else:
                 raise _lib.VaePlayError("backward through eval-mode BatchNorm is not part of the training path")
             if dy_extra is not None:
@@ -483,6 +460,38 @@ def to_channels_last(x_nchw: torch.Tensor) -> torch.Tensor:
 def from_channels_last(a: torch.Tensor) -> torch.Tensor:
     """NHWC activation dtype -> NCHW fp32 (graph exit)."""
     return _FromCL.apply(a)
+
+
+class _TransposeBT(torch.autograd.Function):
+    """[B, R, C] -> [B, C, R] in the same dtype (vp_transpose_bt); its own inverse with (R, C) swapped."""
+
+    @staticmethod
+    def forward(ctx, a, rows, cols):
+        _require_cuda(a, "transpose")
+        b = a.numel() // (rows * cols)
+        out = torch.empty(a.numel(), dtype=a.dtype, device=a.device)
+        _lib.call("vp_transpose_bt", _ptr(a), _ptr(out), _code(a.dtype), b, rows, cols, _stream())
+        ctx.rc = (rows, cols)
+        ctx.in_shape = a.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, d):
+        rows, cols = ctx.rc
+        return _TransposeBT.apply(d.contiguous(), cols, rows).reshape(ctx.in_shape), None, None
+
+
+def hwc_to_chw_flat(a: torch.Tensor) -> torch.Tensor:
+    """channels-last map [B,H,W,C] -> the NCHW-flatten vector ``ten.view(len(ten), -1)`` of the reference
+    (models/networks.py:74-75), as [B,1,1,C*H*W]."""
+    n, h, w, c = a.shape
+    return _TransposeBT.apply(a, h * w, c).reshape(n, 1, 1, c * h * w)
+
+
+def chw_flat_to_hwc(v: torch.Tensor, c: int, h: int, w: int) -> torch.Tensor:
+    """[B,1,1,C*H*W] in NCHW-flatten order (``ten.view(len(ten), -1, 8, 8)``, models/networks.py:110) -> [B,H,W,C]."""
+    n = v.shape[0]
+    return _TransposeBT.apply(v, c, h * w).reshape(n, h, w, c)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -40,6 +40,7 @@ class Conv2d(nn.Module):
         self.conv = nn.Sequential(*mods)
         self._bn = bn if bn in ("batch", "instance") else None
         self._layer = TapLayer("conv", in_channel, out_channel, k=kernel_size, stride=stride, pad=(kernel_size - 1) // 2)
+        VF.weights_channels_last(self)
 
     def forward_cl(self, a):
         conv = self.conv[0]

@@ -20,8 +20,8 @@ from .. import functional as VF
 from ..functional import DualLinear, NormCfg, TapLayer
 
 
-def _bn_cfg(bn: nn.modules.batchnorm._BatchNorm, perm_T=0):
-    return NormCfg("batch", eps=bn.eps, momentum=bn.momentum, perm_T=perm_T)
+def _bn_cfg(bn: nn.modules.batchnorm._BatchNorm):
+    return NormCfg("batch", eps=bn.eps, momentum=bn.momentum)
 
 
 # encoder block (used in encoder and discriminator) -- reference networks.py:10-30
@@ -31,6 +31,7 @@ class EncoderBlock(nn.Module):
         self.conv = nn.Conv2d(in_channels=channel_in, out_channels=channel_out, kernel_size=5, padding=2, stride=2, bias=False)
         self.bn = nn.BatchNorm2d(num_features=channel_out, momentum=0.9)
         self._layer = TapLayer("conv", channel_in, channel_out, k=5, stride=2, pad=2)
+        VF.weights_channels_last(self)
 
     def forward_cl(self, a, out=False):
         act, pre = VF.fused_layer(a, self.conv.weight, None, self.bn.weight, self.bn.bias, self._layer, _bn_cfg(self.bn),
@@ -52,6 +53,7 @@ class DecoderBlock(nn.Module):
         self.conv = nn.ConvTranspose2d(channel_in, channel_out, kernel_size=5, padding=2, stride=2, output_padding=1, bias=False)
         self.bn = nn.BatchNorm2d(channel_out, momentum=0.9)
         self._layer = TapLayer("convT", channel_in, channel_out, k=5, stride=2, pad=2, out_pad=1)
+        VF.weights_channels_last(self)
 
     def forward_cl(self, a):
         act, _ = VF.fused_layer(a, self.conv.weight, None, self.bn.weight, self.bn.bias, self._layer, _bn_cfg(self.bn),
@@ -81,7 +83,7 @@ class Encoder(nn.Module):
                                 nn.ReLU(True))
         self.l_mu = nn.Linear(in_features=1024, out_features=z_size)
         self.l_var = nn.Linear(in_features=1024, out_features=z_size)
-        self._fc_layer = TapLayer("flatten_in", self.size, 1024, spatial=8)
+        self._fc_layer = TapLayer("linear", 8 * 8 * self.size, 1024)
         self._heads = DualLinear(1024, z_size)
         self.z_size = z_size
 
@@ -92,7 +94,7 @@ class Encoder(nn.Module):
             a = blk.forward_cl(a)
         if a.shape[1] != 8 or a.shape[2] != 8:
             raise ValueError(f"Encoder expects an 8x8 map before fc, got {tuple(a.shape)} (img_size must be 8 * 2**iter_level)")
-        h, _ = VF.fused_layer(a, self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
+        h, _ = VF.fused_layer(VF.hwc_to_chw_flat(a), self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
                               _bn_cfg(self.fc[1]), "relu", 0.0, self.training, self.fc[1])
         return VF.dual_linear(h, self.l_mu.weight, self.l_mu.bias, self.l_var.weight, self.l_var.bias, self._heads)
 
@@ -109,7 +111,8 @@ class Decoder(nn.Module):
                                 nn.BatchNorm1d(num_features=8 * 8 * size, momentum=0.9),
                                 nn.ReLU(True))
         self.size = size
-        self._fc_layer = TapLayer("flatten_out", z_size, size, spatial=8)
+        self._fc_layer = TapLayer("linear", z_size, 8 * 8 * size)
+        self._fc_size = size
         layers_list = [DecoderBlock(channel_in=self.size, channel_out=self.size)]
         for _ in range(iter_level - 1):
             layers_list.append(DecoderBlock(channel_in=self.size, channel_out=self.size // 2))
@@ -125,7 +128,8 @@ class Decoder(nn.Module):
     def forward_cl(self, z_cl):
         """z as [B,1,1,Z] in the activation dtype -> x_tilde channels-last."""
         a, _ = VF.fused_layer(z_cl, self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
-                              _bn_cfg(self.fc[1], perm_T=64), "relu", 0.0, self.training, self.fc[1])
+                              _bn_cfg(self.fc[1]), "relu", 0.0, self.training, self.fc[1])
+        a = VF.chw_flat_to_hwc(a, self._fc_size, 8, 8)
         blocks = list(self.conv)
         for blk in blocks[:-1]:
             a = blk.forward_cl(a)
@@ -194,7 +198,7 @@ class Discriminator(nn.Module):
             nn.ReLU(inplace=True),
             nn.Linear(in_features=512, out_features=1),
         )
-        self._fc_layer = TapLayer("flatten_in", self.size, 512, spatial=8)
+        self._fc_layer = TapLayer("linear", 8 * 8 * self.size, 512)
         self._out_layer = TapLayer("linear", 512, 1)
         self._nonorm = NormCfg(None)
 
@@ -212,7 +216,7 @@ class Discriminator(nn.Module):
                 return VF.from_channels_last(pre).reshape(len(ten), -1)
             else:
                 a = lay.forward_cl(a)
-        h, _ = VF.fused_layer(a, self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
+        h, _ = VF.fused_layer(VF.hwc_to_chw_flat(a), self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
                               _bn_cfg(self.fc[1]), "relu", 0.0, self.training, self.fc[1])
         o, _ = VF.fused_layer(h, self.fc[3].weight, self.fc[3].bias, None, None, self._out_layer, self._nonorm, "sigmoid",
                               0.0, self.training, None, torch.float32)

@@ -27,8 +27,9 @@ class FusedRMSprop(torch.optim.Optimizer):
         if hit is not None and hit[0] == key:
             return hit[1]
         for p in plist:
-            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous() or not p.grad.is_contiguous():
-                raise _lib.VaePlayError("FusedRMSprop needs contiguous fp32 CUDA parameters and gradients")
+            dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+            if not p.is_cuda or p.dtype != torch.float32 or not dense or p.grad.stride() != p.stride():
+                raise _lib.VaePlayError("FusedRMSprop needs dense fp32 CUDA parameters whose gradients share their strides")
             st = self.state[p]
             if "square_avg" not in st:
                 st["step"] = 0

@@ -48,7 +48,8 @@ class GradBuckets:
         for bi, b in enumerate(self.buckets):
             off = 0
             for p in b["params"]:
-                view = b["buf"][off: off + p.numel()].view_as(p)
+                # same strides as the parameter (conv weights live in channels-last order): the slot IS the gradient
+                view = torch.as_strided(b["buf"], p.shape, p.stride(), storage_offset=off)
                 self.slot[id(p)] = (bi, view)
                 off += p.numel()
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
