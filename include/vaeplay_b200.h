@@ -58,6 +58,11 @@ int vp_abi_version(void);
 /* compute capability major*10+minor of the current device, or a negative error code */
 int vp_device_arch(void);
 
+/* Scratch memory for split-K partial sums of skinny contractions (the fc layers: a few output tiles, thousands of K
+ * iterations): a DEVICE buffer owned by the caller, used stream-ordered (one stream at a time) by every later call until
+ * replaced; without one such contractions run unsplit on a few SMs.  >= 4 * (rows * out_features) bytes to be useful. */
+int vp_set_workspace(void* ptr, size_t bytes);
+
 /* ---- weight layout ------------------------------------------------------------------------------- */
 /* Wp[t][n][k] = (dtype) w[n*stride_n + k*stride_k + t*stride_t],  t in [0,taps).  `w` fp32 (torch layout).
  * (Conv2d: stride_t = 1.  The NCHW-flatten Linear layers of models/networks.py:65,88 are expressed as

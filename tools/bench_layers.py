@@ -20,8 +20,8 @@ for i in range(L):
     layers.append((f"enc{i+1}", VF.TapLayer("conv", c, co, k=5, stride=2, pad=2), (co, c, 5, 5), h, c))
     c, h = co, h // 2
 size = c
-layers.append(("enc_fc", VF.TapLayer("flatten_in", size, 1024, spatial=8), (1024, 64 * size), 8, size))
-layers.append(("dec_fc", VF.TapLayer("flatten_out", 128, size, spatial=8), (64 * size, 128), 1, 128))
+layers.append(("enc_fc", VF.TapLayer("linear", 64 * size, 1024), (1024, 64 * size), 1, 64 * size))
+layers.append(("dec_fc", VF.TapLayer("linear", 128, 64 * size), (64 * size, 128), 1, 128))
 c, h = size, 8
 for i in range(L):
     co = c if i == 0 else c // 2
@@ -52,11 +52,13 @@ for name, layer, wshape, hin, cin in layers:
     if only and only not in name:
         continue
     w = torch.randn(*wshape, device="cuda") * 0.05
+    if w.dim() == 4 and wshape[0] % 64 == 0 and wshape[1] % 64 == 0:
+        w = w.contiguous(memory_format=torch.channels_last)
     xin = torch.randn(B, hin, hin, cin, device="cuda").to(torch.bfloat16)
     y = layer.fwd(xin, w, None)
     dy = torch.randn_like(y)
     mac = {"conv": B * y.shape[1] * y.shape[2] * layer.cout * layer.cin * 25, "convT": B * hin * hin * layer.cin * layer.cout * 25,
-           "flatten_in": B * wshape[0] * wshape[1], "flatten_out": B * wshape[0] * wshape[1]}[layer.kind]
+           "linear": B * wshape[0] * wshape[1]}[layer.kind]
     gf = 2.0 * mac / 1e9
     tf = timeit(lambda: layer.fwd(xin, w, None))
     td = timeit(lambda: layer.dgrad(dy, w, tuple(xin.shape))) if name != "enc1" else 0.0

@@ -61,6 +61,7 @@ SIGNATURES = {
     "vp_im2col": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
     "vp_pad_rows": [_p, _p, _i, _i64, _i, _i, _p],
     "vp_unpad_rows": [_p, _p, _i64, _i, _i, _p],
+    "vp_set_workspace": [_p, C.c_size_t],
     "vp_conv_fwd_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
     "vp_conv_dgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
     "vp_conv_wgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
@@ -99,6 +100,20 @@ def load(build_if_missing: bool = True):
         raise VaePlayError("libvaeplay_b200.so ABI version mismatch; rebuild with `python -m vae_play_b200.build --force`")
     _lib = lib
     return lib
+
+
+_workspace = {}
+
+
+def ensure_workspace(device, nbytes: int = 32 << 20):
+    """Register a per-device scratch buffer for split-K partial sums (vp_set_workspace)."""
+    import torch
+    key = (device.type, device.index)
+    if key not in _workspace:
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _workspace[key] = buf
+        call("vp_set_workspace", C.c_void_p(buf.data_ptr()), nbytes)
+    return _workspace[key]
 
 
 def check(rc: int, what: str):

@@ -148,6 +148,14 @@ extern "C" const char* vp_last_error(void) { return g_err; }
 extern "C" int vp_abi_version(void) { return VP_ABI_VERSION; }
 extern "C" uint64_t vp_launch_count(void) { return g_launches.load(); }
 
+namespace vp { void set_splitk_workspace(void* ptr, size_t bytes); }
+/* Scratch memory for split-K partial sums (skinny contractions such as the fc layers): a device buffer owned by the caller,
+ * used stream-ordered by every later call until replaced; without one those contractions run unsplit. */
+extern "C" int vp_set_workspace(void* ptr, size_t bytes) {
+    vp::set_splitk_workspace(ptr, ptr ? bytes : 0);
+    return VP_OK;
+}
+
 extern "C" int vp_device_arch(void) {
     int dev = 0, maj = 0, min = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return VP_ECUDA; }

@@ -112,8 +112,11 @@ struct TcParams {
     int kblocks;           // K / 64
     int bt, ht, wt;        // tile brick, bt*ht*wt == 128
     int ntiles_n;          // N tiles
-    int total_tiles;       // sum over phases of M-tiles, times ntiles_n
+    int total_tiles;       // sum over phases of M-tiles, times ntiles_n (times ksplit)
     int nphases;
+    int ksplit;            // > 1: the (tap, k-block) iterations of a tile are split over ksplit CTAs, partial tiles are
+    int iters_per_split;   //      added into an fp32 workspace (D) with red.global.add and finished by splitk_finish_kernel
+    int base_tiles;
     TcPhase ph[kMaxPhases];
 };
 
@@ -125,10 +128,12 @@ struct SmemLayout {
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16;
 };
 
-struct TileCoord { int phase, n0, gy0, gx0, col0; };
+struct TileCoord { int phase, n0, gy0, gx0, col0, split; };
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int q, int BN) {
     TileCoord c;
+    c.split = 0;
+    if (p.ksplit > 1) { c.split = q / p.base_tiles; q -= c.split * p.base_tiles; }
     const int nt = q % p.ntiles_n;
     int mt = q / p.ntiles_n;
     int ph = 0;
@@ -193,8 +198,9 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
             for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x) {
                 const TileCoord tc = decode_tile(p, q, BN);
                 const TcPhase& ph = p.ph[tc.phase];
-                const int iters = ph.taps.ntaps * p.kblocks;
-                for (int it = 0; it < iters; ++it, ++g) {
+                int iters = ph.taps.ntaps * p.kblocks, it0 = 0;
+                if (p.ksplit > 1) { it0 = tc.split * p.iters_per_split; iters = min(iters, it0 + p.iters_per_split); }
+                for (int it = it0; it < iters; ++it, ++g) {
                     const int s = g % STAGES;
                     mbar_wait(&empty[s], ((g / STAGES) & 1) ^ 1);
                     const int t = it / p.kblocks;
@@ -223,12 +229,13 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
             uint32_t g = 0, i = 0;
             for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
                 const TileCoord tc = decode_tile(p, q, BN);
-                const int iters = p.ph[tc.phase].taps.ntaps * p.kblocks;
+                int iters = p.ph[tc.phase].taps.ntaps * p.kblocks, it0 = 0;
+                if (p.ksplit > 1) { it0 = tc.split * p.iters_per_split; iters = min(iters, it0 + p.iters_per_split); }
                 const uint32_t buf = i & 1, use = i >> 1;
                 mbar_wait(&acc_empty[buf], (use & 1) ^ 1);          // epilogue has drained this TMEM buffer
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + buf * kAccCols;
-                for (int it = 0; it < iters; ++it, ++g) {
+                for (int it = it0; it < iters; ++it, ++g) {
                     const int s = g % STAGES;
                     mbar_wait(&full[s], (g / STAGES) & 1);
                     tc_fence_after();
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                     const uint64_t bdesc = BMN ? smem_desc_mn_sw128(sa + kABytes) : smem_desc_k_sw128(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k)   // per UMMA_K=16: K-major +32 B (+2 in the addr>>4 field), MN-major +16 rows = 2048 B (+128)
-                        tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * (BMN ? 128 : 2)), idesc, (it | k) != 0);
+                        tc_mma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * (BMN ? 128 : 2)), idesc, ((it - it0) | k) != 0);
                     tc_commit(&empty[s]);
                 }
                 tc_commit(&acc_full[buf]);
@@ -269,7 +276,16 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                 if (CH == 32) tmem_ld32(taddr, v);
                 else tmem_ld16(taddr, v);
                 tmem_ld_wait();
-                if (row_ok) store_chunk<CH>(v, p.D, row_off, tc.col0 + c, p.N, p.bias, p.act, p.slope, p.out_f32 != 0);
+                if (row_ok) {
+                    if (p.ksplit > 1) {
+                        float* out = (float*)p.D + row_off + tc.col0 + c;
+#pragma unroll
+                        for (int j = 0; j < CH; ++j)
+                            if (tc.col0 + c + j < p.N) atomicAdd(out + j, __uint_as_float(v[j]));
+                    } else {
+                        store_chunk<CH>(v, p.D, row_off, tc.col0 + c, p.N, p.bias, p.act, p.slope, p.out_f32 != 0);
+                    }
+                }
             }
             // this warp's TMEM reads are complete (wait::ld above): hand the buffer back to the MMA warp
             tc_fence_before();
@@ -312,6 +328,32 @@ int tc_variant() {
 }
 
 }  // namespace
+
+// ---- split-K support ------------------------------------------------------------------------------------------------
+static void* g_ws = nullptr;
+static size_t g_ws_bytes = 0;
+void set_splitk_workspace(void* ptr, size_t bytes) { g_ws = ptr; g_ws_bytes = bytes; }
+void* splitk_workspace(size_t bytes) { return bytes <= g_ws_bytes ? g_ws : nullptr; }
+
+namespace {
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, void* __restrict__ D, const float* __restrict__ bias, int act,
+                                                            float slope, int64_t n, int N, int out_f32) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float x = ws[i];
+        if (bias) x += bias[i % N];
+        x = act_fwd(x, act, slope);
+        if (out_f32) ((float*)D)[i] = x;
+        else ((bf16*)D)[i] = __float2bfloat16_rn(x);
+    }
+}
+}  // namespace
+int launch_splitk_finish(const float* ws, void* D, const float* bias, int act, float slope, int64_t n, int N, bool out_f32, cudaStream_t s) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, s>>>(ws, D, bias, act, slope, n, N, out_f32 ? 1 : 0);
+    VP_CHECK_LAUNCH("splitk_finish");
+    return VP_OK;
+}
 
 bool tc_available() {
     static int cached = -1;
@@ -373,6 +415,24 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     if (mtiles * tp.ntiles_n > 0x7fffffff) { set_error("tcgen05 engine: too many tiles"); return VP_EUNSUPPORTED; }
     tp.total_tiles = (int)(mtiles * tp.ntiles_n);
     tp.nphases = nphases;
+    tp.ksplit = 1; tp.base_tiles = tp.total_tiles;
+    // skinny problems (the fc layers: a handful of output tiles, thousands of K iterations): split K over the idle SMs
+    float* ws = nullptr;
+    {
+        const int iters = phases[0].taps.ntaps * (p.K / kBlockK);
+        const int64_t out_elems = (int64_t)p.n * p.hd * p.wd * p.N;
+        if (nphases == 1 && tp.total_tiles * 2 <= num_sms() && iters >= 16 && tc_variant() != 3) {
+            int ks = (2 * num_sms()) / tp.total_tiles;
+            if (ks > iters / 4) ks = iters / 4;
+            ws = (float*)splitk_workspace((size_t)out_elems * sizeof(float));
+            if (ks > 1 && ws) {
+                tp.iters_per_split = (iters + ks - 1) / ks;
+                tp.ksplit = (iters + tp.iters_per_split - 1) / tp.iters_per_split;
+                tp.total_tiles = tp.base_tiles * tp.ksplit;
+                cudaMemsetAsync(ws, 0, (size_t)out_elems * sizeof(float), s);
+            }
+        }
+    }
 
     // ---- tensor maps -----------------------------------------------------------------------------------
     CUtensorMap mA, mB;
@@ -393,6 +453,19 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     tp.D = p.D; tp.bias = p.bias; tp.n = p.n; tp.hd = p.hd; tp.wd = p.wd; tp.N = p.N;
     tp.as = p.as; tp.ds = p.ds; tp.act = p.act; tp.slope = p.slope;
     tp.out_f32 = (p.out_dtype == VP_F32); tp.kblocks = p.K / kBlockK;
+    if (tp.ksplit > 1) {
+        tp.D = ws; tp.out_f32 = 1;
+        int rc;
+        if (bmn) rc = BN == 128 ? launch_cfg<128, 3, 2, true>(mA, mB, tp, s) : launch_cfg<64, 4, 2, true>(mA, mB, tp, s);
+        else switch (BN) {
+            case 128: rc = launch_cfg<128, 3, 2>(mA, mB, tp, s); break;
+            case 64: rc = launch_cfg<64, 4, 2>(mA, mB, tp, s); break;
+            case 32: rc = launch_cfg<32, 5, 2>(mA, mB, tp, s); break;
+            default: rc = launch_cfg<16, 5, 2>(mA, mB, tp, s); break;
+        }
+        if (rc) return rc;
+        return launch_splitk_finish(ws, p.D, p.bias, p.act, p.slope, (int64_t)p.n * p.hd * p.wd * p.N, p.N, p.out_dtype == VP_F32, s);
+    }
     if (one_cta) {
         switch (BN) {
             case 256: return launch_cfg<256, 4, 1>(mA, mB, tp, s);

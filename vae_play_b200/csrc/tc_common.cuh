@@ -12,6 +12,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode();
 struct TapGemm;
 int encode_weight_map(CUtensorMap* m, const TapGemm& p, bool bmn, int BN);
+void set_splitk_workspace(void* ptr, size_t bytes);
+void* splitk_workspace(size_t bytes);
+int launch_splitk_finish(const float* ws, void* D, const float* bias, int act, float slope, int64_t n, int N, bool out_f32, cudaStream_t s);
 int pow2_floor(int v);
 int pow2_ceil(int v);
 int num_sms();

@@ -83,6 +83,7 @@ def _stream():
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise _lib.VaePlayError(f"{what}: tensor is on {t.device}; vae_play_b200 has no CPU path")
+    _lib.ensure_workspace(t.device)
     if not t.is_contiguous():
         raise _lib.VaePlayError(f"{what}: tensor must be contiguous")
 
