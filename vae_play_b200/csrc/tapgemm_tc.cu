@@ -279,9 +279,17 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                 if (row_ok) {
                     if (p.ksplit > 1) {
                         float* out = (float*)p.D + row_off + tc.col0 + c;
+                        if (tc.col0 + c + CH <= p.N && (p.N & 3) == 0) {
 #pragma unroll
-                        for (int j = 0; j < CH; ++j)
-                            if (tc.col0 + c + j < p.N) atomicAdd(out + j, __uint_as_float(v[j]));
+                            for (int j = 0; j < CH; j += 4)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + j), "f"(__uint_as_float(v[j])),
+                                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                                             : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < CH; ++j)
+                                if (tc.col0 + c + j < p.N) atomicAdd(out + j, __uint_as_float(v[j]));
+                        }
                     } else {
                         store_chunk<CH>(v, p.D, row_off, tc.col0 + c, p.N, p.bias, p.act, p.slope, p.out_f32 != 0);
                     }
@@ -422,7 +430,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
         const int iters = phases[0].taps.ntaps * (p.K / kBlockK);
         const int64_t out_elems = (int64_t)p.n * p.hd * p.wd * p.N;
         if (nphases == 1 && tp.total_tiles * 2 <= num_sms() && iters >= 16 && tc_variant() != 3) {
-            int ks = (2 * num_sms()) / tp.total_tiles;
+            int ks = num_sms() / tp.total_tiles;
             if (ks > iters / 4) ks = iters / 4;
             ws = (float*)splitk_workspace((size_t)out_elems * sizeof(float));
             if (ks > 1 && ws) {

@@ -77,13 +77,13 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 def _stream():
+    _lib.ensure_workspace(torch.device("cuda", torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise _lib.VaePlayError(f"{what}: tensor is on {t.device}; vae_play_b200 has no CPU path")
-    _lib.ensure_workspace(t.device)
     if not t.is_contiguous():
         raise _lib.VaePlayError(f"{what}: tensor must be contiguous")
 
