@@ -226,6 +226,8 @@ extern "C" int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* 
     TapWgrad p;
     fill_wgrad(g, x, dy, dw_cl, true, p);
     cudaMemsetAsync(dw_cl, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    const int rc = launch_tapwgrad_win(p, g->kh, g->kw, g->pad, s);
+    if (rc != VP_EUNSUPPORTED) return rc;
     return launch_tapwgrad_tc(p, s);
 }
 
@@ -239,7 +241,8 @@ extern "C" int vp_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy,
     fill_wgrad(g, x, dy, dwp, false, p);
     cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     if (engine != VP_ENGINE_SIMT && dtype == VP_BF16) {
-        const int rc = launch_tapwgrad_tc(p, s);
+        int rc = launch_tapwgrad_win(p, g->kh, g->kw, g->pad, s);
+        if (rc == VP_EUNSUPPORTED) rc = launch_tapwgrad_tc(p, s);
         if (rc != VP_EUNSUPPORTED || engine == VP_ENGINE_TC) return rc;
     } else if (engine == VP_ENGINE_TC) {
         set_error("tensor-core engine needs dtype bf16");

@@ -135,6 +135,8 @@ int launch_tapgemm_tc(const TapGemm& p, cudaStream_t s);
 // all output-parity phases of one layer in a single persistent launch (phases share everything but grid/offset/taps)
 int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s);
 int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s);
+// tap-row weight gradient (G and the A halo shared by all taps of a filter row); VP_EUNSUPPORTED when not of that form
+int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t s);
 // stride-1 tap sets with the activation halo re-used across taps; VP_EUNSUPPORTED when not of that form
 int launch_tapgemm_win(const TapGemm* phases, int nphases, cudaStream_t s);
 bool tc_available();
