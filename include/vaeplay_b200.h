@@ -192,6 +192,16 @@ int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_
 int vp_conv_fwd_cl(const VpConvGeom* g, const void* x, const void* w_cl, const float* bias, void* y, int out_dtype,
                    int act, float slope, void* stream);
 int vp_conv_dgrad_cl(const VpConvGeom* g, const void* dy, const void* w_cl, void* dx, int out_dtype, void* stream);
+/* Forward of a layer that is followed by BatchNorm (EncoderBlock / DecoderBlock, models/networks.py:14-16,38-40): y in bf16
+ * without bias / activation, plus the batch statistics of y taken in the GEMM epilogue from the values being stored --
+ * stat_parts[*nparts][2][co] fp32 per-CTA partial column sums and sums of squares (stat_capacity = parts the buffer holds;
+ * 2 * #SMs always suffices).  co a multiple of 64, <= 512.  Replaces the separate vp_norm_stats pass over y. */
+int vp_conv_fwd_cl_stats(const VpConvGeom* g, const void* x, const void* w_cl, void* y, float* stat_parts,
+                         int stat_capacity, int* nparts, void* stream);
+/* vp_norm_finalize from such partial sums (added in double, fixed order) */
+int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, float momentum, float eps,
+                           float* mean, float* invstd, float* scale, float* shift, int64_t rows, int c, void* stream);
 int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, void* stream);
 /* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
 int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
@@ -207,6 +217,9 @@ int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, 
  *   wgrad: ci == 1 (co a multiple of 64)   or   co == 1 at stride 1 (ci a multiple of 64) */
 int vp_thin_conv_fwd(const VpConvGeom* g, const void* x, const float* w, const float* bias, void* y, int out_dtype,
                      int act, float slope, void* stream);
+/* single-channel-input forward + BatchNorm partial sums of y (as vp_conv_fwd_cl_stats) */
+int vp_thin_conv_fwd_stats(const VpConvGeom* g, const void* x, const float* w, void* y, float* stat_parts,
+                           int stat_capacity, int* nparts, void* stream);
 int vp_thin_conv_dgrad(const VpConvGeom* g, const void* dy, const float* w, void* dx, int out_dtype, void* stream);
 int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, void* stream);
 

@@ -655,3 +655,48 @@ def test_fused_rmsprop_matches_torch(vp):
         for x, y in zip(pa, pb):
             close(npy(x), npy(y), 1e-5, "rmsprop param")
             close(npy(oa.state[x]["square_avg"]), npy(ob.state[y]["square_avg"]), 1e-5, "rmsprop state")
+
+
+@pytest.mark.parametrize("kind,cin,cout,hw,b", [("enc", 64, 128, 32, 6), ("enc", 128, 256, 16, 5), ("enc", 1, 64, 64, 7), ("enc", 64, 128, 20, 3),
+                                                 ("dec", 128, 64, 32, 4), ("dec", 256, 256, 8, 9), ("dec", 256, 128, 16, 3), ("dec", 128, 64, 13, 2)])
+def test_epilogue_batchnorm_statistics(vp, kind, cin, cout, hw, b):
+    """BatchNorm statistics taken in the GEMM epilogue (from the bf16 values being stored, per-CTA partial sums): the
+    running statistics match float64 statistics of the stored pre-norm tensor, and activations / gradients match the
+    path with a separate statistics pass."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200.models.networks import DecoderBlock, EncoderBlock, _bn_cfg
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    torch.manual_seed(5)
+    blk = (EncoderBlock if kind == "enc" else DecoderBlock)(cin, cout).cuda().train()
+    with torch.no_grad():
+        blk.bn.weight.uniform_(0.5, 1.5)
+        blk.bn.bias.uniform_(-0.5, 0.5)
+    x = torch.randn(b, hw, hw, cin, device="cuda").to(torch.bfloat16)
+    res = {}
+    try:
+        for on in (False, True):
+            vp.set_epilogue_stats(on)
+            blk.bn.running_mean.zero_(); blk.bn.running_var.fill_(1.0)
+            blk.zero_grad(set_to_none=True)
+            xin = x.clone().requires_grad_(True)
+            n0 = vp._lib.launch_count()
+            a, y = VF.fused_layer(xin, blk.conv.weight, None, blk.bn.weight, blk.bn.bias, blk._layer, _bn_cfg(blk.bn), "relu", 0.0, True, blk.bn)
+            launches = vp._lib.launch_count() - n0
+            a.float().square().sum().backward()
+            yd = y.detach().double().reshape(-1, cout)
+            m = yd.shape[0]
+            want_rm = 0.9 * yd.mean(0)                                           # momentum 0.9 from running_mean = 0
+            want_rv = 0.1 + 0.9 * yd.var(0, unbiased=False) * m / (m - 1)
+            res[on] = (npy(a), npy(blk.bn.running_mean), npy(blk.bn.running_var), npy(blk.conv.weight.grad), npy(blk.bn.weight.grad), launches,
+                       want_rm.cpu().numpy(), want_rv.cpu().numpy())
+    finally:
+        vp.set_epilogue_stats(True)
+    assert blk._layer.stats_in_epilogue(torch.bfloat16, blk.conv.weight)
+    assert res[True][5] < res[False][5]                      # the statistics pass is gone
+    for on in (False, True):
+        # the batch mean is a cancelling sum (|mean| << std): bound its error by the std, i.e. by sqrt(running_var)
+        assert np.max(np.abs(res[on][1] - res[on][6]) / np.sqrt(res[on][7])) < 2e-6, ("running_mean", on)
+        close(res[on][2], res[on][7], 2e-6, f"running_var (epilogue={on})")
+    close(res[True][0], res[False][0], 1e-2, "activations")  # one bf16 ulp where a rounding boundary moves
+    assert rel_l2(res[True][3], res[False][3]) < 5e-3 and rel_l2(res[True][4], res[False][4]) < 5e-3

@@ -6,6 +6,6 @@ There is no CPU path: tensors must live on a CUDA device and the library must be
 """
 from . import _lib  # noqa: F401
 from .functional import (act_dtype, bce_dice_loss, get_precision, l1_loss, mse_loss, philox_normal, reparam_kl,  # noqa: F401
-                         set_engine, set_precision, vae_loss)
+                         set_engine, set_epilogue_stats, set_precision, vae_loss)
 
 __version__ = "0.1.0"

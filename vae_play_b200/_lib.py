@@ -63,6 +63,9 @@ SIGNATURES = {
     "vp_unpad_rows": [_p, _p, _i64, _i, _i, _p],
     "vp_set_workspace": [_p, C.c_size_t],
     "vp_conv_fwd_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
+    "vp_conv_fwd_cl_stats": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, C.POINTER(C.c_int), _p],
+    "vp_thin_conv_fwd_stats": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, C.POINTER(C.c_int), _p],
+    "vp_norm_finalize_parts": [_p, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i64, _i, _p],
     "vp_conv_dgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
     "vp_conv_wgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
     "vp_transpose_bt": [_p, _p, _i, _i, _i, _i, _p],

@@ -96,10 +96,14 @@ int run_tapgemm(const TapGemm& p, int dtype, int engine, cudaStream_t s) {
 //                                                                       convT fwd / conv dgrad -> scatter)
 // wlay: 0 = packed panels Wp[tap][N][K]; 1 = the module's weight in channels-last order [d0][kh][kw][d1] read in place, with
 // (N, K) = (d0, d1) -> K-major operand; 2 = same with (N, K) = (d1, d0) -> MN-major operand
+struct StatOut { float* parts; int capacity; int* nparts; };
+
 int conv_like(const VpConvGeom& g, bool gather, const void* A, int ha, int wa, int K, void* D, int hd, int wd, int N,
-              const void* wp, const float* bias, int act, float slope, int dtype, int out_dtype, int engine, cudaStream_t s, int wlay = 0) {
+              const void* wp, const float* bias, int act, float slope, int dtype, int out_dtype, int engine, cudaStream_t s, int wlay = 0,
+              const StatOut* st = nullptr) {
     TapGemm p;
     memset(&p, 0, sizeof(p));
+    if (st) { p.stat_parts = st->parts; p.stat_capacity = st->capacity; p.stat_nparts = st->nparts; }
     p.out_dtype = out_dtype;
     const int64_t T = (int64_t)g.kh * g.kw;
     if (wlay == 0) { p.w_st = (int64_t)N * K; p.w_sn = K; p.w_sk = 1; }
@@ -210,6 +214,18 @@ extern "C" int vp_conv_fwd_cl(const VpConvGeom* g, const void* x, const void* w_
     VP_CHECK_ARG(x && w_cl && y, "vp_conv_fwd_cl: null pointer");
     return conv_like(*g, !g->transposed, x, g->hi, g->wi, g->ci, y, g->ho, g->wo, g->co, w_cl, bias, act, slope, VP_BF16, out_dtype,
                      VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 2 : 1);
+}
+
+/* vp_conv_fwd_cl for a layer followed by BatchNorm (bf16 output, no bias / activation) that also returns the statistics of y:
+ * stat_parts[*nparts][2][co] fp32 = per-CTA partial column sums and sums of squares (vp_norm_finalize_parts adds them up).
+ * stat_capacity: parts the buffer can hold (2 * #SMs is always enough).  co must be a multiple of 64, <= 512. */
+extern "C" int vp_conv_fwd_cl_stats(const VpConvGeom* g, const void* x, const void* w_cl, void* y, float* stat_parts, int stat_capacity,
+                                    int* nparts, void* stream) {
+    if (!check_geom(g, "vp_conv_fwd_cl_stats")) return VP_EINVAL;
+    VP_CHECK_ARG(x && w_cl && y && stat_parts && nparts && stat_capacity > 0, "vp_conv_fwd_cl_stats: null pointer");
+    StatOut st{stat_parts, stat_capacity, nparts};
+    return conv_like(*g, !g->transposed, x, g->hi, g->wi, g->ci, y, g->ho, g->wo, g->co, w_cl, nullptr, VP_ACT_NONE, 0.f, VP_BF16, VP_BF16,
+                     VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 2 : 1, &st);
 }
 
 extern "C" int vp_conv_dgrad_cl(const VpConvGeom* g, const void* dy, const void* w_cl, void* dx, int out_dtype, void* stream) {

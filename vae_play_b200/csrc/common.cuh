@@ -113,6 +113,11 @@ struct TapGemm {
     // w_sn = K, w_sk = 1.  One of w_sn / w_sk must be 1: w_sk == 1 is a K-major operand, w_sn == 1 an MN-major one
     // (the module's own channels-last weight read without any re-packing).
     int64_t w_st, w_sn, w_sk;
+    // optional (tcgen05 engine, bf16 output, N % 64 == 0, N <= 512, no bias / activation): per-CTA partial column sums and
+    // sums of squares of the stored output, stat_parts[cta][2][N] fp32; *stat_nparts receives the number of CTAs.
+    float* stat_parts;
+    int stat_capacity;
+    int* stat_nparts;
     TapList taps;
 };
 

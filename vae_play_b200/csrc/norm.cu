@@ -377,6 +377,59 @@ extern "C" int vp_norm_finalize(const double* sums, const float* gamma, const fl
     return VP_OK;
 }
 
+namespace vp {
+namespace {
+// block = 32 channels x 8 part lanes: coalesced rows of the parts array, 8 independent partial sums per channel
+__global__ void __launch_bounds__(256) finalize_parts_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
+                                                             float eps, float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C) {
+    __shared__ double sh1[8][32], sh2[8][32];
+    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    double a1 = 0, a2 = 0;
+    if (c < C) {
+#pragma unroll 4
+        for (int i = pl; i < nparts; i += 8) { a1 += (double)parts[(size_t)i * 2 * C + c]; a2 += (double)parts[(size_t)i * 2 * C + C + c]; }
+    }
+    sh1[pl][cl] = a1; sh2[pl][cl] = a2;
+    __syncthreads();
+    if (pl != 0 || c >= C) return;
+    double s1 = 0, s2 = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s1 += sh1[i][cl]; s2 += sh2[i][cl]; }
+    const double m = (double)rows;
+    const double mu = s1 / m;
+    double var = s2 / m - mu * mu;
+    if (var < 0) var = 0;
+    const float is = (float)(1.0 / sqrt(var + (double)eps));
+    const float g = gamma ? gamma[c] : 1.f;
+    const float b = beta ? beta[c] : 0.f;
+    mean[c] = (float)mu;
+    invstd[c] = is;
+    const float sc = g * is;
+    scale[c] = sc;
+    shift[c] = b - (float)mu * sc;
+    if (running_mean) {
+        const double unb = var * m / (m > 1 ? m - 1 : 1);
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+    }
+}
+}  // namespace
+}  // namespace vp
+
+/* vp_norm_finalize for BatchNorm statistics delivered as per-CTA partial sums by a GEMM epilogue (vp_conv_fwd_cl_stats,
+ * vp_thin_conv_fwd_stats): parts[nparts][2][c] fp32, added in double in a fixed order (deterministic). */
+extern "C" int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta, float* running_mean,
+                                      float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
+                                      float* shift, int64_t rows, int c, void* stream) {
+    VP_CHECK_ARG(parts && nparts > 0 && mean && invstd && scale && shift && rows > 0 && c > 0, "vp_norm_finalize_parts: bad arguments");
+    finalize_parts_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(parts, nparts, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                         mean, invstd, scale, shift, rows, c);
+    VP_CHECK_LAUNCH("vp_norm_finalize_parts");
+    return VP_OK;
+}
+
 extern "C" int vp_norm_apply_act(const void* x, const float* scale, const float* shift, void* a, int dtype,
                                  int64_t groups, int64_t rpg, int c, int act, float slope, void* stream) {
     VP_CHECK_ARG(x && a && groups > 0 && rpg > 0 && c > 0, "vp_norm_apply_act: bad arguments");

@@ -54,6 +54,21 @@ int encode_weight_map(CUtensorMap* m, const TapGemm& p, bool bmn, int BN) {
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+int encode_out_map(CUtensorMap* m, void* D, int N, int hd, int wd, int n, int ds, int doy, int dox, int bw, int bh, int bb) {
+    EncodeTiledFn encode = get_encode();
+    const int gh = (hd - doy + ds - 1) / ds, gw = (wd - dox + ds - 1) / ds;
+    if (gh <= 0 || gw <= 0) return -1;
+    uint8_t* base = (uint8_t*)D + ((int64_t)doy * wd + dox) * N * 2;
+    cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)gw, (cuuint64_t)gh, (cuuint64_t)n};
+    cuuint64_t strides[3] = {(cuuint64_t)ds * N * 2, (cuuint64_t)ds * wd * N * 2, (cuuint64_t)hd * wd * N * 2};
+    cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bb};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    if (((uintptr_t)base & 15) != 0) return -1;
+    CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
@@ -117,6 +132,8 @@ struct TcParams {
     int ksplit;            // > 1: the (tap, k-block) iterations of a tile are split over ksplit CTAs, partial tiles are
     int iters_per_split;   //      added into an fp32 workspace (D) with red.global.add and finished by splitk_finish_kernel
     int base_tiles;
+    int tma_store;         // bf16 output, N % 64 == 0: epilogue through per-warp staging tiles + TMA stores (omaps)
+    float* stat_parts;     // [gridDim.x][2][N] per-CTA BatchNorm partial sums of the stored output, or null
     TcPhase ph[kMaxPhases];
 };
 
@@ -124,7 +141,9 @@ template <int BN, int STAGES>
 struct SmemLayout {
     static constexpr int kBBytes = BN * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kBarOffset = STAGES * kStageBytes;
+    static constexpr int kOutOffset = STAGES * kStageBytes;                 // 4 warps x [32 rows][64 B] staging tiles
+    static constexpr int kStatOffset = kOutOffset + 4 * 2048;               // sum[kStatMaxN], sumsq[kStatMaxN]
+    static constexpr int kBarOffset = kStatOffset + 2 * kStatMaxN * 4;
     static constexpr int kTotal = kBarOffset + (2 * STAGES + 4) * 8 + 16;
 };
 
@@ -154,6 +173,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int q, int B
 template <int BN, int STAGES, int CTAS_PER_SM, bool BMN>
 __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                  const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ OutMaps omaps,
                                                                  const __grid_constant__ TcParams p) {
     using L = SmemLayout<BN, STAGES>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -163,6 +183,9 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
     uint64_t* acc_full = empty + STAGES;     // [2]
     uint64_t* acc_empty = acc_full + 2;      // [2]
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    float* s_stat = (float*)(smem + L::kStatOffset);
+    if (p.stat_parts)
+        for (int i = threadIdx.x; i < 2 * kStatMaxN; i += kFwdThreads) s_stat[i] = 0.f;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -269,6 +292,30 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
             constexpr int CH = BN >= 32 ? 32 : 16;
+            if (BN >= 32 && p.tma_store) {
+                // staging tile -> (BatchNorm partial sums) -> TMA store; the warp's 32 rows are a sub-brick of the tile
+                uint8_t* st = smem + L::kOutOffset + (warp & 3) * 2048;
+                const int r0 = lane_base;
+                const uint32_t row_mask = __ballot_sync(0xffffffffu, row_ok);
+                const int sx = tc.gx0 + r0 % p.wt, sy = tc.gy0 + (r0 / p.wt) % p.ht, sn = tc.n0 + r0 / (p.wt * p.ht);
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    if (tc.col0 + c >= p.N) break;
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + buf * kAccCols + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+                    if (lane == 0) tma_store_wait_read<0>();       // the previous store has finished reading the staging tile
+                    tmem_ld_wait();
+                    __syncwarp();
+                    stage_chunk32_sw64(st, lane, tc.col0 + c, v, p.bias, p.act, p.slope);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (p.stat_parts) stats_chunk32_sw64(st, lane, s_stat + tc.col0 + c, s_stat + kStatMaxN + tc.col0 + c, row_mask);
+                    if (lane == 0) {
+                        tma_store_4d(&omaps.m[tc.phase], st, tc.col0 + c, sx, sy, sn);
+                        tma_store_commit();
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < BN; c += CH) {
                 uint32_t v[32];
@@ -295,11 +342,13 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
                     }
                 }
             }
+            }
             // this warp's TMEM reads are complete (wait::ld above): hand the buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
         }
+        if (p.tma_store && lane == 0) tma_store_wait_read<0>();
     }
     // teardown: everyone is done with TMEM before the allocating warp frees it
     tc_fence_before();
@@ -308,11 +357,15 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
+    if (p.stat_parts) {
+        float* out = p.stat_parts + (size_t)blockIdx.x * 2 * p.N;
+        for (int i = threadIdx.x; i < 2 * p.N; i += kFwdThreads) out[i] = s_stat[(i < p.N) ? i : (kStatMaxN + i - p.N)];
+    }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------
 template <int BN, int STAGES, int CTAS, bool BMN = false>
-int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp, cudaStream_t s) {
+int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const OutMaps& om, const TcParams& tp, cudaStream_t s, int* grid_out = nullptr) {
     using L = SmemLayout<BN, STAGES>;
     constexpr int smem_bytes = L::kTotal + 1024;  // + alignment slack
     static bool attr_set = false;
@@ -323,7 +376,8 @@ int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const TcParams& tp,
     }
     const int slots = num_sms() * CTAS;
     const int grid = tp.total_tiles < slots ? tp.total_tiles : slots;
-    tapgemm_tc_kernel<BN, STAGES, CTAS, BMN><<<grid, kFwdThreads, smem_bytes, s>>>(mA, mB, tp);
+    if (grid_out) *grid_out = grid;
+    tapgemm_tc_kernel<BN, STAGES, CTAS, BMN><<<grid, kFwdThreads, smem_bytes, s>>>(mA, mB, om, tp);
     VP_CHECK_LAUNCH("tapgemm_tc");
     return VP_OK;
 }
@@ -429,7 +483,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     {
         const int iters = phases[0].taps.ntaps * (p.K / kBlockK);
         const int64_t out_elems = (int64_t)p.n * p.hd * p.wd * p.N;
-        if (nphases == 1 && tp.total_tiles * 2 <= num_sms() && iters >= 16 && tc_variant() != 3) {
+        if (nphases == 1 && tp.total_tiles * 2 <= num_sms() && iters >= 16 && !p.stat_parts && tc_variant() != 3) {
             int ks = num_sms() / tp.total_tiles;
             if (ks > iters / 4) ks = iters / 4;
             ws = (float*)splitk_workspace((size_t)out_elems * sizeof(float));
@@ -461,36 +515,58 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     tp.D = p.D; tp.bias = p.bias; tp.n = p.n; tp.hd = p.hd; tp.wd = p.wd; tp.N = p.N;
     tp.as = p.as; tp.ds = p.ds; tp.act = p.act; tp.slope = p.slope;
     tp.out_f32 = (p.out_dtype == VP_F32); tp.kblocks = p.K / kBlockK;
+    OutMaps om;
+    memset(&om, 0, sizeof(om));
+    int grid_used = 0;
+    tp.tma_store = 0; tp.stat_parts = nullptr;
+    if (tp.ksplit == 1 && !tp.out_f32 && p.N % 64 == 0 && BN >= 32 && !one_cta && tc_variant() != 4) {
+        // warp q of the epilogue owns rows [32q, 32q+32) of the (bt x ht x wt) brick: a {bw, bh, bb} sub-brick
+        const int bw = wt < 32 ? wt : 32, bh = ht < 32 / bw ? ht : 32 / bw, bb = 32 / (bw * bh);
+        bool ok = true;
+        for (int i = 0; i < nphases && ok; ++i)
+            ok = encode_out_map(&om.m[i], p.D, p.N, p.hd, p.wd, p.n, p.ds, phases[i].doy, phases[i].dox, bw, bh, bb) == 0;
+        if (ok) {
+            tp.tma_store = 1;
+            if (p.stat_parts && p.N <= kStatMaxN && p.bias == nullptr && p.act == VP_ACT_NONE) tp.stat_parts = p.stat_parts;
+        }
+    }
+    if (p.stat_parts && !tp.stat_parts) { set_error("tcgen05 engine: epilogue statistics not available for this shape"); return VP_EUNSUPPORTED; }
+    if (tp.stat_parts) {
+        const int slots = num_sms() * 2;
+        const int g = tp.total_tiles < slots ? tp.total_tiles : slots;
+        if (g > p.stat_capacity) { set_error("tcgen05 engine: statistics buffer holds %d parts, %d needed", p.stat_capacity, g); return VP_EINVAL; }
+        if (p.stat_nparts) *p.stat_nparts = g;
+    }
     if (tp.ksplit > 1) {
         tp.D = ws; tp.out_f32 = 1;
         int rc;
-        if (bmn) rc = BN == 128 ? launch_cfg<128, 3, 2, true>(mA, mB, tp, s) : launch_cfg<64, 4, 2, true>(mA, mB, tp, s);
+        if (bmn) rc = BN == 128 ? launch_cfg<128, 3, 2, true>(mA, mB, om, tp, s, &grid_used) : launch_cfg<64, 4, 2, true>(mA, mB, om, tp, s, &grid_used);
         else switch (BN) {
-            case 128: rc = launch_cfg<128, 3, 2>(mA, mB, tp, s); break;
-            case 64: rc = launch_cfg<64, 4, 2>(mA, mB, tp, s); break;
-            case 32: rc = launch_cfg<32, 5, 2>(mA, mB, tp, s); break;
-            default: rc = launch_cfg<16, 5, 2>(mA, mB, tp, s); break;
+            case 128: rc = launch_cfg<128, 3, 2>(mA, mB, om, tp, s, &grid_used); break;
+            case 64: rc = launch_cfg<64, 4, 2>(mA, mB, om, tp, s, &grid_used); break;
+            case 32: rc = launch_cfg<32, 5, 2>(mA, mB, om, tp, s, &grid_used); break;
+            default: rc = launch_cfg<16, 5, 2>(mA, mB, om, tp, s, &grid_used); break;
         }
         if (rc) return rc;
         return launch_splitk_finish(ws, p.D, p.bias, p.act, p.slope, (int64_t)p.n * p.hd * p.wd * p.N, p.N, p.out_dtype == VP_F32, s);
     }
     if (one_cta) {
         switch (BN) {
-            case 256: return launch_cfg<256, 4, 1>(mA, mB, tp, s);
-            case 128: return launch_cfg<128, 6, 1>(mA, mB, tp, s);
-            case 64: return launch_cfg<64, 8, 1>(mA, mB, tp, s);
-            case 32: return launch_cfg<32, 8, 1>(mA, mB, tp, s);
-            default: return launch_cfg<16, 8, 1>(mA, mB, tp, s);
+            case 256: return launch_cfg<256, 4, 1>(mA, mB, om, tp, s, &grid_used);
+            case 128: return launch_cfg<128, 6, 1>(mA, mB, om, tp, s, &grid_used);
+            case 64: return launch_cfg<64, 8, 1>(mA, mB, om, tp, s, &grid_used);
+            case 32: return launch_cfg<32, 8, 1>(mA, mB, om, tp, s, &grid_used);
+            default: return launch_cfg<16, 8, 1>(mA, mB, om, tp, s, &grid_used);
         }
     }
-    if (bmn) return BN == 128 ? launch_cfg<128, 3, 2, true>(mA, mB, tp, s) : launch_cfg<64, 4, 2, true>(mA, mB, tp, s);
+    if (bmn) return BN == 128 ? launch_cfg<128, 3, 2, true>(mA, mB, om, tp, s, &grid_used) : launch_cfg<64, 4, 2, true>(mA, mB, om, tp, s, &grid_used);
     // default: two persistent CTAs per SM (two TMA issue streams, two epilogues in flight), <= 113 KB smem and
     // <= 256 TMEM columns each
     switch (BN) {
-        case 128: return launch_cfg<128, 3, 2>(mA, mB, tp, s);
-        case 64: return launch_cfg<64, 4, 2>(mA, mB, tp, s);
-        case 32: return launch_cfg<32, 5, 2>(mA, mB, tp, s);
-        default: return launch_cfg<16, 5, 2>(mA, mB, tp, s);
+        case 128: return launch_cfg<128, 3, 2>(mA, mB, om, tp, s, &grid_used);
+        case 64: return launch_cfg<64, 4, 2>(mA, mB, om, tp, s, &grid_used);
+        case 32: return launch_cfg<32, 5, 2>(mA, mB, om, tp, s, &grid_used);
+        default: return launch_cfg<16, 5, 2>(mA, mB, om, tp, s, &grid_used);
     }
 }
 

@@ -48,6 +48,8 @@ struct WinParams {
     int Hh, Wh;                // halo extent in pixels
     int halo_bytes;            // Hh*Wh*128 rounded up to 1024
     int ntiles_n, total_tiles, nphases;
+    int tma_store;             // bf16 output, N % 64 == 0: staging tiles + TMA stores (omaps)
+    float* stat_parts;         // [gridDim.x][2][N] per-CTA BatchNorm partial sums of the stored output, or null
     WinPhase ph[kMaxPh];
 };
 
@@ -76,6 +78,7 @@ __device__ __forceinline__ uint64_t wdesc_mn_sw128(uint32_t saddr) {
 template <int BN, int BSTAGES, bool BMN>
 __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                    const __grid_constant__ CUtensorMap mapB,
+                                                                   const __grid_constant__ OutMaps omaps,
                                                                    const __grid_constant__ WinParams p) {
     constexpr int kBBytes = BN * 128;
     constexpr int kAccCols = BN < 32 ? 32 : BN;        // TMEM columns per brick accumulator
@@ -84,7 +87,11 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int a_stage_bytes = 2 * p.halo_bytes;
     uint8_t* smem_b = smem + kAStages * a_stage_bytes;
-    uint64_t* a_full = (uint64_t*)(smem_b + BSTAGES * kBBytes);
+    uint8_t* smem_out = smem_b + BSTAGES * kBBytes;            // 4 warps x 2 x [32 rows][64 B] staging tiles
+    float* s_stat = (float*)(smem_out + 4 * 2 * 2048);          // sum[kStatMaxN], sumsq[kStatMaxN]
+    uint64_t* a_full = (uint64_t*)(s_stat + 2 * kStatMaxN);
+    if (p.stat_parts)
+        for (int i = threadIdx.x; i < 2 * kStatMaxN; i += kWThreads) s_stat[i] = 0.f;
     uint64_t* a_empty = a_full + kAStages;
     uint64_t* b_full = a_empty + kAStages;
     uint64_t* b_empty = b_full + BSTAGES;
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
         const int lane_base = (warp & 3) * 32;
         const int r = lane_base + lane;
         const int by = r >> 3, bx = r & 7;
-        uint32_t i = 0;
+        uint32_t i = 0, sg = 0;
         for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
             const WTile t = wdecode(p, q, BN);
             const WinPhase& ph = p.ph[t.phase];
@@ -215,6 +222,28 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
                 const bool row_ok = gy < ph.gh && gx < ph.gw && oy < p.hd && ox < p.wd;
                 const int64_t row_off = (((int64_t)t.n * p.hd + oy) * p.wd + ox) * p.N;
                 constexpr int CH = BN >= 32 ? 32 : 16;
+                if (BN >= 32 && p.tma_store) {
+                    uint8_t* my_stage = smem_out + (warp & 3) * 4096;
+                    const uint32_t row_mask = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll 1
+                    for (int c = 0; c < BN; c += 32, ++sg) {
+                        if (t.col0 + c >= p.N) break;
+                        uint8_t* st = my_stage + (sg & 1) * 2048;
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + (buf * 2 + br) * kAccCols + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+                        if (lane == 0) tma_store_wait_read<1>();       // the store that last read this buffer has drained it
+                        tmem_ld_wait();
+                        __syncwarp();
+                        stage_chunk32_sw64(st, lane, t.col0 + c, v, p.bias, p.act, p.slope);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (p.stat_parts) stats_chunk32_sw64(st, lane, s_stat + t.col0 + c, s_stat + kStatMaxN + t.col0 + c, row_mask);
+                        if (lane == 0) {
+                            tma_store_4d(&omaps.m[t.phase], st, t.col0 + c, t.gx0 + br * kBrickW, t.gy0 + (warp & 3) * 4, t.n);
+                            tma_store_commit();
+                        }
+                    }
+                } else {
 #pragma unroll 1
                 for (int c = 0; c < BN; c += CH) {
                     uint32_t v[32];
@@ -224,11 +253,13 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
                     tmem_ld_wait();
                     if (row_ok) store_chunk<CH>(v, p.D, row_off, t.col0 + c, p.N, p.bias, p.act, p.slope, p.out_f32 != 0);
                 }
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[buf])) : "memory");
         }
+        if (p.tma_store && lane == 0) tma_store_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -236,11 +267,16 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
+    if (p.stat_parts) {
+        float* out = p.stat_parts + (size_t)blockIdx.x * 2 * p.N;
+        for (int i = threadIdx.x; i < 2 * p.N; i += kWThreads) out[i] = s_stat[(i < p.N) ? i : (kStatMaxN + i - p.N)];
+    }
 }
 
 template <int BN, int BSTAGES, bool BMN = false>
-int launch_win(const CUtensorMap& mA, const CUtensorMap& mB, const WinParams& wp, cudaStream_t s) {
-    const int smem_bytes = kAStages * 2 * wp.halo_bytes + BSTAGES * BN * 128 + (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024;
+int launch_win(const CUtensorMap& mA, const CUtensorMap& mB, const OutMaps& om, const WinParams& wp, cudaStream_t s) {
+    const int smem_bytes = kAStages * 2 * wp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 +
+                           (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024;
     if (smem_bytes > 227 * 1024) { set_error("windowed tap GEMM: %d bytes of shared memory", smem_bytes); return VP_EUNSUPPORTED; }
     static int attr_set = 0;
     if (attr_set < smem_bytes) {
@@ -249,7 +285,7 @@ int launch_win(const CUtensorMap& mA, const CUtensorMap& mB, const WinParams& wp
         attr_set = smem_bytes;
     }
     const int grid = wp.total_tiles < num_sms() ? wp.total_tiles : num_sms();
-    tapgemm_win_kernel<BN, BSTAGES, BMN><<<grid, kWThreads, smem_bytes, s>>>(mA, mB, wp);
+    tapgemm_win_kernel<BN, BSTAGES, BMN><<<grid, kWThreads, smem_bytes, s>>>(mA, mB, om, wp);
     VP_CHECK_LAUNCH("tapgemm_win");
     return VP_OK;
 }
@@ -311,12 +347,30 @@ int launch_tapgemm_win(const TapGemm* phases, int nphases, cudaStream_t s) {
     const bool bmn = p.w_sn == 1 && p.w_sk != 1;
     if ((!bmn && p.w_sk != 1) || (bmn && (p.N % 64 != 0 || BN < 64))) return VP_EUNSUPPORTED;
     if (encode_weight_map(&mB, p, bmn, BN)) return VP_EUNSUPPORTED;
-    if (bmn) return BN == 128 ? launch_win<128, 5, true>(mA, mB, wp, s) : launch_win<64, 8, true>(mA, mB, wp, s);
+    OutMaps om;
+    memset(&om, 0, sizeof(om));
+    wp.tma_store = 0; wp.stat_parts = nullptr;
+    if (!wp.out_f32 && p.N % 64 == 0 && BN >= 32) {
+        bool ok = true;
+        for (int i = 0; i < nphases && ok; ++i)
+            ok = encode_out_map(&om.m[i], p.D, p.N, p.hd, p.wd, p.n, p.ds, phases[i].doy, phases[i].dox, kBrickW, 4, 1) == 0;
+        if (ok) {
+            wp.tma_store = 1;
+            if (p.stat_parts && p.N <= kStatMaxN && p.bias == nullptr && p.act == VP_ACT_NONE) wp.stat_parts = p.stat_parts;
+        }
+    }
+    if (p.stat_parts && !wp.stat_parts) return VP_EUNSUPPORTED;      // the caller's other engine reports the error
+    if (wp.stat_parts) {
+        const int g = wp.total_tiles < num_sms() ? wp.total_tiles : num_sms();
+        if (g > p.stat_capacity) { set_error("windowed tap GEMM: statistics buffer holds %d parts, %d needed", p.stat_capacity, g); return VP_EINVAL; }
+        if (p.stat_nparts) *p.stat_nparts = g;
+    }
+    if (bmn) return BN == 128 ? launch_win<128, 4, true>(mA, mB, om, wp, s) : launch_win<64, 6, true>(mA, mB, om, wp, s);
     switch (BN) {
-        case 128: return launch_win<128, 5>(mA, mB, wp, s);
-        case 64: return launch_win<64, 8>(mA, mB, wp, s);
-        case 32: return launch_win<32, 8>(mA, mB, wp, s);
-        default: return launch_win<16, 8>(mA, mB, wp, s);
+        case 128: return launch_win<128, 4>(mA, mB, om, wp, s);
+        case 64: return launch_win<64, 6>(mA, mB, om, wp, s);
+        case 32: return launch_win<32, 8>(mA, mB, om, wp, s);
+        default: return launch_win<16, 8>(mA, mB, om, wp, s);
     }
 }
 

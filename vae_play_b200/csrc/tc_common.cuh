@@ -15,6 +15,8 @@ int encode_weight_map(CUtensorMap* m, const TapGemm& p, bool bmn, int BN);
 void set_splitk_workspace(void* ptr, size_t bytes);
 void* splitk_workspace(size_t bytes);
 int launch_splitk_finish(const float* ws, void* D, const float* bias, int act, float slope, int64_t n, int N, bool out_f32, cudaStream_t s);
+// output tensor map of one phase: pixel (gy, gx) of the phase grid -> D[n, gy*ds + doy, gx*ds + dox, :], box {32 ch, bw, bh, bb}, SWIZZLE_64B
+int encode_out_map(CUtensorMap* m, void* D, int N, int hd, int wd, int n, int ds, int doy, int dox, int bw, int bh, int bb);
 int pow2_floor(int v);
 int pow2_ceil(int v);
 int num_sms();
@@ -223,6 +225,73 @@ __device__ __forceinline__ void stage_chunk32(uint8_t* stile, int lane, int cbas
         *reinterpret_cast<uint4*>(row + (((j0 + j) ^ (lane & 7)) << 4)) = pk;
     }
 }
+
+// ---- 32-column staging tiles (SWIZZLE_64B) for the persistent GEMM kernels -------------------------------------------
+// [32 rows][64 B] per warp, 512-byte aligned; chunk j (16 B = 8 bf16) of row r lives at ((j ^ ((r >> 1) & 3)) << 4).
+// Half the shared memory of the 64-column tiles above, which is what lets two CTAs of tapgemm_tc_kernel share an SM.
+__device__ __forceinline__ void stage_chunk32_sw64(uint8_t* stile, int lane, int cbase, const uint32_t* v, const float* bias, int act, float slope) {
+    uint8_t* row = stile + lane * 64;
+    const bool plain = (bias == nullptr) && (act == VP_ACT_NONE);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = __uint_as_float(v[j * 8 + e]);
+            if (!plain) {
+                if (bias) x += bias[cbase + j * 8 + e];
+                x = act_fwd(x, act, slope);
+            }
+            f[e] = x;
+        }
+        uint4 pk;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]), h3 = __floats2bfloat162_rn(f[6], f[7]);
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(row + ((j ^ ((lane >> 1) & 3)) << 4)) = pk;
+    }
+}
+// BatchNorm statistics of the tile that is about to be stored: per-column sum and sum of squares of the staged bf16 values
+// (exactly the numbers a separate pass over the stored tensor would see), added to the CTA's shared accumulators.
+// Lane = (row parity h, 32-bit word w): conflict-free 4-byte reads.  row_mask: bit r set when row r of the warp's sub-tile is an
+// output pixel inside the tensor (rows beyond a ragged edge are computed from partly valid inputs and must not be counted).
+__device__ __forceinline__ void stats_chunk32_sw64(const uint8_t* stile, int lane, float* s_sum, float* s_sq, uint32_t row_mask) {
+    const int h = lane >> 4, w = lane & 15;
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int r = 2 * i + h;
+        uint32_t word = *reinterpret_cast<const uint32_t*>(stile + r * 64 + (((w >> 2) ^ (i & 3)) << 4) + (w & 3) * 4);
+        word = ((row_mask >> r) & 1u) ? word : 0u;
+        const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xffff0000u);
+        s0 += lo; q0 = fmaf(lo, lo, q0);
+        s1 += hi; q1 = fmaf(hi, hi, q1);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+    if (h == 0) {
+        atomicAdd(s_sum + 2 * w, s0); atomicAdd(s_sum + 2 * w + 1, s1);
+        atomicAdd(s_sq + 2 * w, q0); atomicAdd(s_sq + 2 * w + 1, q1);
+    }
+}
+
+// same for a 64-column [32 rows][128 B] SWIZZLE_128B staging tile: lane = 32-bit word (two channels), all 32 rows
+__device__ __forceinline__ void stats_group64_sw128(const uint8_t* stile, int lane, float* s_sum, float* s_sq) {
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const uint32_t word = *reinterpret_cast<const uint32_t*>(stile + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
+        const float lo = __uint_as_float(word << 16), hi = __uint_as_float(word & 0xffff0000u);
+        s0 += lo; q0 = fmaf(lo, lo, q0);
+        s1 += hi; q1 = fmaf(hi, hi, q1);
+    }
+    atomicAdd(s_sum + 2 * lane, s0); atomicAdd(s_sum + 2 * lane + 1, s1);
+    atomicAdd(s_sq + 2 * lane, q0); atomicAdd(s_sq + 2 * lane + 1, q1);
+}
+
+struct OutMaps { CUtensorMap m[4]; };      // one output tensor map per output-parity phase (TMA-store epilogue)
+constexpr int kStatMaxN = 512;             // widest layer whose BatchNorm statistics are taken in the GEMM epilogue
 
 }  // namespace tc
 }  // namespace vp

@@ -208,6 +208,7 @@ struct ThinKParams {
     int out_f32;
     int tiles_w, tiles_h, total_tiles;
     int tma_store;                    // bf16 output with N % 64 == 0: epilogue through shared memory + TMA store
+    float* stat_parts;                // [gridDim.x][2][N] per-CTA BatchNorm partial sums of the stored output, or null
 };
 
 constexpr int kKStages = 3;
@@ -219,13 +220,15 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
     uint8_t* smem_b = smem + kKStages * 16384;                  // weight tile: N rows x 128 B (<= 16 KB)
     uint8_t* stage_out = smem_b + 16384;                        // per epilogue warp: 2 x [32 rows][128 B] staging tiles
     uint8_t* halo = stage_out + 4 * 2 * 4096;                   // 2 source-halo buffers
-    uint64_t* full = (uint64_t*)(halo + 2 * kHaloBuf);
+    float* s_stat = (float*)(halo + 2 * kHaloBuf);              // sum[128], sumsq[128]
+    uint64_t* full = (uint64_t*)(s_stat + 256);
     uint64_t* empty = full + kKStages;
     uint64_t* acc_full = empty + kKStages;
     uint64_t* acc_empty = acc_full + 2;
     uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kTmemCols = 256;                              // 2 accumulators x 128 columns
+    if (threadIdx.x < 256) s_stat[threadIdx.x] = 0.f;
 
     if (warp == 4) {
         if (lane == 0) {
@@ -305,6 +308,7 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
+                    if (p.stat_parts) stats_group64_sw128(st, lane, s_stat + c, s_stat + 128 + c);
                     if (lane == 0) {
                         tma_store_4d(&mapD, st, c, tw * 8, th * 16 + (warp & 3) * 4, m);
                         tma_store_commit();
@@ -331,16 +335,26 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
     }
+    if (p.stat_parts) {
+        float* out = p.stat_parts + (size_t)blockIdx.x * 2 * p.N;
+        for (int i = threadIdx.x; i < 2 * p.N; i += kKThreads) out[i] = s_stat[(i < p.N) ? i : (128 + i - p.N)];
+    }
 }
 
-constexpr int kKSmem = kKStages * 16384 + 16384 + 4 * 2 * 4096 + 2 * kHaloBuf + (2 * kKStages + 4) * 8 + 16 + 1024;
+constexpr int kKSmem = kKStages * 16384 + 16384 + 4 * 2 * 4096 + 2 * kHaloBuf + 256 * 4 + (2 * kKStages + 4) * 8 + 16 + 1024;
 
 int encode_box(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh);
 
-int launch_thin_k(ThinKParams& p, cudaStream_t s) {
+int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* stat_nparts = nullptr) {
     CUtensorMap mD;
     memset(&mD, 0, sizeof(mD));
     p.tma_store = (!p.out_f32 && p.N % 64 == 0) ? 1 : 0;
+    if (p.stat_parts) {
+        const int g = p.total_tiles < 2 * num_sms() ? p.total_tiles : 2 * num_sms();
+        if (!p.tma_store || p.bias || p.act != VP_ACT_NONE) { set_error("thin_k: epilogue statistics need a bf16 output, N %% 64 == 0, no bias/activation"); return VP_EUNSUPPORTED; }
+        if (g > stat_capacity) { set_error("thin_k: statistics buffer holds %d parts, %d needed", stat_capacity, g); return VP_EINVAL; }
+        if (stat_nparts) *stat_nparts = g;
+    }
     if (p.tma_store && encode_box(&mD, p.D, p.N, p.gw, p.gh, p.n, 8, 4)) { set_error("thin_k: cuTensorMapEncodeTiled(D) failed"); return VP_EUNSUPPORTED; }
     static bool attr_set = false;
     if (!attr_set) {
@@ -690,8 +704,24 @@ void fill_gather(ThinGather& tg, const VpConvGeom* g, bool flipped) {
 }  // namespace
 
 // y = act(conv(x, w) + bias) for an nn.Conv2d with ONE input channel (thin K) or <= 2 output channels at stride 1 (thin N).
+static int thin_conv_fwd_impl(const VpConvGeom* g, const void* x, const float* w, const float* bias, void* y, int out_dtype, int act, float slope,
+                              float* stat_parts, int stat_capacity, int* stat_nparts, void* stream);
+
 extern "C" int vp_thin_conv_fwd(const VpConvGeom* g, const void* x, const float* w, const float* bias, void* y, int out_dtype, int act,
                                 float slope, void* stream) {
+    return thin_conv_fwd_impl(g, x, w, bias, y, out_dtype, act, slope, nullptr, 0, nullptr, stream);
+}
+
+// same (single input channel, bf16 output, no bias / activation) + per-CTA BatchNorm partial sums of y: stat_parts[*nparts][2][co]
+extern "C" int vp_thin_conv_fwd_stats(const VpConvGeom* g, const void* x, const float* w, void* y, float* stat_parts, int stat_capacity,
+                                      int* nparts, void* stream) {
+    VP_CHECK_ARG(stat_parts && nparts && stat_capacity > 0, "vp_thin_conv_fwd_stats: bad statistics buffer");
+    if (g && g->ci != 1) { set_error("vp_thin_conv_fwd_stats: single-channel input only"); return VP_EUNSUPPORTED; }
+    return thin_conv_fwd_impl(g, x, w, nullptr, y, VP_BF16, VP_ACT_NONE, 0.f, stat_parts, stat_capacity, nparts, stream);
+}
+
+static int thin_conv_fwd_impl(const VpConvGeom* g, const void* x, const float* w, const float* bias, void* y, int out_dtype, int act, float slope,
+                              float* stat_parts, int stat_capacity, int* stat_nparts, void* stream) {
     if (!thin_geom_ok(g, "vp_thin_conv_fwd")) return VP_EINVAL;
     VP_CHECK_ARG(x && w && y, "vp_thin_conv_fwd: null pointer");
     if (!tc_available() || g->transposed) { set_error("vp_thin_conv_fwd: needs sm_100 and a plain Conv2d"); return VP_EUNSUPPORTED; }
@@ -710,8 +740,10 @@ extern "C" int vp_thin_conv_fwd(const VpConvGeom* g, const void* x, const float*
         const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.n;
         if (total > 0x7fffffff) { set_error("vp_thin_conv_fwd: too many tiles"); return VP_EUNSUPPORTED; }
         p.total_tiles = (int)total;
-        return launch_thin_k(p, s);
+        p.stat_parts = stat_parts;
+        return launch_thin_k(p, s, stat_capacity, stat_nparts);
     }
+    if (stat_parts) { set_error("vp_thin_conv_fwd_stats: shape not of the thin-input form"); return VP_EUNSUPPORTED; }
     if (g->stride == 1 && g->co * T <= 32 && T <= kMaxThinTaps && g->ci % 64 == 0 && g->ci <= 64 * kNMaxKb && g->kh <= 5 && g->kw <= 5 &&
         ((uintptr_t)x & 15) == 0) {
         ThinNParams p;

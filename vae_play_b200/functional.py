@@ -55,6 +55,11 @@ def get_precision() -> str:
     return _STATE["precision"]
 
 
+def set_epilogue_stats(on: bool):
+    """BatchNorm statistics from the GEMM epilogue (default) or from a separate pass over the stored output (tests)."""
+    _STATE["epilogue_stats"] = bool(on)
+
+
 def set_engine(name: str):
     """'auto' | 'simt' | 'tc' -- engine used for the contractions (tests force one or the other)."""
     _STATE["engine"] = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tc": _lib.ENGINE_TC}[name]
@@ -230,6 +235,32 @@ class TapLayer:
                       ACT[act], float(slope), _STATE["engine"], _stream())
         return y
 
+    def stats_in_epilogue(self, dt, weight):
+        """True when the forward GEMM can also deliver the BatchNorm statistics of its output (vp_*_fwd_*_stats)."""
+        weight = weight.detach()
+        if self.cout % 64 or self.cout > 512 or _STATE.get("epilogue_stats", True) is False:
+            return False
+        if self._thin("fwd", dt, weight):
+            return self.cin == 1 and self.cout <= 128
+        return self._cl(dt, weight)
+
+    def fwd_stats(self, x, weight):
+        """y (bf16, no bias / activation) and the per-CTA partial sums of its batch statistics: (y, parts, nparts)."""
+        n, h, w, _ = x.shape
+        weight = weight.detach()
+        shp = self.out_shape(n, h, w)
+        y = torch.empty(shp, dtype=x.dtype, device=x.device)
+        g = self._layer_geom(n, h, w, shp[1], shp[2])
+        cap = 2 * _num_sms(x.device)
+        parts = torch.empty(cap * 2 * self.cout, dtype=torch.float32, device=x.device)
+        nparts = C.c_int(0)
+        if self._thin("fwd", x.dtype, weight):
+            _lib.call("vp_thin_conv_fwd_stats", C.byref(g), _ptr(x), _ptr(weight), _ptr(y), _ptr(parts), cap, C.byref(nparts), _stream())
+        else:
+            _lib.call("vp_conv_fwd_cl_stats", C.byref(g), _ptr(x), _ptr(self._shadow(weight)), _ptr(y), _ptr(parts), cap,
+                      C.byref(nparts), _stream())
+        return y, parts, nparts.value
+
     def dgrad(self, dy, weight, x_shape, out_dtype=None):
         n, h, w, _ = x_shape
         dt = dy.dtype
@@ -294,7 +325,11 @@ class _FusedLayerFn(torch.autograd.Function):
             ctx.save_for_backward(x, weight, a)
             ctx.out_dtype = out_dtype
             return a, None
-        y = layer.fwd(x, weight, bias, "none", 0.0, dt)
+        fuse_stats = norm.kind == "batch" and training and bias is None and layer.stats_in_epilogue(dt, weight)
+        if fuse_stats:
+            y, parts, nparts = layer.fwd_stats(x, weight)
+        else:
+            y = layer.fwd(x, weight, bias, "none", 0.0, dt)
         n, h, w, c = y.shape
         if norm.kind == "batch":
             groups, rpg, cc = 1, n * h * w, c
@@ -305,13 +340,17 @@ class _FusedLayerFn(torch.autograd.Function):
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         g_, b_ = gamma, beta
         if training or norm.kind == "instance":
-            sums = torch.empty(2 * groups * cc, dtype=torch.float64, device=dev)
-            _lib.call("vp_norm_stats", _ptr(y), _ptr(sums), _code(dt), groups, rpg, cc, _stream())
             rm = rv = None
             if norm.kind == "batch" and bn_module is not None and bn_module.track_running_stats:
                 rm, rv = bn_module.running_mean, bn_module.running_var
-            _lib.call("vp_norm_finalize", _ptr(sums), _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum), float(norm.eps),
-                      _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), groups, rpg, cc, _stream())
+            if fuse_stats:
+                _lib.call("vp_norm_finalize_parts", _ptr(parts), nparts, _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum),
+                          float(norm.eps), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), rpg, cc, _stream())
+            else:
+                sums = torch.empty(2 * groups * cc, dtype=torch.float64, device=dev)
+                _lib.call("vp_norm_stats", _ptr(y), _ptr(sums), _code(dt), groups, rpg, cc, _stream())
+                _lib.call("vp_norm_finalize", _ptr(sums), _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum), float(norm.eps),
+                          _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), groups, rpg, cc, _stream())
             if rm is not None:
                 bn_module.num_batches_tracked += 1
         else:
