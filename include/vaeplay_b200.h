@@ -171,18 +171,6 @@ int vp_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n,
 /* sum += a (fp32, n elements): gradient accumulation helper */
 int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
 
-/* ---- thin layers on the tensor cores: im2col + zero-padded weight panels ------------------------------------
- * A layer with <= 4 input (or output) channels has a reduction of only cin*taps elements: instead of running it on
- * CUDA cores, its taps are gathered into the channel axis so that it becomes a 1x1 layer with K = 64 or 128.
- * dst[n,gy,gx, c*taps + t] = src[n, gy*stride + ty[t], gx*stride + tx[t], c]  (0 outside src and for padding columns);
- * host_ty / host_tx: HOST arrays of `taps` offsets. */
-int vp_im2col(const void* src, void* dst, int dtype, int n, int hs, int ws, int cs, int gh, int gw, int stride, int taps,
-              const int8_t* host_ty, const int8_t* host_tx, int dst_cols, void* stream);
-/* dst[r][c] = c < cols ? (dtype) src[r*cols + c] : 0, dst row length dst_cols  (fp32 -> dtype) */
-int vp_pad_rows(const float* src, void* dst, int dtype, int64_t rows, int cols, int dst_cols, void* stream);
-/* dst[r*cols + c] = src[r*src_cols + c]  (fp32 -> fp32): drops the padding columns of a weight-gradient panel */
-int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_cols, void* stream);
-
 /* ---- contractions on the module's own weight (no packed panels) -----------------------------------------------------
  * w_cl: bf16 copy of the layer's weight in channels-last element order, i.e. exactly the bytes of the nn.Parameter when it is
  * kept in torch.channels_last memory format: nn.Conv2d [co][kh][kw][ci], nn.ConvTranspose2d [ci][kh][kw][co], nn.Linear
@@ -228,6 +216,10 @@ int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float
  * params/grads/sq: host arrays of `count` device pointers, numel: host array of element counts. */
 int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* sq, const int64_t* numel, int count,
                     float lr, float alpha, float eps, float weight_decay, void* stream);
+/* same, and shadows[i] (nullable per entry) receives the bf16 copy of the updated parameter in the same element order:
+ * the operand the in-place contractions (vp_conv_*_cl) read next step, so no cast pass is needed. */
+int vp_rmsprop_step_shadow(void* const* params, const void* const* grads, void* const* sq, void* const* shadows,
+                           const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay, void* stream);
 
 /* debug: tcgen05 operand-window probe (tools/probe_umma.py); x bf16 [256][64], ident bf16 [64][64], out fp32 [128][64] */
 int vp_debug_umma_probe(const void* x, const void* ident, float* out, int off_rows, int sbo_rows, int base_offset, void* stream);

@@ -58,9 +58,6 @@ SIGNATURES = {
     "vp_sum_into": [_p, _i64, _f, _p, _p],
     "vp_fill_from": [_p, _f, _p, _i64, _p],
     "vp_debug_umma_probe": [_p, _p, _p, _i, _i, _i, _p],
-    "vp_im2col": [_p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _i, _p],
-    "vp_pad_rows": [_p, _p, _i, _i64, _i, _i, _p],
-    "vp_unpad_rows": [_p, _p, _i64, _i, _i, _p],
     "vp_set_workspace": [_p, C.c_size_t],
     "vp_conv_fwd_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
     "vp_conv_fwd_cl_stats": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, C.POINTER(C.c_int), _p],
@@ -73,6 +70,7 @@ SIGNATURES = {
     "vp_thin_conv_dgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
     "vp_thin_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
     "vp_rmsprop_step": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
+    "vp_rmsprop_step_shadow": [_p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
 }
 PLAIN = {"vp_last_error": (C.c_char_p, []), "vp_abi_version": (_i, []), "vp_device_arch": (_i, []),
          "vp_launch_count": (_u64, [])}

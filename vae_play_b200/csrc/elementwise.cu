@@ -531,15 +531,17 @@ struct OptTable {
     float* p[kOptMax];
     const float* g[kOptMax];
     float* sq[kOptMax];
+    bf16* sh[kOptMax];          // optional bf16 copy of the updated parameter (same element order), or null
     int64_t n[kOptMax];
 };
 __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd) {
     const int ti = blockIdx.y;
     float* __restrict__ p = t.p[ti];
+    bf16* __restrict__ sh = t.sh[ti];
     const float* __restrict__ g = t.g[ti];
     float* __restrict__ sq = t.sq[ti];
     const int64_t n = t.n[ti];
-    const int64_t n4 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)sq) & 15) == 0 ? n / 4 : 0;
+    const int64_t n4 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)sq) & 15) == 0 && ((uintptr_t)sh & 7) == 0 ? n / 4 : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pv = reinterpret_cast<float4*>(p)[i];
@@ -554,19 +556,33 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
         }
         reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
         reinterpret_cast<float4*>(sq)[i] = make_float4(se[0], se[1], se[2], se[3]);
+        if (sh) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(pe[0], pe[1]), h1 = __floats2bfloat162_rn(pe[2], pe[3]);
+            reinterpret_cast<uint2*>(sh)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
     }
     for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float gg = g[i] + wd * p[i];
         const float s2 = alpha * sq[i] + (1.f - alpha) * gg * gg;
         sq[i] = s2;
-        p[i] -= lr * (gg / (sqrtf(s2) + eps));
+        const float pn = p[i] - lr * (gg / (sqrtf(s2) + eps));
+        p[i] = pn;
+        if (sh) sh[i] = __float2bfloat16_rn(pn);
     }
 }
 }  // namespace
 }  // namespace vp
 
+extern "C" int vp_rmsprop_step_shadow(void* const* params, const void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
+                                      int count, float lr, float alpha, float eps, float weight_decay, void* stream);
+
 extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* sq, const int64_t* numel, int count, float lr,
                                float alpha, float eps, float weight_decay, void* stream) {
+    return vp_rmsprop_step_shadow(params, grads, sq, nullptr, numel, count, lr, alpha, eps, weight_decay, stream);
+}
+
+extern "C" int vp_rmsprop_step_shadow(void* const* params, const void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
+                                      int count, float lr, float alpha, float eps, float weight_decay, void* stream) {
     VP_CHECK_ARG(params && grads && sq && numel && count >= 0, "vp_rmsprop_step: bad arguments");
     for (int base = 0; base < count; base += kOptMax) {
         OptTable t;
@@ -575,6 +591,7 @@ extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, vo
         for (int i = 0; i < m; ++i) {
             t.p[i] = (float*)params[base + i]; t.g[i] = (const float*)grads[base + i]; t.sq[i] = (float*)sq[base + i];
             t.n[i] = numel[base + i];
+            t.sh[i] = shadows ? (bf16*)shadows[base + i] : nullptr;
             nmax = numel[base + i] > nmax ? numel[base + i] : nmax;
         }
         int64_t bx = (nmax / 4 + 255) / 256;
@@ -583,94 +600,6 @@ extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, vo
         rmsprop_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, lr, alpha, eps, weight_decay);
         VP_CHECK_LAUNCH("vp_rmsprop_step");
     }
-    return VP_OK;
-}
-
-// ---- im2col for thin layers -----------------------------------------------------------------------------------------
-namespace vp {
-namespace {
-struct Im2colTaps { int8_t ty[kMaxTaps], tx[kMaxTaps]; };
-
-template <typename T>
-__global__ void __launch_bounds__(256) im2col_kernel(const T* __restrict__ src, T* __restrict__ dst, int n, int hs, int ws, int cs, int gh,
-                                                     int gw, int stride, int taps, const __grid_constant__ Im2colTaps tt, int dst_cols) {
-    // one thread = one destination pixel x 8 consecutive columns (16-byte store for bf16)
-    const int groups = dst_cols >> 3;
-    const int64_t total = (int64_t)n * gh * gw * groups;
-    const int valid = cs * taps;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int g8 = (int)(i % groups) * 8;
-        int64_t m = i / groups;
-        const int gx = (int)(m % gw); m /= gw;
-        const int gy = (int)(m % gh);
-        const int img = (int)(m / gh);
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int col = g8 + j;
-            float x = 0.f;
-            if (col < valid) {
-                const int c = col / taps, t = col - c * taps;
-                const int sy = gy * stride + tt.ty[t], sx = gx * stride + tt.tx[t];
-                if (sy >= 0 && sy < hs && sx >= 0 && sx < ws) x = Cvt<T>::ld(src + (((int64_t)img * hs + sy) * ws + sx) * cs + c);
-            }
-            v[j] = x;
-        }
-        T* out = dst + (((int64_t)img * gh + gy) * gw + gx) * dst_cols + g8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) Cvt<T>::st(out + j, v[j]);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) pad_rows_kernel(const float* __restrict__ src, T* __restrict__ dst, int64_t rows, int cols, int dst_cols) {
-    const int64_t total = rows * dst_cols;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / dst_cols;
-        const int c = (int)(i - r * dst_cols);
-        Cvt<T>::st(dst + i, c < cols ? src[r * cols + c] : 0.f);
-    }
-}
-
-__global__ void __launch_bounds__(256) unpad_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t rows, int cols,
-                                                         int src_cols) {
-    const int64_t total = rows * cols;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t r = i / cols;
-        dst[i] = src[r * src_cols + (i - r * cols)];
-    }
-}
-}  // namespace
-}  // namespace vp
-
-extern "C" int vp_im2col(const void* src, void* dst, int dtype, int n, int hs, int ws, int cs, int gh, int gw, int stride, int taps,
-                         const int8_t* host_ty, const int8_t* host_tx, int dst_cols, void* stream) {
-    VP_CHECK_ARG(src && dst && host_ty && host_tx && n > 0 && hs > 0 && ws > 0 && cs > 0 && gh > 0 && gw > 0 && stride > 0,
-                 "vp_im2col: bad arguments");
-    VP_CHECK_ARG(taps > 0 && taps <= kMaxTaps && dst_cols % 8 == 0 && cs * taps <= dst_cols, "vp_im2col: taps/columns");
-    Im2colTaps tt;
-    for (int t = 0; t < taps; ++t) { tt.ty[t] = host_ty[t]; tt.tx[t] = host_tx[t]; }
-    const int64_t total = (int64_t)n * gh * gw * (dst_cols >> 3);
-    const unsigned g = grid_for(total);
-    if (dtype == VP_F32) im2col_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, n, hs, ws, cs, gh, gw, stride, taps, tt, dst_cols);
-    else im2col_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, n, hs, ws, cs, gh, gw, stride, taps, tt, dst_cols);
-    VP_CHECK_LAUNCH("vp_im2col");
-    return VP_OK;
-}
-
-extern "C" int vp_pad_rows(const float* src, void* dst, int dtype, int64_t rows, int cols, int dst_cols, void* stream) {
-    VP_CHECK_ARG(src && dst && rows > 0 && cols > 0 && dst_cols >= cols, "vp_pad_rows: bad arguments");
-    const unsigned g = grid_for(rows * dst_cols);
-    if (dtype == VP_F32) pad_rows_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(src, (float*)dst, rows, cols, dst_cols);
-    else pad_rows_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, rows, cols, dst_cols);
-    VP_CHECK_LAUNCH("vp_pad_rows");
-    return VP_OK;
-}
-
-extern "C" int vp_unpad_rows(const float* src, float* dst, int64_t rows, int cols, int src_cols, void* stream) {
-    VP_CHECK_ARG(src && dst && rows > 0 && cols > 0 && src_cols >= cols, "vp_unpad_rows: bad arguments");
-    unpad_rows_kernel<<<grid_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(src, dst, rows, cols, src_cols);
-    VP_CHECK_LAUNCH("vp_unpad_rows");
     return VP_OK;
 }
 

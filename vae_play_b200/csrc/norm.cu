@@ -379,24 +379,24 @@ extern "C" int vp_norm_finalize(const double* sums, const float* gamma, const fl
 
 namespace vp {
 namespace {
-// block = 32 channels x 8 part lanes: coalesced rows of the parts array, 8 independent partial sums per channel
-__global__ void __launch_bounds__(256) finalize_parts_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ gamma,
+// block = 16 channels x 64 part lanes: every part row is read by one lane, all loads of a thread are independent
+__global__ void __launch_bounds__(1024) finalize_parts_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
                                                              float eps, float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C) {
-    __shared__ double sh1[8][32], sh2[8][32];
-    const int cl = threadIdx.x & 31, pl = threadIdx.x >> 5;
-    const int c = blockIdx.x * 32 + cl;
+    __shared__ double sh1[64][17], sh2[64][17];
+    const int cl = threadIdx.x & 15, pl = threadIdx.x >> 4;
+    const int c = blockIdx.x * 16 + cl;
     double a1 = 0, a2 = 0;
     if (c < C) {
-#pragma unroll 4
-        for (int i = pl; i < nparts; i += 8) { a1 += (double)parts[(size_t)i * 2 * C + c]; a2 += (double)parts[(size_t)i * 2 * C + C + c]; }
+#pragma unroll 5
+        for (int i = pl; i < nparts; i += 64) { a1 += (double)parts[(size_t)i * 2 * C + c]; a2 += (double)parts[(size_t)i * 2 * C + C + c]; }
     }
     sh1[pl][cl] = a1; sh2[pl][cl] = a2;
     __syncthreads();
     if (pl != 0 || c >= C) return;
     double s1 = 0, s2 = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { s1 += sh1[i][cl]; s2 += sh2[i][cl]; }
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) { s1 += sh1[i][cl]; s2 += sh2[i][cl]; }
     const double m = (double)rows;
     const double mu = s1 / m;
     double var = s2 / m - mu * mu;
@@ -424,7 +424,7 @@ extern "C" int vp_norm_finalize_parts(const float* parts, int nparts, const floa
                                       float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
                                       float* shift, int64_t rows, int c, void* stream) {
     VP_CHECK_ARG(parts && nparts > 0 && mean && invstd && scale && shift && rows > 0 && c > 0, "vp_norm_finalize_parts: bad arguments");
-    finalize_parts_kernel<<<(c + 31) / 32, 256, 0, (cudaStream_t)stream>>>(parts, nparts, gamma, beta, running_mean, running_var, momentum, eps,
+    finalize_parts_kernel<<<(c + 15) / 16, 1024, 0, (cudaStream_t)stream>>>(parts, nparts, gamma, beta, running_mean, running_var, momentum, eps,
                                                                          mean, invstd, scale, shift, rows, c);
     VP_CHECK_LAUNCH("vp_norm_finalize_parts");
     return VP_OK;

@@ -151,6 +151,12 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
                     if (p.dgamma) p.dgamma[cl + j] = (float)p.sums[C + cl + j];
                 }
             }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {       // m1 <- ka = -scale*invstd*m2,  m2 <- kb = -scale*m1 - ka*mean
+                const float ka = -sc[j] * is[j] * m2[j];
+                const float kb = -sc[j] * m1[j] - ka * mu[j];
+                m1[j] = ka; m2[j] = kb;
+            }
         }
     }
 
@@ -196,19 +202,22 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
                     float d[V];
                     SV<T, V>::ld(ds + (int64_t)r * C + cl, d);
                     if (MODE == M_BWD_REDUCE) {
+                        // b accumulates sum d*(x - mean); the common factor invstd is applied once, after the loop
 #pragma unroll
                         for (int j = 0; j < V; ++j) {
-                            d[j] *= dact<RELU>(fmaf(v[j], sc[j], sh[j]), p.act, p.slope);
+                            const float pre = fmaf(v[j], sc[j], sh[j]);
+                            d[j] = RELU ? (pre > 0.f ? d[j] : 0.f) : d[j] * act_grad(pre, p.act, p.slope);
                             a[j] += d[j];
-                            b[j] = fmaf(d[j], (v[j] - mu[j]) * is[j], b[j]);
+                            b[j] = fmaf(d[j], v[j] - mu[j], b[j]);
                         }
                         if (p.out) SV<T, V>::st(reinterpret_cast<T*>(p.out) + (r0 + r) * C + cl, d);
                     } else {
+                        // dx = scale*(dd - m1 - xhat*m2) = scale*dd + (ka*x + kb), ka/kb per channel (held in m1/m2 from here on)
 #pragma unroll
                         for (int j = 0; j < V; ++j) {
-                            const float dd = d[j] * dact<RELU>(fmaf(v[j], sc[j], sh[j]), p.act, p.slope);
-                            const float xh = (v[j] - mu[j]) * is[j];
-                            d[j] = sc[j] * (dd - m1[j] - xh * m2[j]);
+                            const float pre = fmaf(v[j], sc[j], sh[j]);
+                            const float dd = RELU ? (pre > 0.f ? d[j] : 0.f) : d[j] * act_grad(pre, p.act, p.slope);
+                            d[j] = fmaf(sc[j], dd, fmaf(m1[j], v[j], m2[j]));
                         }
                         SV<T, V>::st(reinterpret_cast<T*>(p.out) + (r0 + r) * C + cl, d);
                     }
@@ -228,6 +237,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
         for (int cc = threadIdx.x; cc < C; cc += NT) {
             double t1 = 0, t2 = 0;
             for (int i = 0; i < rlanes; ++i) { t1 += red[i * cpb + cc]; t2 += red[NT * V + i * cpb + cc]; }
+            if (MODE == M_BWD_REDUCE && p.invstd) t2 *= (double)p.invstd[cc];
             atomicAdd(p.sums + cc, t1);
             if (MODE == M_STATS || p.mean) atomicAdd(p.sums + C + cc, t2);
         }

@@ -21,6 +21,7 @@ _STATE = {"precision": "bf16", "engine": _lib.ENGINE_AUTO}
 _EPOCH = [0]       # bumped by invalidate_caches(): forces every packed-weight cache to miss once
 _TRACE = None      # when a list: every fused layer appends its activated output (tests / diagnostics only)
 _GRAD_SINKS = {}   # param.data_ptr() -> (bucket view, param): where wgrad writes directly (vae_play_b200.parallel)
+_SHADOWS = {}      # weight.data_ptr() -> (TapLayer, bf16 copy): lets a fused optimiser refresh the copy while it updates the master
 
 
 def set_grad_sinks(sinks_by_param_id, params=None):
@@ -189,17 +190,18 @@ class TapLayer:
         """bf16 copy of the master weight, element for element (same strides)."""
         hit = self._cache.get("shadow")
         key = (weight.data_ptr(), weight._version, _EPOCH[0])
-        if hit is not None and hit[0] == key:
-            return hit[1]
+        if hit is not None and (hit[0] == key or (len(hit) > 2 and hit[0][:2] == key[:2])):
+            return hit[1]      # up to date (a copy refreshed by the optimiser stays valid across invalidate_caches())
         sh = hit[1] if hit is not None and hit[1].shape == weight.shape and hit[1].stride() == weight.stride() else \
             torch.empty_like(weight, dtype=torch.bfloat16)
         _lib.call("vp_cast", _ptr(weight), F32, _ptr(sh), BF16, weight.numel(), _stream())
         self._cache["shadow"] = (key, sh)
+        _SHADOWS[weight.data_ptr()] = (self, sh)
         return sh
 
     def shadow_refreshed(self, weight, shadow):
         """Called by an optimiser that has written the bf16 copy itself."""
-        self._cache["shadow"] = ((weight.data_ptr(), weight._version, _EPOCH[0]), shadow)
+        self._cache["shadow"] = ((weight.data_ptr(), weight._version, _EPOCH[0]), shadow, "optimiser")
 
     # ---- thin layers (a single channel on one side): tcgen05 kernels that read the fp32 master weight directly ----
     def _thin(self, which, dt, weight):

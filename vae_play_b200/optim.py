@@ -21,8 +21,11 @@ class FusedRMSprop(torch.optim.Optimizer):
         self._tables = {}
 
     def _table(self, gi, group):
+        from . import functional as VF
         plist = [p for p in group["params"] if p.grad is not None]
-        key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in plist)
+        shadows = [VF._SHADOWS.get(p.data_ptr()) for p in plist]
+        shadows = [s if s is not None and s[1].stride() == p.stride() else None for s, p in zip(shadows, plist)]
+        key = tuple((p.data_ptr(), p.grad.data_ptr(), s[1].data_ptr() if s else 0) for p, s in zip(plist, shadows))
         hit = self._tables.get(gi)
         if hit is not None and hit[0] == key:
             return hit[1]
@@ -37,7 +40,8 @@ class FusedRMSprop(torch.optim.Optimizer):
         n = len(plist)
         arr = lambda vals: (C.c_void_p * n)(*vals)
         tab = (arr([p.data_ptr() for p in plist]), arr([p.grad.data_ptr() for p in plist]),
-               arr([self.state[p]["square_avg"].data_ptr() for p in plist]), (C.c_int64 * n)(*[p.numel() for p in plist]), n, plist)
+               arr([self.state[p]["square_avg"].data_ptr() for p in plist]), (C.c_int64 * n)(*[p.numel() for p in plist]), n, plist,
+               arr([s[1].data_ptr() if s else None for s in shadows]), shadows)
         self._tables[gi] = (key, tab)
         return tab
 
@@ -49,12 +53,16 @@ class FusedRMSprop(torch.optim.Optimizer):
                 loss = closure()
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for gi, group in enumerate(self.param_groups):
-            pa, ga, sa, na, n, plist = self._table(gi, group)
+            pa, ga, sa, na, n, plist, sha, shadows = self._table(gi, group)
             if n == 0:
                 continue
-            _lib.call("vp_rmsprop_step", pa, ga, sa, na, n, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
+            # the bf16 operand copies of the weights (functional.TapLayer._shadow) are refreshed by the same kernel
+            _lib.call("vp_rmsprop_step_shadow", pa, ga, sa, sha, na, n, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
                       float(group["weight_decay"]), stream)
             # the parameters were modified by a kernel torch does not know about: bump their version counters so that
             # everything keyed on tensor._version (the packed-weight caches, autograd's saved-tensor checks) sees it
             torch._C._autograd._unsafe_set_version_counter(plist, [p._version + 1 for p in plist])
+            for p, sh in zip(plist, shadows):
+                if sh is not None:
+                    sh[0].shadow_refreshed(p, sh[1])
         return loss
