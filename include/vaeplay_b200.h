@@ -116,6 +116,15 @@ int vp_norm_bwd_apply(const void* x, const void* da, const float* mean, const fl
                       const float* scale, const float* shift, const double* sums,
                       void* dx, float* dgamma, float* dbeta, int dtype,
                       int64_t groups, int64_t rows_per_group, int c, int act, float slope, void* stream);
+/* Train-mode BatchNorm (+ activation) over x [rows, c] with FEW rows (<= 8192) in one launch per direction -- the
+ * BatchNorm1d behind the fc layers (models/networks.py:66,89): statistics + finalize + apply (forward), reduce + apply
+ * (backward).  Same outputs as the vp_norm_* sequence; c a multiple of 4, tensors 16-byte aligned. */
+int vp_bn_rows_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float momentum, float eps, void* a, float* mean, float* invstd, float* scale, float* shift,
+                   int dtype, int64_t rows, int c, int act, float slope, void* stream);
+int vp_bn_rows_bwd(const void* x, const void* da, const float* mean, const float* invstd, const float* scale,
+                   const float* shift, void* dx, float* dgamma, float* dbeta, int dtype, int64_t rows, int c,
+                   int act, float slope, void* stream);
 /* out[c] = sum over rows of x[rows,c] (bias gradients).  out fp32, written (not accumulated);
  * scratch_c: double [2][c] (zeroed by the call). */
 int vp_colsum(const void* x, float* out, double* scratch_c, int dtype, int64_t rows, int c, void* stream);
@@ -175,7 +184,9 @@ int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
  * w_cl: bf16 copy of the layer's weight in channels-last element order, i.e. exactly the bytes of the nn.Parameter when it is
  * kept in torch.channels_last memory format: nn.Conv2d [co][kh][kw][ci], nn.ConvTranspose2d [ci][kh][kw][co], nn.Linear
  * [out][in].  The TMA reads it in place, as a K-major or an MN-major tcgen05 operand depending on the direction.
- * dw_cl: fp32 gradient in the same element order, zeroed by the call.  bf16 activations, tcgen05 engine only:
+ * dw_cl: fp32 gradient in the same element order, zeroed by the call unless accumulate != 0 (then dw_cl += dL/dw: the
+ * caller guarantees it holds what the gradient must be added to, e.g. zeros left by vp_rmsprop_step_shadow).
+ * bf16 activations, tcgen05 engine only:
  * VP_EUNSUPPORTED when the shape is not eligible (reduction channels not a multiple of 64, ...). */
 int vp_conv_fwd_cl(const VpConvGeom* g, const void* x, const void* w_cl, const float* bias, void* y, int out_dtype,
                    int act, float slope, void* stream);
@@ -190,7 +201,7 @@ int vp_conv_fwd_cl_stats(const VpConvGeom* g, const void* x, const void* w_cl, v
 int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, float momentum, float eps,
                            float* mean, float* invstd, float* scale, float* shift, int64_t rows, int c, void* stream);
-int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, void* stream);
+int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int accumulate, void* stream);
 /* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
 int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
 
@@ -209,7 +220,7 @@ int vp_thin_conv_fwd(const VpConvGeom* g, const void* x, const float* w, const f
 int vp_thin_conv_fwd_stats(const VpConvGeom* g, const void* x, const float* w, void* y, float* stat_parts,
                            int stat_capacity, int* nparts, void* stream);
 int vp_thin_conv_dgrad(const VpConvGeom* g, const void* dy, const float* w, void* dx, int out_dtype, void* stream);
-int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, void* stream);
+int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, int accumulate, void* stream);
 
 /* ---- optimiser: torch.optim.RMSprop (train.py:136-140; alpha .99, eps 1e-8, no momentum, not centered) as ONE
  * multi-tensor kernel over fp32 masters:  sq = alpha*sq + (1-alpha)*g*g;  p -= lr * g / (sqrt(sq) + eps).
@@ -217,9 +228,12 @@ int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float
 int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* sq, const int64_t* numel, int count,
                     float lr, float alpha, float eps, float weight_decay, void* stream);
 /* same, and shadows[i] (nullable per entry) receives the bf16 copy of the updated parameter in the same element order:
- * the operand the in-place contractions (vp_conv_*_cl) read next step, so no cast pass is needed. */
-int vp_rmsprop_step_shadow(void* const* params, const void* const* grads, void* const* sq, void* const* shadows,
-                           const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay, void* stream);
+ * the operand the in-place contractions (vp_conv_*_cl) read next step, so no cast pass is needed.  zero_grads != 0: each
+ * gradient is cleared after it has been consumed, so that the next step's weight-gradient kernels can accumulate into
+ * it without a memset (vp_conv_wgrad_cl / vp_thin_conv_wgrad with accumulate = 1). */
+int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const* sq, void* const* shadows,
+                           const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay,
+                           int zero_grads, void* stream);
 
 /* debug: tcgen05 operand-window probe (tools/probe_umma.py); x bf16 [256][64], ident bf16 [64][64], out fp32 [128][64] */
 int vp_debug_umma_probe(const void* x, const void* ident, float* out, int off_rows, int sbo_rows, int base_offset, void* stream);

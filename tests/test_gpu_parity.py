@@ -693,10 +693,50 @@ def test_epilogue_batchnorm_statistics(vp, kind, cin, cout, hw, b):
     finally:
         vp.set_epilogue_stats(True)
     assert blk._layer.stats_in_epilogue(torch.bfloat16, blk.conv.weight)
-    assert res[True][5] < res[False][5]                      # the statistics pass is gone
+    if y.numel() // cout > 8192:                             # (smaller tensors take the single-launch few-rows kernel when the epilogue path is off)
+        assert res[True][5] < res[False][5]                  # the statistics pass is gone
     for on in (False, True):
         # the batch mean is a cancelling sum (|mean| << std): bound its error by the std, i.e. by sqrt(running_var)
         assert np.max(np.abs(res[on][1] - res[on][6]) / np.sqrt(res[on][7])) < 2e-6, ("running_mean", on)
         close(res[on][2], res[on][7], 2e-6, f"running_var (epilogue={on})")
     close(res[True][0], res[False][0], 1e-2, "activations")  # one bf16 ulp where a rounding boundary moves
     assert rel_l2(res[True][3], res[False][3]) < 5e-3 and rel_l2(res[True][4], res[False][4]) < 5e-3
+
+
+def test_persistent_grads_and_zeroing_optimizer(vp):
+    """persistent_grads + FusedRMSprop(zero_grads=True): the weight-gradient kernels accumulate into slots the optimiser
+    cleared (no memset), the bf16 operand copies are refreshed by the optimiser kernel -- and three training steps end with
+    the same parameters as the plain flow (fresh gradient tensors, torch-style zero_grad, separate cast pass)."""
+    import copy
+    import vae_play_b200.functional as VF
+    from vae_play_b200.models.networks import VaeGan
+    from vae_play_b200.optim import FusedRMSprop
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    torch.manual_seed(0)
+    ref = VaeGan(64, 128).cuda().train()
+    x = torch.rand(8, 1, 64, 64, device="cuda")
+    eps = torch.randn(8, 128, device="cuda")
+    results = []
+    for persistent in (False, True):
+        VF.set_grad_sinks({})
+        m = copy.deepcopy(ref)
+        params = list(m.encoder.parameters()) + list(m.decoder.parameters())
+        opt = FusedRMSprop(params, lr=1e-3, zero_grads=persistent)
+        flat = VF.persistent_grads(params) if persistent else None
+        n_memset_free = 0
+        for step in range(3):
+            opt.zero_grad(set_to_none=True)
+            if persistent and step > 0:
+                assert float(flat.abs().max()) == 0.0                  # cleared by the optimiser kernel
+                n_memset_free = sum(1 for e in VF._GRAD_SINKS.values() if e[2])
+            xt, mulv, kl = m.vae_forward(x, eps=eps)
+            VF.vae_loss(x, xt, kl).backward()
+            opt.step()
+        if persistent:
+            assert n_memset_free == len(params)
+            assert all(p.grad.data_ptr() == VF._GRAD_SINKS[p.data_ptr()][0].data_ptr() for p in params)
+        results.append([npy(p) for p in params])
+    VF.set_grad_sinks({})
+    for a, b in zip(*results):
+        assert rel_l2(a, b) < 2e-3          # split-K atomics order differs run to run; otherwise the same arithmetic

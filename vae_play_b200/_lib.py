@@ -42,6 +42,8 @@ SIGNATURES = {
     "vp_norm_apply_act": [_p, _p, _p, _p, _i, _i64, _i64, _i, _i, _f, _p],
     "vp_norm_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i64, _i, _i, _f, _p],
     "vp_norm_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i64, _i, _i, _f, _p],
+    "vp_bn_rows_fwd": [_p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _f, _p],
+    "vp_bn_rows_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _f, _p],
     "vp_colsum": [_p, _p, _p, _i, _i64, _i, _p],
     "vp_reparam_kl_fwd": [_p, _p, _i64, _p, _u64, _u64, _p, _i, _p, _i, _p, _p, _i64, _i, _p],
     "vp_reparam_kl_bwd": [_p, _p, _i64, _p, _p, _i, _p, _p, _p, _i, _i64, _i64, _i, _p],
@@ -64,13 +66,13 @@ SIGNATURES = {
     "vp_thin_conv_fwd_stats": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, C.POINTER(C.c_int), _p],
     "vp_norm_finalize_parts": [_p, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i64, _i, _p],
     "vp_conv_dgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
-    "vp_conv_wgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
+    "vp_conv_wgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
     "vp_transpose_bt": [_p, _p, _i, _i, _i, _i, _p],
     "vp_thin_conv_fwd": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
     "vp_thin_conv_dgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
-    "vp_thin_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _p],
+    "vp_thin_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
     "vp_rmsprop_step": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
-    "vp_rmsprop_step_shadow": [_p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
+    "vp_rmsprop_step_shadow": [_p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _i, _p],
 }
 PLAIN = {"vp_last_error": (C.c_char_p, []), "vp_abi_version": (_i, []), "vp_device_arch": (_i, []),
          "vp_launch_count": (_u64, [])}

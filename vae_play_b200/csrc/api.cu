@@ -235,13 +235,13 @@ extern "C" int vp_conv_dgrad_cl(const VpConvGeom* g, const void* dy, const void*
                      out_dtype, VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 1 : 2);
 }
 
-extern "C" int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, void* stream) {
+extern "C" int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int accumulate, void* stream) {
     if (!check_geom(g, "vp_conv_wgrad_cl")) return VP_EINVAL;
     VP_CHECK_ARG(x && dy && dw_cl, "vp_conv_wgrad_cl: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
     TapWgrad p;
     fill_wgrad(g, x, dy, dw_cl, true, p);
-    cudaMemsetAsync(dw_cl, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    if (!accumulate) cudaMemsetAsync(dw_cl, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     const int rc = launch_tapwgrad_win(p, g->kh, g->kw, g->pad, s);
     if (rc != VP_EUNSUPPORTED) return rc;
     return launch_tapwgrad_tc(p, s);

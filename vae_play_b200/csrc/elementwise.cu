@@ -534,7 +534,7 @@ struct OptTable {
     bf16* sh[kOptMax];          // optional bf16 copy of the updated parameter (same element order), or null
     int64_t n[kOptMax];
 };
-__global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd) {
+__global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd, int zero_g) {
     const int ti = blockIdx.y;
     float* __restrict__ p = t.p[ti];
     bf16* __restrict__ sh = t.sh[ti];
@@ -556,6 +556,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
         }
         reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
         reinterpret_cast<float4*>(sq)[i] = make_float4(se[0], se[1], se[2], se[3]);
+        if (zero_g) reinterpret_cast<float4*>(const_cast<float*>(g))[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sh) {
             __nv_bfloat162 h0 = __floats2bfloat162_rn(pe[0], pe[1]), h1 = __floats2bfloat162_rn(pe[2], pe[3]);
             reinterpret_cast<uint2*>(sh)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
@@ -567,22 +568,23 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
         sq[i] = s2;
         const float pn = p[i] - lr * (gg / (sqrtf(s2) + eps));
         p[i] = pn;
+        if (zero_g) const_cast<float*>(g)[i] = 0.f;
         if (sh) sh[i] = __float2bfloat16_rn(pn);
     }
 }
 }  // namespace
 }  // namespace vp
 
-extern "C" int vp_rmsprop_step_shadow(void* const* params, const void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
-                                      int count, float lr, float alpha, float eps, float weight_decay, void* stream);
+extern "C" int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
+                                      int count, float lr, float alpha, float eps, float weight_decay, int zero_grads, void* stream);
 
 extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* sq, const int64_t* numel, int count, float lr,
                                float alpha, float eps, float weight_decay, void* stream) {
-    return vp_rmsprop_step_shadow(params, grads, sq, nullptr, numel, count, lr, alpha, eps, weight_decay, stream);
+    return vp_rmsprop_step_shadow(params, const_cast<void* const*>(grads), sq, nullptr, numel, count, lr, alpha, eps, weight_decay, 0, stream);
 }
 
-extern "C" int vp_rmsprop_step_shadow(void* const* params, const void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
-                                      int count, float lr, float alpha, float eps, float weight_decay, void* stream) {
+extern "C" int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
+                                      int count, float lr, float alpha, float eps, float weight_decay, int zero_grads, void* stream) {
     VP_CHECK_ARG(params && grads && sq && numel && count >= 0, "vp_rmsprop_step: bad arguments");
     for (int base = 0; base < count; base += kOptMax) {
         OptTable t;
@@ -597,7 +599,7 @@ extern "C" int vp_rmsprop_step_shadow(void* const* params, const void* const* gr
         int64_t bx = (nmax / 4 + 255) / 256;
         if (bx > 148 * 2) bx = 148 * 2;
         if (bx < 1) bx = 1;
-        rmsprop_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, lr, alpha, eps, weight_decay);
+        rmsprop_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, lr, alpha, eps, weight_decay, zero_grads);
         VP_CHECK_LAUNCH("vp_rmsprop_step");
     }
     return VP_OK;

@@ -500,3 +500,190 @@ extern "C" int vp_colsum(const void* x, float* out, double* scratch_c, int dtype
     VP_CHECK_LAUNCH("vp_colsum");
     return VP_OK;
 }
+
+// =====================================================================================================================
+// BatchNorm over FEW rows and many channels in ONE launch per direction: the BatchNorm1d behind the fc layers
+// (models/networks.py:66,89: [batch, 1024] and [batch, 8*8*C]).  A block owns 128 channels; its 8 row slices each walk
+// the rows of those channels (second pass served by L2), so statistics + finalize + apply -- five launches and three
+// memsets of the generic path -- become one kernel, and the same for the backward pair.
+// =====================================================================================================================
+namespace vp {
+namespace {
+constexpr int SM_CG = 32, SM_RS = 8, SM_V = 4;     // 32 channel groups x 4 channels, 8 row slices -> 256 threads
+
+template <typename T> struct AccT { typedef float type; };
+template <> struct AccT<float> { typedef double type; };   // fp32 check mode: double accumulation
+
+template <typename T>
+__device__ __forceinline__ void ldv4(const T* p, float* v);
+template <> __device__ __forceinline__ void ldv4<float>(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ldv4<bf16>(const bf16* p, float* v) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void stv4(T* p, const float* v);
+template <> __device__ __forceinline__ void stv4<float>(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void stv4<bf16>(bf16* p, const float* v) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_rows_fwd_kernel(const T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* running_mean, float* running_var, float momentum, float eps, T* __restrict__ a,
+                                                          float* mean, float* invstd, float* scale, float* shift, int rows, int C, int act,
+                                                          float slope) {
+    typedef typename AccT<T>::type Acc;
+    __shared__ double red[2][SM_RS][SM_CG * SM_V];
+    __shared__ float par[2][SM_CG * SM_V];
+    const int cg = threadIdx.x % SM_CG, rs = threadIdx.x / SM_CG;
+    const int c0 = blockIdx.x * (SM_CG * SM_V) + cg * SM_V;
+    const bool on = c0 < C;
+    Acc s[SM_V] = {0, 0, 0, 0}, q[SM_V] = {0, 0, 0, 0};
+    if (on)
+        for (int r = rs; r < rows; r += SM_RS) {
+            float v[SM_V];
+            ldv4<T>(y + (int64_t)r * C + c0, v);
+#pragma unroll
+            for (int j = 0; j < SM_V; ++j) { s[j] += v[j]; q[j] += (Acc)v[j] * v[j]; }
+        }
+#pragma unroll
+    for (int j = 0; j < SM_V; ++j) { red[0][rs][cg * SM_V + j] = (double)s[j]; red[1][rs][cg * SM_V + j] = (double)q[j]; }
+    __syncthreads();
+    if (threadIdx.x < SM_CG * SM_V) {
+        const int c = blockIdx.x * (SM_CG * SM_V) + threadIdx.x;
+        if (c < C) {
+            double s1 = 0, s2 = 0;
+#pragma unroll
+            for (int i = 0; i < SM_RS; ++i) { s1 += red[0][i][threadIdx.x]; s2 += red[1][i][threadIdx.x]; }
+            const double m = (double)rows, mu = s1 / m;
+            double var = s2 / m - mu * mu;
+            if (var < 0) var = 0;
+            const float is = (float)(1.0 / sqrt(var + (double)eps));
+            const float sc = (gamma ? gamma[c] : 1.f) * is;
+            const float sh = (beta ? beta[c] : 0.f) - (float)mu * sc;
+            mean[c] = (float)mu; invstd[c] = is; scale[c] = sc; shift[c] = sh;
+            par[0][threadIdx.x] = sc; par[1][threadIdx.x] = sh;
+            if (running_mean) {
+                const double unb = var * m / (m > 1 ? m - 1 : 1);
+                running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+                running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+            }
+        }
+    }
+    __syncthreads();
+    if (!on) return;
+    float sc[SM_V], sh[SM_V];
+#pragma unroll
+    for (int j = 0; j < SM_V; ++j) { sc[j] = par[0][cg * SM_V + j]; sh[j] = par[1][cg * SM_V + j]; }
+    for (int r = rs; r < rows; r += SM_RS) {
+        float v[SM_V];
+        ldv4<T>(y + (int64_t)r * C + c0, v);
+#pragma unroll
+        for (int j = 0; j < SM_V; ++j) v[j] = act_fwd(fmaf(v[j], sc[j], sh[j]), act, slope);
+        stv4<T>(a + (int64_t)r * C + c0, v);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const T* __restrict__ y, const T* __restrict__ da, const float* __restrict__ mean,
+                                                          const float* __restrict__ invstd, const float* __restrict__ scale,
+                                                          const float* __restrict__ shift, T* __restrict__ dy, float* dgamma, float* dbeta, int rows,
+                                                          int C, int act, float slope) {
+    typedef typename AccT<T>::type Acc;
+    __shared__ double red[2][SM_RS][SM_CG * SM_V];
+    __shared__ float par[2][SM_CG * SM_V];
+    const int cg = threadIdx.x % SM_CG, rs = threadIdx.x / SM_CG;
+    const int c0 = blockIdx.x * (SM_CG * SM_V) + cg * SM_V;
+    const bool on = c0 < C;
+    float sc[SM_V] = {1, 1, 1, 1}, sh[SM_V] = {0, 0, 0, 0}, mu[SM_V] = {0, 0, 0, 0}, is[SM_V] = {0, 0, 0, 0};
+    if (on) {
+#pragma unroll
+        for (int j = 0; j < SM_V; ++j) { sc[j] = scale[c0 + j]; sh[j] = shift[c0 + j]; mu[j] = mean[c0 + j]; is[j] = invstd[c0 + j]; }
+    }
+    Acc s[SM_V] = {0, 0, 0, 0}, q[SM_V] = {0, 0, 0, 0};
+    if (on)
+        for (int r = rs; r < rows; r += SM_RS) {
+            float v[SM_V], d[SM_V];
+            ldv4<T>(y + (int64_t)r * C + c0, v);
+            ldv4<T>(da + (int64_t)r * C + c0, d);
+#pragma unroll
+            for (int j = 0; j < SM_V; ++j) {
+                const float dd = d[j] * act_grad(fmaf(v[j], sc[j], sh[j]), act, slope);
+                s[j] += dd;
+                q[j] += (Acc)dd * ((v[j] - mu[j]) * is[j]);
+            }
+        }
+#pragma unroll
+    for (int j = 0; j < SM_V; ++j) { red[0][rs][cg * SM_V + j] = (double)s[j]; red[1][rs][cg * SM_V + j] = (double)q[j]; }
+    __syncthreads();
+    if (threadIdx.x < SM_CG * SM_V) {
+        const int c = blockIdx.x * (SM_CG * SM_V) + threadIdx.x;
+        if (c < C) {
+            double s1 = 0, s2 = 0;
+#pragma unroll
+            for (int i = 0; i < SM_RS; ++i) { s1 += red[0][i][threadIdx.x]; s2 += red[1][i][threadIdx.x]; }
+            if (dbeta) dbeta[c] = (float)s1;
+            if (dgamma) dgamma[c] = (float)s2;
+            par[0][threadIdx.x] = (float)(s1 / rows); par[1][threadIdx.x] = (float)(s2 / rows);
+        }
+    }
+    __syncthreads();
+    if (!on) return;
+    float m1[SM_V], m2[SM_V];
+#pragma unroll
+    for (int j = 0; j < SM_V; ++j) { m1[j] = par[0][cg * SM_V + j]; m2[j] = par[1][cg * SM_V + j]; }
+    for (int r = rs; r < rows; r += SM_RS) {
+        float v[SM_V], d[SM_V];
+        ldv4<T>(y + (int64_t)r * C + c0, v);
+        ldv4<T>(da + (int64_t)r * C + c0, d);
+#pragma unroll
+        for (int j = 0; j < SM_V; ++j) {
+            const float dd = d[j] * act_grad(fmaf(v[j], sc[j], sh[j]), act, slope);
+            d[j] = sc[j] * (dd - m1[j] - (v[j] - mu[j]) * is[j] * m2[j]);
+        }
+        stv4<T>(dy + (int64_t)r * C + c0, d);
+    }
+}
+}  // namespace
+}  // namespace vp
+
+/* Train-mode BatchNorm (+ activation) over x [rows, c] with few rows (<= 8192) in ONE launch: statistics, finalize
+ * (mean / invstd / scale / shift as vp_norm_finalize, running statistics blended in place) and a = act(x*scale + shift).
+ * c must be a multiple of 4 and the tensors 16-byte aligned.  The BatchNorm1d of models/networks.py:66,89. */
+extern "C" int vp_bn_rows_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
+                              float eps, void* a, float* mean, float* invstd, float* scale, float* shift, int dtype, int64_t rows, int c,
+                              int act, float slope, void* stream) {
+    VP_CHECK_ARG(x && a && mean && invstd && scale && shift && rows > 0 && rows <= 8192 && c > 0 && c % 4 == 0, "vp_bn_rows_fwd: bad arguments");
+    VP_CHECK_ARG((((uintptr_t)x | (uintptr_t)a) & 15) == 0, "vp_bn_rows_fwd: 16-byte alignment");
+    const unsigned grid = (unsigned)((c + SM_CG * SM_V - 1) / (SM_CG * SM_V));
+    if (dtype == VP_F32)
+        bn_rows_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                         (float*)a, mean, invstd, scale, shift, (int)rows, c, act, slope);
+    else
+        bn_rows_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                        (bf16*)a, mean, invstd, scale, shift, (int)rows, c, act, slope);
+    VP_CHECK_LAUNCH("vp_bn_rows_fwd");
+    return VP_OK;
+}
+
+/* Backward of the above in one launch: dx, dgamma, dbeta (nullable) from x, da and the saved statistics. */
+extern "C" int vp_bn_rows_bwd(const void* x, const void* da, const float* mean, const float* invstd, const float* scale, const float* shift,
+                              void* dx, float* dgamma, float* dbeta, int dtype, int64_t rows, int c, int act, float slope, void* stream) {
+    VP_CHECK_ARG(x && da && dx && mean && invstd && scale && shift && rows > 0 && rows <= 8192 && c > 0 && c % 4 == 0,
+                 "vp_bn_rows_bwd: bad arguments");
+    VP_CHECK_ARG((((uintptr_t)x | (uintptr_t)da | (uintptr_t)dx) & 15) == 0, "vp_bn_rows_bwd: 16-byte alignment");
+    const unsigned grid = (unsigned)((c + SM_CG * SM_V - 1) / (SM_CG * SM_V));
+    if (dtype == VP_F32)
+        bn_rows_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, (float*)dx,
+                                                                         dgamma, dbeta, (int)rows, c, act, slope);
+    else
+        bn_rows_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, (bf16*)dx,
+                                                                        dgamma, dbeta, (int)rows, c, act, slope);
+    VP_CHECK_LAUNCH("vp_bn_rows_bwd");
+    return VP_OK;
+}

@@ -807,7 +807,7 @@ extern "C" int vp_thin_conv_dgrad(const VpConvGeom* g, const void* dy, const flo
 
 // dw (fp32, torch layout [co][ci][kh][kw], zeroed by the call) = dL/dw of an nn.Conv2d with ONE input channel, or with ONE
 // output channel at stride 1.
-extern "C" int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, void* stream) {
+extern "C" int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, int accumulate, void* stream) {
     if (!thin_geom_ok(g, "vp_thin_conv_wgrad")) return VP_EINVAL;
     VP_CHECK_ARG(x && dy && dw, "vp_thin_conv_wgrad: null pointer");
     const int T = g->kh * g->kw;
@@ -844,6 +844,6 @@ extern "C" int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void
     p.total_tiles = (int)total;
     CUtensorMap mw;
     if (encode_box(&mw, wide, wc, p.gw, p.gh, p.n, 8, 16)) { set_error("vp_thin_conv_wgrad: cuTensorMapEncodeTiled failed"); return VP_EUNSUPPORTED; }
-    cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->co * g->ci * T, s);
+    if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->co * g->ci * T, s);
     return launch_thin_w(mw, p, wc / 64, s);
 }

@@ -25,9 +25,35 @@ _SHADOWS = {}      # weight.data_ptr() -> (TapLayer, bf16 copy): lets a fused op
 
 
 def set_grad_sinks(sinks_by_param_id, params=None):
-    """Register flat-bucket slots for parameter gradients (data-parallel training)."""
+    """Register persistent slots for parameter gradients: param.data_ptr() -> (view with the parameter's strides, param).
+    The weight-gradient kernels write straight into them (flat data-parallel buckets, ``persistent_grads``)."""
     _GRAD_SINKS.clear()
-    _GRAD_SINKS.update(sinks_by_param_id)
+    for k, v in sinks_by_param_id.items():
+        _GRAD_SINKS[k] = [v[0], v[1], False]        # [slot, param, slot is known to hold zeros]
+
+
+def persistent_grads(params):
+    """Give every parameter a slot in ONE flat fp32 buffer that serves as its ``.grad`` step after step.  Together with an
+    optimiser that clears each gradient once it has consumed it (``FusedRMSprop(zero_grads=True)``) the weight-gradient
+    kernels accumulate into known-zero memory: no per-tensor memset, no allocation.  Returns the flat buffer."""
+    params = [p for p in params if p.requires_grad]
+    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    sinks, off = {}, 0
+    for p in params:
+        sinks[p.data_ptr()] = (torch.as_strided(flat, p.shape, p.stride(), storage_offset=off), p)
+        off += p.numel()
+    set_grad_sinks(sinks)
+    for e in _GRAD_SINKS.values():
+        e[2] = True
+    return flat
+
+
+def sinks_zeroed(params):
+    """An optimiser reports that it has cleared the gradients of ``params`` (those living in registered slots)."""
+    for p in params:
+        e = _GRAD_SINKS.get(p.data_ptr())
+        if e is not None and p.grad is not None and p.grad.data_ptr() == e[0].data_ptr():
+            e[2] = True
 
 
 def invalidate_caches():
@@ -37,12 +63,16 @@ def invalidate_caches():
 
 
 def _grad_target(weight):
+    """Where a weight gradient is written: (tensor, holds_zeros).  A registered slot is used when it can become the
+    parameter's .grad as is (no gradient accumulated yet this step, or the slot already IS the .grad and was cleared)."""
     hit = _GRAD_SINKS.get(weight.data_ptr())
     if hit is not None:
-        view, param = hit
-        if param.grad is None and view.shape == weight.shape and view.stride() == weight.stride():
-            return view
-    return torch.empty_like(weight, dtype=torch.float32)
+        view, param, zeroed = hit
+        if view.shape == weight.shape and view.stride() == weight.stride():
+            if param.grad is None:
+                hit[2] = False
+                return view, zeroed
+    return torch.empty_like(weight, dtype=torch.float32), False
 
 
 def set_precision(mode: str):
@@ -286,13 +316,13 @@ class TapLayer:
         g = self._layer_geom(n, h, w, dy.shape[1], dy.shape[2])
         thin, cl = self._thin("wgrad", dt, weight), self._cl(dt, weight)
         if thin or cl:
-            dw = _grad_target(weight)       # same strides as the weight: the kernel writes the gradient in place
-            _lib.call("vp_thin_conv_wgrad" if thin else "vp_conv_wgrad_cl", C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), _stream())
+            dw, zeroed = _grad_target(weight)       # same strides as the weight: the kernel writes the gradient in place
+            _lib.call("vp_thin_conv_wgrad" if thin else "vp_conv_wgrad_cl", C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), int(zeroed), _stream())
             return dw
         p = self._recipe("wgrad", weight)
         dwp = torch.empty(p.taps * p.n * p.k, dtype=torch.float32, device=x.device)
         _lib.call("vp_conv_wgrad", C.byref(g), _ptr(x), _ptr(dy), _ptr(dwp), _code(dt), _STATE["engine"], _stream())
-        dw = _grad_target(weight)
+        dw, _ = _grad_target(weight)
         _lib.call("vp_unpack_wgrad", _ptr(dwp), _ptr(dw), p.taps, p.n, p.k, p.sn, p.sk, p.st, _stream())
         return dw
 
@@ -322,6 +352,7 @@ class _FusedLayerFn(torch.autograd.Function):
         ctx.layer, ctx.norm, ctx.act, ctx.slope = layer, norm, act, slope
         ctx.x_shape = tuple(x.shape)
         ctx.has_bias = bias is not None
+        ctx.few_rows = False
         if norm.kind is None:
             a = layer.fwd(x, weight, bias, act, slope, out_dtype)
             ctx.save_for_backward(x, weight, a)
@@ -341,6 +372,22 @@ class _FusedLayerFn(torch.autograd.Function):
         stats = torch.empty(4, groups * cc, dtype=torch.float32, device=dev)  # mean, invstd, scale, shift
         mean, invstd, scale, shift = stats[0], stats[1], stats[2], stats[3]
         g_, b_ = gamma, beta
+        # few rows, many channels (the BatchNorm1d behind the fc layers): statistics + finalize + apply in ONE launch
+        few_rows = norm.kind == "batch" and training and not fuse_stats and rpg <= 8192 and cc % 4 == 0 and out_dtype == dt
+        ctx.few_rows = few_rows
+        if few_rows:
+            rm = rv = None
+            if bn_module is not None and bn_module.track_running_stats:
+                rm, rv = bn_module.running_mean, bn_module.running_var
+                bn_module.num_batches_tracked += 1
+            a = torch.empty_like(y)
+            _lib.call("vp_bn_rows_fwd", _ptr(y), _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum), float(norm.eps), _ptr(a),
+                      _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _code(dt), rpg, cc, ACT[act], float(slope), _stream())
+            ctx.save_for_backward(x, weight, y, stats)
+            ctx.dims = (groups, rpg, cc, c)
+            ctx.train_stats = True
+            ctx.has_affine = gamma is not None
+            return a, y
         if training or norm.kind == "instance":
             rm = rv = None
             if norm.kind == "batch" and bn_module is not None and bn_module.track_running_stats:
@@ -419,7 +466,13 @@ class _FusedLayerFn(torch.autograd.Function):
                 return dx, dw, None, None, None, None, None, None, None, None, None, None
             da = da.contiguous()
             dy = torch.empty_like(y)
-            if ctx.train_stats:
+            if ctx.few_rows:
+                if ctx.has_affine:
+                    dgamma = torch.empty(cc, dtype=torch.float32, device=dev)
+                    dbeta = torch.empty(cc, dtype=torch.float32, device=dev)
+                _lib.call("vp_bn_rows_bwd", _ptr(y), _ptr(da), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _ptr(dy), _ptr(dgamma),
+                          _ptr(dbeta), _code(dt), rpg, cc, ACT[act], float(slope), _stream())
+            elif ctx.train_stats:
                 sums = torch.empty(2 * groups * cc, dtype=torch.float64, device=dev)
                 _lib.call("vp_norm_bwd_reduce", _ptr(y), _ptr(da), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
                           _ptr(sums), None, _code(dt), groups, rpg, cc, ACT[act], float(slope), _stream())

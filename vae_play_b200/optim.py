@@ -14,11 +14,15 @@ from . import _lib
 
 
 class FusedRMSprop(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0.0, zero_grads=False):
+        """zero_grads=True: ``step()`` also clears every gradient it has consumed (the tensors stay attached to the
+        parameters).  Use with ``functional.persistent_grads`` / ``parallel.GradBuckets`` and do NOT call ``zero_grad()``:
+        the next backward then accumulates into known-zero memory without any memset."""
         if lr < 0 or eps < 0 or alpha < 0 or weight_decay < 0:
             raise ValueError("invalid hyper-parameter")
         super().__init__(params, dict(lr=lr, alpha=alpha, eps=eps, weight_decay=weight_decay))
         self._tables = {}
+        self.zero_grads = bool(zero_grads)
 
     def _table(self, gi, group):
         from . import functional as VF
@@ -58,11 +62,14 @@ class FusedRMSprop(torch.optim.Optimizer):
                 continue
             # the bf16 operand copies of the weights (functional.TapLayer._shadow) are refreshed by the same kernel
             _lib.call("vp_rmsprop_step_shadow", pa, ga, sa, sha, na, n, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
-                      float(group["weight_decay"]), stream)
+                      float(group["weight_decay"]), int(self.zero_grads), stream)
             # the parameters were modified by a kernel torch does not know about: bump their version counters so that
             # everything keyed on tensor._version (the packed-weight caches, autograd's saved-tensor checks) sees it
             torch._C._autograd._unsafe_set_version_counter(plist, [p._version + 1 for p in plist])
             for p, sh in zip(plist, shadows):
                 if sh is not None:
                     sh[0].shadow_refreshed(p, sh[1])
+            if self.zero_grads:
+                from . import functional as VF
+                VF.sinks_zeroed(plist)
         return loss
