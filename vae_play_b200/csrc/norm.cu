@@ -503,13 +503,13 @@ extern "C" int vp_colsum(const void* x, float* out, double* scratch_c, int dtype
 
 // =====================================================================================================================
 // BatchNorm over FEW rows and many channels in ONE launch per direction: the BatchNorm1d behind the fc layers
-// (models/networks.py:66,89: [batch, 1024] and [batch, 8*8*C]).  A block owns 128 channels; its 8 row slices each walk
+// (models/networks.py:66,89: [batch, 1024] and [batch, 8*8*C]).  A block owns 32 channels; its 32 row slices each walk
 // the rows of those channels (second pass served by L2), so statistics + finalize + apply -- five launches and three
 // memsets of the generic path -- become one kernel, and the same for the backward pair.
 // =====================================================================================================================
 namespace vp {
 namespace {
-constexpr int SM_CG = 32, SM_RS = 8, SM_V = 4;     // 32 channel groups x 4 channels, 8 row slices -> 256 threads
+constexpr int SM_CG = 8, SM_RS = 32, SM_V = 4;      // 8 channel groups x 4 channels, 32 row slices -> 256 threads, 32 channels per block
 
 template <typename T> struct AccT { typedef float type; };
 template <> struct AccT<float> { typedef double type; };   // fp32 check mode: double accumulation

@@ -25,11 +25,11 @@ _SHADOWS = {}      # weight.data_ptr() -> (TapLayer, bf16 copy): lets a fused op
 
 
 def set_grad_sinks(sinks_by_param_id, params=None):
-    """Register persistent slots for parameter gradients: param.data_ptr() -> (view with the parameter's strides, param).
+    """Register persistent slots for parameter gradients: param.data_ptr() -> (flat fp32 buffer, element offset, param).
     The weight-gradient kernels write straight into them (flat data-parallel buckets, ``persistent_grads``)."""
     _GRAD_SINKS.clear()
     for k, v in sinks_by_param_id.items():
-        _GRAD_SINKS[k] = [v[0], v[1], False]        # [slot, param, slot is known to hold zeros]
+        _GRAD_SINKS[k] = [v[0], int(v[1]), v[2], False]        # [flat, offset, param, slot is known to hold zeros]
 
 
 def persistent_grads(params):
@@ -40,11 +40,11 @@ def persistent_grads(params):
     flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
     sinks, off = {}, 0
     for p in params:
-        sinks[p.data_ptr()] = (torch.as_strided(flat, p.shape, p.stride(), storage_offset=off), p)
+        sinks[p.data_ptr()] = (flat, off, p)
         off += p.numel()
     set_grad_sinks(sinks)
     for e in _GRAD_SINKS.values():
-        e[2] = True
+        e[3] = True
     return flat
 
 
@@ -52,27 +52,27 @@ def sinks_zeroed(params):
     """An optimiser reports that it has cleared the gradients of ``params`` (those living in registered slots)."""
     for p in params:
         e = _GRAD_SINKS.get(p.data_ptr())
-        if e is not None and p.grad is not None and p.grad.data_ptr() == e[0].data_ptr():
-            e[2] = True
+        if e is not None and p.grad is not None and p.grad.data_ptr() == e[0].data_ptr() + 4 * e[1]:
+            e[3] = True
+
+
+def _grad_target(weight):
+    """Where a weight gradient is written: (tensor, holds_zeros).  A registered slot is used when it can become the
+    parameter's .grad as is (no gradient accumulated yet this step).  The view is created afresh and referenced by nobody
+    else, so that autograd's AccumulateGrad adopts it instead of cloning it."""
+    hit = _GRAD_SINKS.get(weight.data_ptr())
+    if hit is not None:
+        flat, off, param, zeroed = hit
+        if param.grad is None and param.shape == weight.shape and param.stride() == weight.stride():
+            hit[3] = False
+            return torch.as_strided(flat, weight.shape, weight.stride(), storage_offset=off), zeroed
+    return torch.empty_like(weight, dtype=torch.float32), False
 
 
 def invalidate_caches():
     """Force re-packing of all weight panels on next use (call before CUDA-graph capture so that the
     pack kernels are part of the captured step)."""
     _EPOCH[0] += 1
-
-
-def _grad_target(weight):
-    """Where a weight gradient is written: (tensor, holds_zeros).  A registered slot is used when it can become the
-    parameter's .grad as is (no gradient accumulated yet this step, or the slot already IS the .grad and was cleared)."""
-    hit = _GRAD_SINKS.get(weight.data_ptr())
-    if hit is not None:
-        view, param, zeroed = hit
-        if view.shape == weight.shape and view.stride() == weight.stride():
-            if param.grad is None:
-                hit[2] = False
-                return view, zeroed
-    return torch.empty_like(weight, dtype=torch.float32), False
 
 
 def set_precision(mode: str):

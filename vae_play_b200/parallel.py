@@ -50,7 +50,7 @@ class GradBuckets:
             for p in b["params"]:
                 # same strides as the parameter (conv weights live in channels-last order): the slot IS the gradient
                 view = torch.as_strided(b["buf"], p.shape, p.stride(), storage_offset=off)
-                self.slot[id(p)] = (bi, view)
+                self.slot[id(p)] = (bi, view, off)
                 off += p.numel()
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self._install_sinks()
@@ -64,13 +64,13 @@ class GradBuckets:
     def _install_sinks(self):
         try:
             from . import functional as VF
-            VF.set_grad_sinks({p.data_ptr(): (self.slot[id(p)][1], p) for p in self.params})
+            VF.set_grad_sinks({p.data_ptr(): (self.buckets[self.slot[id(p)][0]]["buf"], self.slot[id(p)][2], p) for p in self.params})
         except Exception:  # pragma: no cover - CPU-only host-logic tests
             pass
 
     # ---- hook: called once per parameter per backward, after .grad has been accumulated -----------
     def _on_grad(self, p):
-        bi, view = self.slot[id(p)]
+        bi, view, _ = self.slot[id(p)]
         g = p.grad
         if g.data_ptr() != view.data_ptr():
             # gradient was produced elsewhere (e.g. accumulated over several backward calls): copy in
