@@ -184,8 +184,8 @@ int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream);
  * w_cl: bf16 copy of the layer's weight in channels-last element order, i.e. exactly the bytes of the nn.Parameter when it is
  * kept in torch.channels_last memory format: nn.Conv2d [co][kh][kw][ci], nn.ConvTranspose2d [ci][kh][kw][co], nn.Linear
  * [out][in].  The TMA reads it in place, as a K-major or an MN-major tcgen05 operand depending on the direction.
- * dw_cl: fp32 gradient in the same element order, zeroed by the call unless accumulate != 0 (then dw_cl += dL/dw: the
- * caller guarantees it holds what the gradient must be added to, e.g. zeros left by vp_rmsprop_step_shadow).
+ * dw_cl: fp32 gradient in the same element order.  prezeroed != 0: the caller guarantees that dw_cl already holds zeros
+ * (e.g. cleared by vp_rmsprop_step_shadow), so the call skips its own clearing pass.
  * bf16 activations, tcgen05 engine only:
  * VP_EUNSUPPORTED when the shape is not eligible (reduction channels not a multiple of 64, ...). */
 int vp_conv_fwd_cl(const VpConvGeom* g, const void* x, const void* w_cl, const float* bias, void* y, int out_dtype,
@@ -201,7 +201,7 @@ int vp_conv_fwd_cl_stats(const VpConvGeom* g, const void* x, const void* w_cl, v
 int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, float momentum, float eps,
                            float* mean, float* invstd, float* scale, float* shift, int64_t rows, int c, void* stream);
-int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int accumulate, void* stream);
+int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int prezeroed, void* stream);
 /* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
 int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
 
@@ -220,7 +220,7 @@ int vp_thin_conv_fwd(const VpConvGeom* g, const void* x, const float* w, const f
 int vp_thin_conv_fwd_stats(const VpConvGeom* g, const void* x, const float* w, void* y, float* stat_parts,
                            int stat_capacity, int* nparts, void* stream);
 int vp_thin_conv_dgrad(const VpConvGeom* g, const void* dy, const float* w, void* dx, int out_dtype, void* stream);
-int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, int accumulate, void* stream);
+int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy, float* dw, int prezeroed, void* stream);
 
 /* ---- optimiser: torch.optim.RMSprop (train.py:136-140; alpha .99, eps 1e-8, no momentum, not centered) as ONE
  * multi-tensor kernel over fp32 masters:  sq = alpha*sq + (1-alpha)*g*g;  p -= lr * g / (sqrt(sq) + eps).
@@ -230,7 +230,7 @@ int vp_rmsprop_step(void* const* params, const void* const* grads, void* const* 
 /* same, and shadows[i] (nullable per entry) receives the bf16 copy of the updated parameter in the same element order:
  * the operand the in-place contractions (vp_conv_*_cl) read next step, so no cast pass is needed.  zero_grads != 0: each
  * gradient is cleared after it has been consumed, so that the next step's weight-gradient kernels can accumulate into
- * it without a memset (vp_conv_wgrad_cl / vp_thin_conv_wgrad with accumulate = 1). */
+ * it without a memset (vp_conv_wgrad_cl / vp_thin_conv_wgrad with prezeroed = 1). */
 int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const* sq, void* const* shadows,
                            const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay,
                            int zero_grads, void* stream);

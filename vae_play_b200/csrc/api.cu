@@ -241,7 +241,7 @@ extern "C" int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* 
     cudaStream_t s = (cudaStream_t)stream;
     TapWgrad p;
     fill_wgrad(g, x, dy, dw_cl, true, p);
-    if (!accumulate) cudaMemsetAsync(dw_cl, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    p.accumulate = accumulate ? 1 : 0;
     const int rc = launch_tapwgrad_win(p, g->kh, g->kw, g->pad, s);
     if (rc != VP_EUNSUPPORTED) return rc;
     return launch_tapwgrad_tc(p, s);
@@ -255,7 +255,6 @@ extern "C" int vp_conv_wgrad(const VpConvGeom* g, const void* x, const void* dy,
     cudaStream_t s = (cudaStream_t)stream;
     TapWgrad p;
     fill_wgrad(g, x, dy, dwp, false, p);
-    cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     if (engine != VP_ENGINE_SIMT && dtype == VP_BF16) {
         int rc = launch_tapwgrad_win(p, g->kh, g->kw, g->pad, s);
         if (rc == VP_EUNSUPPORTED) rc = launch_tapwgrad_tc(p, s);

@@ -127,6 +127,7 @@ struct TapWgrad {
     const void* A;  // [n, ha, wa, AC]
     float* dWp;     // [taps][GC][AC] (packed) or any layout with AC contiguous: element (tap, gc, ac) at tap*o_st + gc*o_sg + ac
     int64_t o_st, o_sg;
+    int accumulate; // 0: the launcher clears dWp first when it reduces with atomics; 1: dWp is known to hold zeros already
     int n, gh, gw, GC;
     int ha, wa, AC;
     int as;

@@ -625,11 +625,36 @@ __global__ void __launch_bounds__(256) transpose_bt_kernel(const T* __restrict__
     for (int i = ty; i < 32; i += 8)
         if (c0 + i < cols && r0 + tx < rows) d[(int64_t)(c0 + i) * rows + r0 + tx] = tile[tx][i];
 }
+
+// bf16, rows and cols multiples of 64: 64 x 64 tiles, every global access is a 4-byte pair, the 2 x 2 blocks are
+// transposed in registers on the way out (4x fewer, 2x wider memory instructions than the generic kernel)
+__global__ void __launch_bounds__(256) transpose_bt64_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int rows, int cols) {
+    __shared__ uint32_t tile[64][33];
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t* s = src + ((int64_t)b * rows * cols >> 1);
+    uint32_t* d = dst + ((int64_t)b * rows * cols >> 1);
+    for (int i = ty; i < 64; i += 8) tile[i][tx] = s[((int64_t)(r0 + i) * cols + c0 >> 1) + tx];     // row r0+i, column pair tx
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        // output rows (= source columns) c0 + 2i, c0 + 2i + 1; output column pair tx = source rows r0 + 2tx, r0 + 2tx + 1
+        const uint32_t a = tile[2 * tx][i], bb = tile[2 * tx + 1][i];
+        const uint32_t lo = (a & 0xffffu) | (bb << 16), hi = (a >> 16) | (bb & 0xffff0000u);
+        d[((int64_t)(c0 + 2 * i) * rows + r0 >> 1) + tx] = lo;
+        d[((int64_t)(c0 + 2 * i + 1) * rows + r0 >> 1) + tx] = hi;
+    }
+}
 }  // namespace
 }  // namespace vp
 
 extern "C" int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream) {
     VP_CHECK_ARG(src && dst && batch > 0 && rows > 0 && cols > 0 && batch <= 65535, "vp_transpose_bt: bad arguments");
+    if (dtype == VP_BF16 && rows % 64 == 0 && cols % 64 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
+        transpose_bt64_kernel<<<dim3(cols / 64, rows / 64, batch), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, (uint32_t*)dst, rows, cols);
+        VP_CHECK_LAUNCH("vp_transpose_bt");
+        return VP_OK;
+    }
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
     if (dtype == VP_F32) transpose_bt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, cols);
     else transpose_bt_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, cols);

@@ -591,6 +591,7 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int m, int n) {
 struct TcWgradParams {
     float* dWp;
     int64_t o_st, o_sg;        // element (tap, gc, ac) at dWp[tap*o_st + gc*o_sg + ac]
+    int store_only;            // one pixel split and nothing to add to: plain vector stores instead of red.global.add
     int GC, AC;
     int as;
     int bt, ht, wt;            // pixel brick, bt*ht*wt == 64
@@ -704,7 +705,12 @@ __global__ void __launch_bounds__(kFwdThreads) tapwgrad_tc_kernel(const __grid_c
             tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
             tmem_ld_wait();
             if (gc < p.GC) {
-                if (c0 + c + 32 <= p.AC) {
+                if (p.store_only && c0 + c + 32 <= p.AC) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(out + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                                              __uint_as_float(v[j + 3]));
+                } else if (c0 + c + 32 <= p.AC) {
                     // whole chunk inside the tensor: 8 vector reductions (red.global.add.v4.f32), no per-element predicates
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
@@ -792,6 +798,9 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
     if (r) { set_error("tcgen05 wgrad: cuTensorMapEncodeTiled(G) failed (%d)", r); return VP_EUNSUPPORTED; }
     r = encode_nhwc(&mA, p.A, p.AC, p.wa, p.ha, p.n, wt, ht, bt, p.as);
     if (r) { set_error("tcgen05 wgrad: cuTensorMapEncodeTiled(A) failed (%d)", r); return VP_EUNSUPPORTED; }
+    // a single pixel split writes every element exactly once: no clearing pass, plain stores (the fc layers: K = batch only)
+    tp.store_only = (nsplit == 1 && p.AC % 32 == 0) ? 1 : 0;
+    if (!p.accumulate && !tp.store_only) cudaMemsetAsync(p.dWp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     dim3 grid((unsigned)out_tiles, (unsigned)nsplit);
     if (BN == 128) return launch_wgrad_cfg<128, 4>(mG, mA, tp, grid, s);
     return launch_wgrad_cfg<64, 4>(mG, mA, tp, grid, s);
