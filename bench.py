@@ -200,7 +200,7 @@ def run_ours(args):
 
     graph_a = graph_b = None
     static_x = x_dev.clone()
-    launches_per_replay = 0
+    launches_per_replay = launches_opt = 0
     if use_graph:
         # two CUDA graphs per step: A = forward + loss + backward (gradients land in the flat buckets),
         # B = optimiser; the bucketed NCCL all-reduce runs between them, outside the captured regions
@@ -221,8 +221,10 @@ def run_ours(args):
         launches_per_replay = _lib.launch_count() - l0
         if buckets is not None:
             buckets.allreduce(check_missing=False)
+        l0 = _lib.launch_count()
         with torch.cuda.graph(graph_b, pool=graph_a.pool()):
             opt.step()
+        launches_opt = _lib.launch_count() - l0
 
     def step(x):
         if graph_a is None:
@@ -261,7 +263,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    launches = (_lib.launch_count() - n0) if graph_a is None else launches_per_replay * args.steps
+    launches = (_lib.launch_count() - n0) if graph_a is None else (launches_per_replay + launches_opt) * args.steps
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -312,6 +314,7 @@ def run_ours(args):
             "roofline": roof,
             "step_tflops_per_gpu": round(step_tf, 2) if step_tf else None,
             "step_frac_of_sustained_bf16": round(step_tf / peaks["tf_sustained"], 4) if step_tf else None,
+            "step_frac_of_burst_bf16": round(step_tf / peaks["tf_burst"], 4) if step_tf else None,
             "peaks": peaks["src"],
             "loss": loss_host,
         }
@@ -322,31 +325,86 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def kernel_probe(model, B, dev, peaks, iters=20):
-    """Time the dominant contraction alone with CUDA events on the launching stream."""
+def _graph_time_us(fn, iters):
+    """Device time per call: `iters` calls captured into one CUDA graph, replayed once warm and once timed with CUDA
+    events on the replaying stream (no host launch overhead inside the timed region)."""
     import torch
-
-    import vae_play_b200.functional as VF
-    blk = list(model.decoder.conv)[-2]          # last DecoderBlock: convT 5x5 s2, 128->64 at 32x32 -> 64x64 (64x64 model)
-    layer = blk._layer
-    hin = model.decoder.conv[0]._layer and (8 * 2 ** (len(list(model.decoder.conv)) - 2))
-    x = torch.randn(B, hin, hin, layer.cin, device=dev).to(VF.act_dtype())
-    w = blk.conv.weight.detach()
-    for _ in range(3):
-        layer.fwd(x, w, None)
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        fn()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    graph.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        layer.fwd(x, w, None)
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    flops = 2.0 * B * hin * hin * layer.cin * layer.cout * 25          # 2*MAC of the transposed conv
-    tf = flops / (ms / 1e3) / 1e12
-    return {"bound": "tensor", "kernel": f"decoder.conv.{len(list(model.decoder.conv)) - 2} ConvTranspose2d fwd (4 phase launches)",
-            "achieved": round(tf, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": round(tf / peaks["tf_burst"], 4),
-            "traffic": None, "ms_per_launch_group": round(ms, 4), "peak_kind": f"{peaks['src']} burst"}
+    return e0.elapsed_time(e1) / iters * 1e3
+
+
+def kernel_probe(model, B, dev, peaks, iters=20):
+    """Every contraction of the step timed alone (CUDA events around a graph of `iters` launches) and the dominant one --
+    the last DecoderBlock's transposed conv forward, the single longest launch of the step -- reported as `roofline`."""
+    import torch
+
+    import vae_play_b200.functional as VF
+    dt = VF.act_dtype()
+    rows = []
+
+    def add(name, layer, weight, hin):
+        x = torch.randn(B, hin, hin, layer.cin, device=dev).to(dt)
+        w = weight.detach()
+        y = layer.fwd(x, w, None)
+        dy = torch.randn_like(y)
+        mac = B * (hin * hin if layer.kind != "conv" else y.shape[1] * y.shape[2]) * layer.cin * layer.cout * layer.k * layer.k
+        gf = 2.0 * mac / 1e9
+        t_f = _graph_time_us(lambda: layer.fwd(x, w, None), iters)
+        t_d = _graph_time_us(lambda: layer.dgrad(dy, w, tuple(x.shape)), iters) if layer.cin > 1 else None
+        t_w = _graph_time_us(lambda: layer.wgrad(x, dy, w), iters)
+        tf = lambda t: round(gf / t * 1e3, 1) if t else None
+        rows.append({"layer": name, "gflop": round(gf, 2), "fwd_us": round(t_f, 1), "fwd_tflops": tf(t_f),
+                     "dgrad_us": round(t_d, 1) if t_d else None, "dgrad_tflops": tf(t_d), "wgrad_us": round(t_w, 1), "wgrad_tflops": tf(t_w)})
+        return gf, t_f
+
+    img = 8 * 2 ** len(list(model.encoder.conv))
+    hh = img
+    for i, blk in enumerate(model.encoder.conv):
+        add(f"encoder.conv.{i}", blk._layer, blk.conv.weight, hh)
+        hh //= 2
+    add("encoder.fc", model.encoder._fc_layer, model.encoder.fc[0].weight, 1)
+    add("decoder.fc", model.decoder._fc_layer, model.decoder.fc[0].weight, 1)
+    hh = 8
+    dom = None
+    blocks = list(model.decoder.conv)
+    for i, blk in enumerate(blocks[:-1]):
+        gf, t_f = add(f"decoder.conv.{i}", blk._layer, blk.conv.weight, hh)
+        dom = (f"decoder.conv.{i} ConvTranspose2d 5x5 s2 forward ({blk._layer.cin}->{blk._layer.cout} ch, {hh}x{hh}->{2*hh}x{2*hh}, one launch)", gf, t_f)
+        hh *= 2
+    add(f"decoder.conv.{len(blocks)-1}", model.decoder._out_layer, blocks[-1][0].weight, hh)
+    name, gf, t_f = dom
+    tflops = gf / t_f * 1e3
+    total_us = sum((r["fwd_us"] or 0) + (r["dgrad_us"] or 0) + (r["wgrad_us"] or 0) for r in rows)
+    total_gf = sum(r["gflop"] * (3 if r["dgrad_us"] else 2) for r in rows)
+    return {"bound": "tensor", "kernel": name, "achieved": round(tflops, 2), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+            "frac": round(tflops / peaks["tf_burst"], 4), "traffic": DOMINANT_TRAFFIC_BYTES.get(img),
+            "us_per_launch": round(t_f, 2), "flop_per_launch": gf * 1e9, "peak_kind": f"{peaks['src']} burst",
+            "all_contractions": {"sum_us": round(total_us, 1), "gflop": round(total_gf, 1), "tflops": round(total_gf / total_us * 1e3, 1),
+                                 "frac_of_burst": round(total_gf / total_us * 1e3 / peaks["tf_burst"], 4), "layers": rows}}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture
+# summarised in profiles/ (per image size); None until captured
+DOMINANT_TRAFFIC_BYTES = {64: 308572416}     # profiles/r01_ncu_prof_ct3_fwd_r1d.summary.txt: 200.73 MB read + 107.84 MB written
 
 
 def main():

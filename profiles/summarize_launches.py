@@ -10,7 +10,13 @@ def main(path, last_n=None):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    if last_n:
+    if last_n and str(last_n).startswith("step:"):
+        # one whole training step: the launches after the second-to-last optimiser kernel up to and including the last one
+        key = str(last_n)[5:]
+        idx = [i for i, r in enumerate(rows) if key in r["Kernel Name"]]
+        if len(idx) >= 2:
+            rows = rows[idx[-2] + 1: idx[-1] + 1]
+    elif last_n:
         rows = rows[-int(last_n):]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for row in rows:
@@ -28,10 +34,14 @@ def main(path, last_n=None):
         print(f"{k[:100]:100s} {v[0]:5d} {v[1]:10.1f} {100 * v[1] / tot:6.1f}%")
     fam = collections.defaultdict(float)
     for k, v in agg.items():
-        key = ("tcgen05 contraction" if "_tc_kernel" in k else "cuda-core contraction" if ("simt" in k or "thin_wgrad" in k)
-               else "norm/act" if any(s in k for s in ("stats_kernel", "apply_kernel", "bwd_reduce", "finalize", "colsum"))
-               else "pack/unpack/layout" if any(s in k for s in ("pack", "nchw", "nhwc", "cast"))
-               else "torch (optimizer etc.)" if k.startswith("at::") else "other (loss, reparam, ...)")
+        key = ("tcgen05 contraction (fwd/dgrad)" if ("tapgemm_tc" in k or "tapgemm_win" in k or "splitk" in k)
+               else "tcgen05 contraction (wgrad)" if "tapwgrad" in k
+               else "tcgen05 thin layers" if "thin_" in k
+               else "cuda-core contraction" if "simt" in k
+               else "norm/act" if any(s_ in k for s_ in ("norm_stream", "stats_kernel", "apply_kernel", "bwd_reduce", "finalize", "colsum", "bn_rows"))
+               else "optimiser" if "rmsprop" in k
+               else "pack/cast/layout" if any(s_ in k for s_ in ("pack", "nchw", "nhwc", "cast", "transpose"))
+               else "torch" if k.startswith("at::") else "other (loss, reparam, ...)")
         fam[key] += v[1]
     print("# by family")
     for k, v in sorted(fam.items(), key=lambda kv: -kv[1]):

@@ -19,6 +19,8 @@ elif kind == "conv":
     layer = VF.TapLayer("conv", cin, cout, k=5, stride=2, pad=2); w = torch.randn(cout, cin, 5, 5, device="cuda") * 0.05
 else:
     layer = VF.TapLayer("conv", cin, cout, k=5, stride=1, pad=2); w = torch.randn(cout, cin, 5, 5, device="cuda") * 0.05
+if w.dim() == 4 and cin % 64 == 0 and cout % 64 == 0:
+    w = w.contiguous(memory_format=torch.channels_last)      # the layout the models keep their conv weights in
 x = torch.randn(B, hw, hw, cin, device="cuda").to(torch.bfloat16)
 y = layer.fwd(x, w, None)
 dy = torch.randn_like(y)
