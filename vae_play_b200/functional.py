@@ -37,11 +37,12 @@ def persistent_grads(params):
     optimiser that clears each gradient once it has consumed it (``FusedRMSprop(zero_grads=True)``) the weight-gradient
     kernels accumulate into known-zero memory: no per-tensor memset, no allocation.  Returns the flat buffer."""
     params = [p for p in params if p.requires_grad]
-    flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=params[0].device)
+    pad = lambda p: (p.numel() + 3) & ~3          # every slot starts 16-byte aligned
+    flat = torch.zeros(sum(pad(p) for p in params), dtype=torch.float32, device=params[0].device)
     sinks, off = {}, 0
     for p in params:
         sinks[p.data_ptr()] = (flat, off, p)
-        off += p.numel()
+        off += pad(p)
     set_grad_sinks(sinks)
     for e in _GRAD_SINKS.values():
         e[3] = True

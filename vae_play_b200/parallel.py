@@ -37,11 +37,11 @@ class GradBuckets:
         self.buckets = []          # list of dict(buf, params, ready, handle)
         cur, cur_n = [], 0
         for p in order:
-            if cur and cur_n + p.numel() > cap:
+            if cur and cur_n + self._padded(p) > cap:
                 self._close(cur)
                 cur, cur_n = [], 0
             cur.append(p)
-            cur_n += p.numel()
+            cur_n += self._padded(p)
         if cur:
             self._close(cur)
         self.slot = {}
@@ -51,12 +51,17 @@ class GradBuckets:
                 # same strides as the parameter (conv weights live in channels-last order): the slot IS the gradient
                 view = torch.as_strided(b["buf"], p.shape, p.stride(), storage_offset=off)
                 self.slot[id(p)] = (bi, view, off)
-                off += p.numel()
+                off += self._padded(p)
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self._install_sinks()
 
+    @staticmethod
+    def _padded(p):
+        """slot size in elements: every slot starts 16-byte aligned (vector stores / reductions of the wgrad kernels)"""
+        return (p.numel() + 3) & ~3
+
     def _close(self, plist):
-        n = sum(p.numel() for p in plist)
+        n = sum(self._padded(p) for p in plist)
         dev = plist[0].device
         self.buckets.append({"buf": torch.zeros(n, dtype=torch.float32, device=dev), "params": list(plist),
                              "ready": 0, "handle": None})
