@@ -145,6 +145,8 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s);
 int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t s);
 // stride-1 tap sets with the activation halo re-used across taps; VP_EUNSUPPORTED when not of that form
 int launch_tapgemm_win(const TapGemm* phases, int nphases, cudaStream_t s);
+// two output-parity phases per tile, shared shifts as one N = 128 MMA (64-channel stride-2 layers); VP_EUNSUPPORTED otherwise
+int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s);
 bool tc_available();
 
 }  // namespace vp

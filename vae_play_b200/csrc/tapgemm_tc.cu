@@ -434,6 +434,8 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     const TapGemm& p = phases[0];
     // stride-1 tap sets go to the windowed (halo re-use) kernel first; VP_TC_VARIANT=2 disables it (A/B measurements)
     if (tc_variant() != 2) {
+        const int rc0 = launch_tapgemm_pair(phases, nphases, s);
+        if (rc0 != VP_EUNSUPPORTED) return rc0;
         const int rc = launch_tapgemm_win(phases, nphases, s);
         if (rc != VP_EUNSUPPORTED) return rc;
     }
