@@ -190,6 +190,29 @@ def run_ours(args):
         loss.backward()
         return loss
 
+    # Data parallel, graph mode: the backward is cut at the output of the encoder's conv stack.  Stage 1 (decoder, heads,
+    # encoder.fc: 94 % of the gradient bytes) and stage 2 (the encoder convs) are separate graphs, and the all-reduce of
+    # the stage-1 buckets runs on NCCL's stream while stage 2 executes.
+    enc_conv_params = [p for blk in model.encoder.conv for p in blk.parameters()]
+    enc_conv_ids = {id(p) for p in enc_conv_params}
+    stage1_params = [p for p in params if id(p) not in enc_conv_ids]
+    cut = {}
+
+    def fwd_bwd_stage1(x):
+        taps = []
+        xt, mulv, kl = model.vae_forward(x, rng=(rank, 0, off_dev), taps=taps)
+        VF.philox_advance(off_dev, eps_inc)
+        loss = VF.vae_loss(x, xt, kl, mse_scale=1.0 / world)
+        a3 = taps[0]
+        a3.retain_grad()
+        loss.backward(inputs=stage1_params + [a3], retain_graph=True)
+        cut["a"] = a3
+        return loss
+
+    def bwd_stage2():
+        a3 = cut["a"]
+        a3.backward(a3.grad, inputs=enc_conv_params)
+
     def eager_step(x):
         opt.zero_grad(set_to_none=True)
         loss = fwd_bwd(x)
@@ -198,7 +221,9 @@ def run_ours(args):
         opt.step()
         return loss
 
-    graph_a = graph_b = None
+    graph_a = graph_b = graph_a2 = None
+    early = []
+    split_backward = use_graph and buckets is not None and args.split_backward
     static_x = x_dev.clone()
     launches_per_replay = launches_opt = 0
     if use_graph:
@@ -216,8 +241,16 @@ def run_ours(args):
         opt.zero_grad(set_to_none=True)
         graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         l0 = _lib.launch_count()
-        with torch.cuda.graph(graph_a):
-            static_loss = fwd_bwd(static_x)
+        if split_backward:
+            early = buckets.buckets_within(stage1_params)
+            graph_a2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph_a):
+                static_loss = fwd_bwd_stage1(static_x)
+            with torch.cuda.graph(graph_a2, pool=graph_a.pool()):
+                bwd_stage2()
+        else:
+            with torch.cuda.graph(graph_a):
+                static_loss = fwd_bwd(static_x)
         launches_per_replay = _lib.launch_count() - l0
         if buckets is not None:
             buckets.allreduce(check_missing=False)
@@ -232,6 +265,9 @@ def run_ours(args):
         if x.data_ptr() != static_x.data_ptr():
             static_x.copy_(x, non_blocking=True)
         graph_a.replay()
+        if graph_a2 is not None:
+            buckets.allreduce_subset(early)      # overlaps the encoder-conv backward below
+            graph_a2.replay()
         if buckets is not None:
             buckets.allreduce(check_missing=False)
         graph_b.replay()
@@ -306,7 +342,9 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": dict(workload_config(args, B), parallelism=f"dp{world}",
                            l2="no explicit flush: per-step working set (~1 GB of activations at batch 256) exceeds the 126 MB L2",
-                           cuda_graph=graph_a is not None),
+                           cuda_graph=graph_a is not None,
+                           allreduce=(None if world == 1 else "bucketed NCCL all-reduce; decoder/fc buckets overlap the encoder-conv backward graph"
+                                      if graph_a2 is not None else "bucketed NCCL all-reduce between backward and optimiser")),
             "clocks": clocks,
             "e2e": {"value": round(e2e_ips, 1), "unit": "images/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": round(ms2 / args.steps, 4)},
@@ -404,7 +442,7 @@ def kernel_probe(model, B, dev, peaks, iters=20):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture
 # summarised in profiles/ (per image size); None until captured
-DOMINANT_TRAFFIC_BYTES = {64: 308572416}     # profiles/r01_ncu_prof_ct3_fwd_r1d.summary.txt: 200.73 MB read + 107.84 MB written
+DOMINANT_TRAFFIC_BYTES = {64: 222103552}     # profiles/r01_ncu_prof_ct3_fwd_r1e.summary.txt: 132.05 MB read + 90.05 MB written
 
 
 def main():
@@ -421,6 +459,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra-warmup", type=int, default=60, help="additional untimed steps so clocks ramp up and the sampler is live")
     ap.add_argument("--torch-optim", action="store_true", help="use torch.optim.RMSprop instead of the fused multi-tensor kernel")
+    ap.add_argument("--split-backward", action="store_true",
+                    help="data parallel: cut the backward graph at the encoder conv stack and run the all-reduce of the decoder/fc buckets "
+                         "next to the conv-stack backward (measured at 2 GPUs: no gain, the persistent GEMM kernels leave NCCL no SMs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -87,11 +87,15 @@ class Encoder(nn.Module):
         self._heads = DualLinear(1024, z_size)
         self.z_size = z_size
 
-    def forward_packed(self, ten):
-        """NCHW fp32 image -> fused head output [B, 2Z] = (mu | logvar), fp32."""
+    def forward_packed(self, ten, taps=None):
+        """NCHW fp32 image -> fused head output [B, 2Z] = (mu | logvar), fp32.  ``taps`` (a list) receives the output of
+        the conv stack: the point where a two-stage backward can be cut (bench.py overlaps the gradient all-reduce of
+        everything downstream of it with the backward of the conv stack)."""
         a = VF.to_channels_last(ten)
         for blk in self.conv:
             a = blk.forward_cl(a)
+        if taps is not None:
+            taps.append(a)
         if a.shape[1] != 8 or a.shape[2] != 8:
             raise ValueError(f"Encoder expects an 8x8 map before fc, got {tuple(a.shape)} (img_size must be 8 * 2**iter_level)")
         h, _ = VF.fused_layer(VF.hwc_to_chw_flat(a), self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
@@ -274,9 +278,9 @@ class VaeGan(nn.Module):
             return x_tilde, params
 
     # ---- fused hot path (the north-star step): encoder -> reparam+KL -> decoder ---------------------
-    def vae_forward(self, x, eps=None, rng=None):
+    def vae_forward(self, x, eps=None, rng=None, taps=None):
         """Returns (x_tilde NCHW fp32, mu|logvar packed [B,2Z] fp32, kl [B]) without leaving channels-last."""
-        mulv = self.encoder.forward_packed(x)
+        mulv = self.encoder.forward_packed(x, taps)
         z, kl = VF.reparam_kl(mulv, None, eps=eps, z_dtype=VF.act_dtype(), rng=rng)
         xt = self.decoder.forward_cl(z.reshape(len(z), 1, 1, -1))
         return VF.from_channels_last(xt), mulv, kl

@@ -101,6 +101,22 @@ class GradBuckets:
                 b["handle"] = None
             b["ready"] = 0
 
+    def allreduce_subset(self, bucket_ids):
+        """Issue (asynchronously, on NCCL's stream, ordered after the work already queued on the current stream) the
+        all-reduce of the given buckets -- used when the caller knows from the structure of its step that they are
+        complete (CUDA-graph replay, where the readiness hooks do not run).  ``allreduce()`` later waits for them."""
+        if self.world <= 1:
+            return
+        for bi in bucket_ids:
+            b = self.buckets[bi]
+            if b["handle"] is None:
+                b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def buckets_within(self, params):
+        """Indices of the buckets all of whose parameters are in ``params``."""
+        ids = {id(p) for p in params}
+        return [i for i, b in enumerate(self.buckets) if all(id(p) in ids for p in b["params"])]
+
     def total_bytes(self):
         return sum(b["buf"].numel() * 4 for b in self.buckets)
 
