@@ -772,35 +772,32 @@ def test_persistent_grads_and_zeroing_optimizer(vp):
 
 
 def test_two_stage_backward_matches_single(vp):
-    """bench.py's data-parallel step cuts the backward at the output of the encoder's conv stack (so that the gradient
-    all-reduce of everything downstream overlaps the conv-stack backward): same gradients as one backward call."""
-    import copy
+    """bench.py's optional data-parallel step cuts the backward at the output of the encoder's conv stack (so that the
+    gradient all-reduce of everything downstream can overlap the conv-stack backward): same gradients as one backward
+    call through the SAME forward graph."""
     import vae_play_b200.functional as VF
     from vae_play_b200.models.networks import VaeGan
     vp.set_precision("bf16")
     vp.set_engine("auto")
     VF.set_grad_sinks({})
     torch.manual_seed(1)
-    ref = VaeGan(64, 128).cuda().train()
+    m = VaeGan(64, 128).cuda().train()
     x = torch.rand(16, 1, 64, 64, device="cuda")
     eps = torch.randn(16, 128, device="cuda")
-    grads = []
-    for split in (False, True):
-        m = copy.deepcopy(ref)
-        params = list(m.encoder.parameters()) + list(m.decoder.parameters())
-        taps = []
-        xt, mulv, kl = m.vae_forward(x, eps=eps, taps=taps)
-        loss = VF.vae_loss(x, xt, kl)
-        if split:
-            conv_params = [p for blk in m.encoder.conv for p in blk.parameters()]
-            ids = {id(p) for p in conv_params}
-            a3 = taps[0]
-            a3.retain_grad()
-            loss.backward(inputs=[p for p in params if id(p) not in ids] + [a3], retain_graph=True)
-            assert all(p.grad is None for p in conv_params) and all(p.grad is not None for p in params if id(p) not in ids)
-            a3.backward(a3.grad, inputs=conv_params)
-        else:
-            loss.backward()
-        grads.append([npy(p.grad) for p in params])
-    for a, b in zip(*grads):
-        assert rel_l2(a, b) < 3e-2      # same kernels, same operands; two forward passes differ by atomics order, amplified by a few ReLU flips
+    params = list(m.encoder.parameters()) + list(m.decoder.parameters())
+    conv_params = [p for blk in m.encoder.conv for p in blk.parameters()]
+    ids = {id(p) for p in conv_params}
+    taps = []
+    xt, mulv, kl = m.vae_forward(x, eps=eps, taps=taps)
+    loss = VF.vae_loss(x, xt, kl)
+    a3 = taps[0]
+    a3.retain_grad()
+    loss.backward(inputs=[p for p in params if id(p) not in ids] + [a3], retain_graph=True)
+    assert all(p.grad is None for p in conv_params) and all(p.grad is not None for p in params if id(p) not in ids)
+    a3.backward(a3.grad, inputs=conv_params, retain_graph=True)
+    staged = [npy(p.grad) for p in params]
+    for p in params:
+        p.grad = None
+    loss.backward()
+    for a, p in zip(staged, params):
+        assert rel_l2(a, npy(p.grad)) < 1e-4      # same kernels on the same saved activations; only the order of fp32 atomics differs

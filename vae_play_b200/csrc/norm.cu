@@ -448,12 +448,79 @@ extern "C" int vp_norm_apply_act(const void* x, const float* scale, const float*
     return VP_OK;
 }
 
+namespace vp {
+namespace {
+template <typename T> struct AccT { typedef float type; };
+template <> struct AccT<float> { typedef double type; };   // fp32 check mode: double accumulation
+
+template <typename T>
+__device__ __forceinline__ void ldv4(const T* p, float* v);
+template <> __device__ __forceinline__ void ldv4<float>(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+template <> __device__ __forceinline__ void ldv4<bf16>(const bf16* p, float* v) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+}
+template <typename T>
+__device__ __forceinline__ void stv4(T* p, const float* v);
+template <> __device__ __forceinline__ void stv4<float>(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+template <> __device__ __forceinline__ void stv4<bf16>(bf16* p, const float* v) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+}
+
+// Activation backward of a layer WITHOUT normalisation and with very few channels (the decoder's 1-channel output conv:
+// 1 M rows x 1 channel): d = da * act'(.), per-channel sum(d) for the bias gradient.  The tensor is walked as a flat
+// array, 8 elements per thread; element i belongs to channel i % C (C <= 4).
+template <typename T>
+__global__ void __launch_bounds__(256) act_bwd_flat_kernel(const T* __restrict__ x, const T* __restrict__ da, T* __restrict__ dxo, double* sums,
+                                                           int64_t n8, int C, int act, float slope) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float v[8], d[8];
+        ldv4<T>(x + i * 8, v); ldv4<T>(x + i * 8 + 4, v + 4);
+        ldv4<T>(da + i * 8, d); ldv4<T>(da + i * 8 + 4, d + 4);
+        const int c0 = (int)((i * 8) % C);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            d[j] *= act_grad(v[j], act, slope);
+            const int c = (c0 + j) % C;
+            acc[0] += c == 0 ? d[j] : 0.f; acc[1] += c == 1 ? d[j] : 0.f; acc[2] += c == 2 ? d[j] : 0.f; acc[3] += c == 3 ? d[j] : 0.f;
+        }
+        stv4<T>(dxo + i * 8, d); stv4<T>(dxo + i * 8 + 4, d + 4);
+    }
+    __shared__ float red[8][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = warp_sum(acc[c]);
+    if ((threadIdx.x & 31) == 0)
+        for (int c = 0; c < 4; ++c) red[threadIdx.x >> 5][c] = acc[c];
+    __syncthreads();
+    if ((int)threadIdx.x < C) {
+        double t = 0;
+        for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+        atomicAdd(sums + threadIdx.x, t);
+    }
+}
+}  // namespace
+}  // namespace vp
+
 extern "C" int vp_norm_bwd_reduce(const void* x, const void* da, const float* mean, const float* invstd,
                                   const float* scale, const float* shift, double* sums, void* dxo, int dtype,
                                   int64_t groups, int64_t rpg, int c, int act, float slope, void* stream) {
     VP_CHECK_ARG(x && da && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_bwd_reduce: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_bwd_reduce: too many groups");
     cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
+    if (groups == 1 && !mean && !scale && dxo && c <= 4 && (rpg * c) % 8 == 0 && (((uintptr_t)x | (uintptr_t)da | (uintptr_t)dxo) & 15) == 0) {
+        const int64_t n8 = rpg * c / 8;
+        int64_t blocks = (n8 + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (dtype == VP_F32) act_bwd_flat_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, (float*)dxo, sums, n8, c, act, slope);
+        else act_bwd_flat_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, (bf16*)dxo, sums, n8, c, act, slope);
+        VP_CHECK_LAUNCH("vp_norm_bwd_reduce");
+        return VP_OK;
+    }
     if (groups == 1) {
         const int rc = norm_stream(2, dtype, x, da, dxo, mean, invstd, scale, shift, sums, nullptr, nullptr, rpg, c, act, slope,
                                    (cudaStream_t)stream);
@@ -510,27 +577,6 @@ extern "C" int vp_colsum(const void* x, float* out, double* scratch_c, int dtype
 namespace vp {
 namespace {
 constexpr int SM_CG = 8, SM_RS = 32, SM_V = 4;      // 8 channel groups x 4 channels, 32 row slices -> 256 threads, 32 channels per block
-
-template <typename T> struct AccT { typedef float type; };
-template <> struct AccT<float> { typedef double type; };   // fp32 check mode: double accumulation
-
-template <typename T>
-__device__ __forceinline__ void ldv4(const T* p, float* v);
-template <> __device__ __forceinline__ void ldv4<float>(const float* p, float* v) {
-    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-template <> __device__ __forceinline__ void ldv4<bf16>(const bf16* p, float* v) {
-    const uint2 t = *reinterpret_cast<const uint2*>(p);
-    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
-    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
-}
-template <typename T>
-__device__ __forceinline__ void stv4(T* p, const float* v);
-template <> __device__ __forceinline__ void stv4<float>(float* p, const float* v) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
-template <> __device__ __forceinline__ void stv4<bf16>(bf16* p, const float* v) {
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
-    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-}
 
 template <typename T>
 __global__ void __launch_bounds__(256) bn_rows_fwd_kernel(const T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,

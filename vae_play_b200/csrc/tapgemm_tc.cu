@@ -804,6 +804,9 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
     tp.store_only = (nsplit == 1 && p.AC % 32 == 0) ? 1 : 0;
     if (!p.accumulate && !tp.store_only) cudaMemsetAsync(p.dWp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     dim3 grid((unsigned)out_tiles, (unsigned)nsplit);
+    // short reductions (the fc layers: K = batch = a few bricks): a 2-stage ring is enough and lets 3 CTAs share an SM, which
+    // hides the per-CTA prologue (barrier init, TMEM allocation) and epilogue behind the neighbours' main loops
+    if (tp.bricks_per_split <= 4) return BN == 128 ? launch_wgrad_cfg<128, 2>(mG, mA, tp, grid, s) : launch_wgrad_cfg<64, 2>(mG, mA, tp, grid, s);
     if (BN == 128) return launch_wgrad_cfg<128, 4>(mG, mA, tp, grid, s);
     return launch_wgrad_cfg<64, 4>(mG, mA, tp, grid, s);
 }

@@ -434,6 +434,7 @@ class _FusedLayerFn(torch.autograd.Function):
             dt = x.dtype
             n, h, w, c = a.shape
             rows = n * h * w
+            sums = None
             if a.dtype != dt:
                 # fp32 output of a bf16 layer (mu/logvar heads): bring the gradient to the activation dtype
                 d_in = torch.empty(a.shape, dtype=dt, device=dev)
@@ -448,7 +449,9 @@ class _FusedLayerFn(torch.autograd.Function):
                 sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
                 _lib.call("vp_norm_bwd_reduce", _ptr(a), _ptr(da), None, None, None, None, _ptr(sums), _ptr(dy), _code(dt),
                           1, rows, c, ACT[act] | 16, float(slope), _stream())
-            if ctx.has_bias:
+            if ctx.has_bias and sums is not None:
+                dbias = sums[:c].float()        # the activation backward already reduced d over the rows
+            elif ctx.has_bias:
                 dbias = torch.empty(c, dtype=torch.float32, device=dev)
                 scratch = torch.empty(2 * c, dtype=torch.float64, device=dev)
                 _lib.call("vp_colsum", _ptr(dy), _ptr(dbias), _ptr(scratch), _code(dt), rows, c, _stream())
