@@ -464,7 +464,13 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     const int bt = kBlockM / (wt * ht);
     tp.bt = bt; tp.ht = ht; tp.wt = wt;
     const int tiles_b = (p.n + bt - 1) / bt;
-    const bool one_cta = tc_variant() == 1 && p.w_sk == 1;
+    // 256-wide tiles (one CTA per SM, 4 stages): an M128 x N256 MMA reads 12 KB of operands per 128 issue cycles instead of
+    // 8 KB per 64 -- measured +10..17 % on the N = 256 layers; everything else keeps two 128-wide CTAs per SM
+    int64_t mt256 = 0;
+    for (int i = 0; i < nphases; ++i)
+        mt256 += (int64_t)((phases[i].gw + wt - 1) / wt) * ((phases[i].gh + ht - 1) / ht) * tiles_b;
+    const bool wide = p.N % 256 == 0 && mt256 * (p.N / 256) * 3 >= num_sms() * 2 && tc_variant() != 5;
+    const bool one_cta = tc_variant() == 1 || wide;
     const int BN = (one_cta && p.N % 256 == 0) ? 256 : (p.N % 128 == 0) ? 128 : (p.N >= 64 ? 64 : (p.N > 16 ? 32 : 16));
     tp.ntiles_n = (p.N + BN - 1) / BN;
     int64_t mtiles = 0;
@@ -521,7 +527,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     memset(&om, 0, sizeof(om));
     int grid_used = 0;
     tp.tma_store = 0; tp.stat_parts = nullptr;
-    if (tp.ksplit == 1 && !tp.out_f32 && p.N % 64 == 0 && BN >= 32 && !one_cta && tc_variant() != 4) {
+    if (tp.ksplit == 1 && !tp.out_f32 && p.N % 64 == 0 && BN >= 32 && tc_variant() != 4) {
         // warp q of the epilogue owns rows [32q, 32q+32) of the (bt x ht x wt) brick: a {bw, bh, bb} sub-brick
         const int bw = wt < 32 ? wt : 32, bh = ht < 32 / bw ? ht : 32 / bw, bb = 32 / (bw * bh);
         bool ok = true;
@@ -534,7 +540,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
     }
     if (p.stat_parts && !tp.stat_parts) { set_error("tcgen05 engine: epilogue statistics not available for this shape"); return VP_EUNSUPPORTED; }
     if (tp.stat_parts) {
-        const int slots = num_sms() * 2;
+        const int slots = num_sms() * (one_cta ? 1 : 2);
         const int g = tp.total_tiles < slots ? tp.total_tiles : slots;
         if (g > p.stat_capacity) { set_error("tcgen05 engine: statistics buffer holds %d parts, %d needed", p.stat_capacity, g); return VP_EINVAL; }
         if (p.stat_nparts) *p.stat_nparts = g;
@@ -551,6 +557,10 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
         }
         if (rc) return rc;
         return launch_splitk_finish(ws, p.D, p.bias, p.act, p.slope, (int64_t)p.n * p.hd * p.wd * p.N, p.N, p.out_dtype == VP_F32, s);
+    }
+    if (one_cta && bmn) {
+        if (BN == 256) return launch_cfg<256, 4, 1, true>(mA, mB, om, tp, s, &grid_used);
+        return BN == 128 ? launch_cfg<128, 6, 1, true>(mA, mB, om, tp, s, &grid_used) : launch_cfg<64, 8, 1, true>(mA, mB, om, tp, s, &grid_used);
     }
     if (one_cta) {
         switch (BN) {
