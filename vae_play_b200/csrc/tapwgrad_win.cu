@@ -272,10 +272,22 @@ int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t
     rp.nbricks = (int)nbricks;
     rp.mtiles = (p.GC + 127) / 128; rp.ntiles = p.AC / 64;
     const int sets = kh * rp.mtiles * rp.ntiles;
-    int nsplit = num_sms() / sets;          // one wave of CTAs (1 CTA/SM: the kw accumulators fill TMEM)
-    const int max_split = (rp.nbricks + 3) / 4;
-    if (nsplit > max_split) nsplit = max_split;
-    if (nsplit < 1) nsplit = 1;
+    // pixel splits: minimise  waves x (bricks per CTA + epilogue)  -- one CTA per SM (the kw accumulators fill TMEM), so a
+    // launch of `sets x nsplit` CTAs runs in ceil(./#SMs) waves; the wide layers (sets = 80 / 160 at 512 channels) would
+    // otherwise leave half of the machine idle in the last wave
+    const int max_split = (rp.nbricks + 7) / 8;
+    int cand_max = num_sms() / sets > 8 ? num_sms() / sets : 8;
+    if (cand_max > max_split) cand_max = max_split;
+    if (cand_max < 1) cand_max = 1;
+    int nsplit = 1;
+    int64_t best = -1;
+    for (int c = 1; c <= cand_max; ++c) {
+        const int bps = (rp.nbricks + c - 1) / c;
+        const int ctas = sets * ((rp.nbricks + bps - 1) / bps);
+        const int64_t waves = (ctas + num_sms() - 1) / num_sms();
+        const int64_t cost = waves * (bps + 8);          // an epilogue (kw x 128 x 64 fp32 reductions) costs about 8 bricks
+        if (best < 0 || cost < best) { best = cost; nsplit = c; }
+    }
     rp.bricks_per_split = (rp.nbricks + nsplit - 1) / nsplit;
     nsplit = (rp.nbricks + rp.bricks_per_split - 1) / rp.bricks_per_split;
 
