@@ -468,6 +468,8 @@ TC_SHAPES = [
     # channels-last weights: forward / dgrad / wgrad on the module's own weight (K-major and MN-major operands), no packing
     ("conv_cl", 64, 128, 32, 4), ("conv_cl", 128, 256, 16, 3), ("convT_cl", 256, 256, 8, 4), ("convT_cl", 256, 128, 16, 2),
     ("convT_cl", 128, 64, 32, 2), ("conv_s1_cl", 64, 128, 24, 2), ("conv_k3_cl", 128, 64, 20, 3),
+    # ragged grids through the stride-2 sub-lattice window kernel (forward of a conv, data gradient of a transposed conv)
+    ("conv_cl", 64, 128, 26, 3), ("conv_cl", 128, 64, 50, 2), ("convT_cl", 128, 64, 13, 2), ("convT_cl", 64, 128, 27, 2),
 ]
 
 

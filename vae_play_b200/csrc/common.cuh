@@ -147,6 +147,8 @@ int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t
 int launch_tapgemm_win(const TapGemm* phases, int nphases, cudaStream_t s);
 // two output-parity phases per tile, shared shifts as one N = 128 MMA (64-channel stride-2 layers); VP_EUNSUPPORTED otherwise
 int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s);
+// stride-2 gather form with per-parity sub-lattice halos shared by the taps of a class; VP_EUNSUPPORTED otherwise
+int launch_tapgemm_gwin(const TapGemm& p, cudaStream_t s);
 bool tc_available();
 
 }  // namespace vp

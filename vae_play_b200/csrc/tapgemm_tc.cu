@@ -433,6 +433,10 @@ bool tc_available() {
 int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) {
     const TapGemm& p = phases[0];
     // stride-1 tap sets go to the windowed (halo re-use) kernel first; VP_TC_VARIANT=2 disables it (A/B measurements)
+    if (tc_variant() != 2 && nphases == 1) {
+        const int rcg = launch_tapgemm_gwin(phases[0], s);
+        if (rcg != VP_EUNSUPPORTED) return rcg;
+    }
     if (tc_variant() != 2) {
         const int rc0 = launch_tapgemm_pair(phases, nphases, s);
         if (rc0 != VP_EUNSUPPORTED) return rc0;
