@@ -16,9 +16,13 @@
  *   - activations are channels-last (NHWC) in `dtype` (VP_F32: fp32 check mode on CUDA cores;
  *     VP_BF16: bf16 storage, tcgen05 tensor-core contractions with fp32 accumulation).
  *     Parameters, statistics, losses and gradients of parameters are always fp32.
- *   - conv weights are consumed in a packed tap-major layout Wp[tap][N][K] produced by
- *     vp_pack_weight (tap = ky*kw + kx); parameter gradients are produced in the same packed
- *     layout in fp32 and scattered back to the torch layout by vp_unpack_wgrad.
+ *   - weights: three routes.  (1) IN PLACE (vp_conv_*_cl): the layer's own weight, kept in channels-last element
+ *     order, is read by the TMA as a tcgen05 operand and its gradient written in the same order -- no packed copies
+ *     (bf16, both channel counts multiples of 64).  (2) THIN (vp_thin_conv_*): single-channel layers read the fp32
+ *     weight directly.  (3) PACKED (vp_conv_fwd/dgrad/wgrad): tap-major panels Wp[tap][N][K] built by vp_pack_weight
+ *     (tap = ky*kw + kx), gradients in the same packed layout scattered back by vp_unpack_wgrad -- the fp32 check
+ *     mode and every other shape.
+ *   - one stream at a time per process for calls that use the workspace registered with vp_set_workspace.
  */
 #ifndef VAEPLAY_B200_H
 #define VAEPLAY_B200_H
