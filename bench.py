@@ -173,6 +173,10 @@ def run_ours(args):
     buckets = GradBuckets(params, world, overlap=not use_graph) if world > 1 else None
     if buckets is None and not args.torch_optim:
         VF.persistent_grads(params)
+    # data parallel: one optimiser per gradient bucket, so that the update of bucket i runs while NCCL reduces bucket i+1
+    bucket_opts = None
+    if buckets is not None and not args.torch_optim and not args.no_bucket_pipeline:
+        bucket_opts = [FusedRMSprop(b["params"], lr=1e-4, zero_grads=True) for b in buckets.buckets]
     torch.manual_seed(1234 + rank)
     x_host = torch.rand(B, cin, img, img).pin_memory()
     x_dev = x_host.to(dev)
@@ -218,10 +222,15 @@ def run_ours(args):
         loss = fwd_bwd(x)
         if buckets is not None:
             buckets.allreduce()
-        opt.step()
+        if bucket_opts is not None:
+            for o in bucket_opts:
+                o.step()
+        else:
+            opt.step()
         return loss
 
     graph_a = graph_b = graph_a2 = None
+    graph_bs = []
     early = []
     split_backward = use_graph and buckets is not None and args.split_backward
     static_x = x_dev.clone()
@@ -255,8 +264,16 @@ def run_ours(args):
         if buckets is not None:
             buckets.allreduce(check_missing=False)
         l0 = _lib.launch_count()
-        with torch.cuda.graph(graph_b, pool=graph_a.pool()):
-            opt.step()
+        if bucket_opts is not None:
+            graph_bs = []
+            for o in bucket_opts:
+                gb_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb_, pool=graph_a.pool()):
+                    o.step()
+                graph_bs.append(gb_)
+        else:
+            with torch.cuda.graph(graph_b, pool=graph_a.pool()):
+                opt.step()
         launches_opt = _lib.launch_count() - l0
 
     def step(x):
@@ -268,6 +285,12 @@ def run_ours(args):
         if graph_a2 is not None:
             buckets.allreduce_subset(early)      # overlaps the encoder-conv backward below
             graph_a2.replay()
+        if bucket_opts is not None:
+            buckets.allreduce_subset(range(len(buckets.buckets)))      # all buckets queued on NCCL's stream, in order
+            for bi, gb_ in enumerate(graph_bs):
+                buckets.wait_bucket(bi)                                 # update of bucket bi overlaps the all-reduce of bi+1
+                gb_.replay()
+            return static_loss
         if buckets is not None:
             buckets.allreduce(check_missing=False)
         graph_b.replay()
@@ -459,6 +482,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--extra-warmup", type=int, default=60, help="additional untimed steps so clocks ramp up and the sampler is live")
     ap.add_argument("--torch-optim", action="store_true", help="use torch.optim.RMSprop instead of the fused multi-tensor kernel")
+    ap.add_argument("--no-bucket-pipeline", action="store_true", help="data parallel: one optimiser launch after all all-reduces")
     ap.add_argument("--split-backward", action="store_true",
                     help="data parallel: cut the backward graph at the encoder conv stack and run the all-reduce of the decoder/fc buckets "
                          "next to the conv-stack backward (measured at 2 GPUs: no gain, the persistent GEMM kernels leave NCCL no SMs)")

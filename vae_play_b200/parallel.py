@@ -112,6 +112,14 @@ class GradBuckets:
             if b["handle"] is None:
                 b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
+    def wait_bucket(self, bi):
+        """Make the current stream wait for bucket ``bi``'s all-reduce (issued by ``allreduce_subset``)."""
+        b = self.buckets[bi]
+        if b["handle"] is not None:
+            b["handle"].wait()
+            b["handle"] = None
+        b["ready"] = 0
+
     def buckets_within(self, params):
         """Indices of the buckets all of whose parameters are in ``params``."""
         ids = {id(p) for p in params}
