@@ -803,3 +803,39 @@ def test_two_stage_backward_matches_single(vp):
     loss.backward()
     for a, p in zip(staged, params):
         assert rel_l2(a, npy(p.grad)) < 1e-4      # same kernels on the same saved activations; only the order of fp32 atomics differs
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_discriminator_golden(vp, prec):
+    """VAE-GAN Discriminator (models/networks.py:151-195, config 4): 'REC' features, 'GAN' probabilities and parameter
+    gradients against the fixture written by oracle/gen_golden_disc.py from the unmodified reference in float64."""
+    import os
+    from oracle.gen_golden_disc import digest, synth_disc_inputs, synth_disc_params
+    from vae_play_b200.models.networks import Discriminator
+    want = np.load(os.path.join(os.path.dirname(__file__), "golden", "disc64_b2.npz"))
+    vp.set_precision(prec)
+    vp.set_engine("auto")
+    try:
+        d = Discriminator(channel_in=1, recon_level=3, iter_level=3)
+        P = synth_disc_params(0)
+        d.load_state_dict({k: torch.from_numpy(v) for k, v in P.items()}, strict=False)
+        d = d.cuda().train()
+        xs, probe = synth_disc_inputs(0)
+        xt = [torch.from_numpy(x).cuda() for x in xs]
+        rec = d(*xt, "REC")
+        assert tuple(rec.shape) == tuple(want["rec_shape"])
+        d.zero_grad()
+        gan = d(*xt, "GAN")
+        (gan * torch.from_numpy(probe).cuda()).sum().backward()
+        tol = 2e-5 if prec == "fp32" else 2.5e-2
+        close(digest(npy(rec))[3:], want["rec_digest"][3:], tol, "REC features (strided samples)")
+        close(digest(npy(rec))[1:2], want["rec_digest"][1:2], tol, "REC features (l2)")
+        close(npy(gan), want["gan"], tol, "GAN probabilities")
+        if prec == "fp32":
+            close(digest(npy(d.conv[0][0].weight.grad))[3:], want["grad_conv0"][3:], 2e-4, "grad conv.0")
+            close(digest(npy(d.conv[2].conv.weight.grad))[3:], want["grad_conv2"][3:], 2e-4, "grad conv.2")
+            close(npy(d.fc[3].weight.grad), want["grad_fc3"], 2e-4, "grad fc.3")
+        else:
+            assert rel_l2(npy(d.fc[3].weight.grad), want["grad_fc3"]) < 0.1
+    finally:
+        vp.set_precision("bf16")

@@ -436,11 +436,17 @@ class _FusedLayerFn(torch.autograd.Function):
             rows = n * h * w
             sums = None
             if a.dtype != dt:
-                # fp32 output of a bf16 layer (mu/logvar heads): bring the gradient to the activation dtype
-                d_in = torch.empty(a.shape, dtype=dt, device=dev)
-                _lib.call("vp_cast", _ptr(da), _code(da.dtype), _ptr(d_in), _code(dt), da.numel(), _stream())
+                # fp32 output of a bf16 layer (mu/logvar heads, the discriminator's sigmoid score): the activation
+                # backward runs in fp32 on the fp32 output, then the gradient is brought to the activation dtype
+                d32 = da if da.dtype == torch.float32 else da.float()
                 if act not in (None, "none"):
-                    raise _lib.VaePlayError("fp32-output layers must have no activation")
+                    dy32 = torch.empty_like(a)
+                    sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+                    _lib.call("vp_norm_bwd_reduce", _ptr(a), _ptr(d32), None, None, None, None, _ptr(sums), _ptr(dy32), F32,
+                              1, rows, c, ACT[act] | 16, float(slope), _stream())
+                    d32 = dy32
+                d_in = torch.empty(a.shape, dtype=dt, device=dev)
+                _lib.call("vp_cast", _ptr(d32), F32, _ptr(d_in), _code(dt), d32.numel(), _stream())
                 dy = d_in
             elif act in (None, "none"):
                 dy = da
