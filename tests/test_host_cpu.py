@@ -125,3 +125,19 @@ def test_philox_policy_matches_oracle():
     from vae_play_b200.functional import philox_policy
     for n in (1, 255, 256, 32768, 303104, 303105, 5_000_000):
         assert philox_policy(n, 148) == philox.aten_normal_policy(n, 148)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` (the reference's CPU path on the host cores) prints ONE JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-batch", "4"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "train_images_per_sec" and line["unit"] == "images/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
