@@ -88,7 +88,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // bf16 elements = 128 bytes = one swizzle row
-constexpr int kThreads = 192;          // wgrad kernel: TMA, MMA, 4 epilogue warps
 constexpr int kFwdThreads = 224;       // fwd/dgrad kernel: + a second TMA producer warp (B operand)
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
