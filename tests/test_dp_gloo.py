@@ -52,6 +52,27 @@ def _worker(rank, world, port, q):
         gs = torch.autograd.grad(tot, params)
         outs.append(gs)
     ok = all(torch.allclose(a, b, atol=1e-5) for ra, rb in zip(res, outs) for a, b in zip(ra, rb))
+    # every slot starts 16-byte aligned (vector reductions of the weight-gradient kernels), whatever the parameter sizes
+    ok = ok and all(gb.slot[id(p)][2] % 4 == 0 for p in params)
+    # the pipelined exchange of bench.py: all buckets queued at once, consumed one by one (update of bucket i while
+    # bucket i+1 is still being reduced); result identical to allreduce()
+    torch.manual_seed(500 + rank)
+    x = torch.randn(4, 7)
+    net.zero_grad(set_to_none=True)
+    y = net(x)
+    (y.pow(2).mean() / world + y.sum()).backward()
+    local = [p.grad.clone() for p in params]
+    early = gb.buckets_within(params[2:])               # buckets made only of the later layers' parameters
+    ok = ok and len(early) >= 1 and len(early) < len(gb.buckets)
+    gb.allreduce_subset(early)
+    gb.allreduce_subset(range(len(gb.buckets)))         # the rest; already-issued buckets are not issued twice
+    for bi in range(len(gb.buckets)):
+        gb.wait_bucket(bi)
+    summed = [g.clone() for g in local]
+    for g in summed:
+        dist.all_reduce(g)
+    ok = ok and all(torch.allclose(p.grad, g, atol=1e-6) for p, g in zip(params, summed))
+    ok = ok and all(b["handle"] is None and b["ready"] == 0 for b in gb.buckets)
     q.put((rank, ok))
     gb.remove()
     dist.destroy_process_group()
