@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VP_ABI_VERSION 1
+#define VP_ABI_VERSION 2
 
 enum { VP_F32 = 0, VP_BF16 = 1 };
 enum { VP_ACT_NONE = 0, VP_ACT_RELU = 1, VP_ACT_LRELU = 2, VP_ACT_TANH = 3, VP_ACT_SIGMOID = 4 };
@@ -63,8 +63,9 @@ int vp_abi_version(void);
 int vp_device_arch(void);
 
 /* Scratch memory for split-K partial sums of skinny contractions (the fc layers: a few output tiles, thousands of K
- * iterations): a DEVICE buffer owned by the caller, used stream-ordered (one stream at a time) by every later call until
- * replaced; without one such contractions run unsplit on a few SMs.  >= 4 * (rows * out_features) bytes to be useful. */
+ * iterations): a DEVICE buffer owned by the caller, registered for the CURRENT device (one buffer per device) and used
+ * stream-ordered (one stream at a time per device) by every later call on that device until replaced; without one such
+ * contractions run unsplit on a few SMs.  >= 4 * (rows * out_features) bytes to be useful. */
 int vp_set_workspace(void* ptr, size_t bytes);
 
 /* ---- weight layout ------------------------------------------------------------------------------- */
@@ -100,11 +101,12 @@ int vp_norm_stats(const void* x, double* sums, int dtype, int64_t groups, int64_
 /* From sums: mean/invstd (saved for backward, fp32 [groups][c]) and the fused affine
  * scale = gamma*invstd, shift = beta - mean*scale (fp32 [groups][c]; gamma/beta may be NULL = 1/0).
  * If running_mean/var are non-NULL they are blended in place with `momentum` (unbiased variance),
- * torch convention running = (1-momentum)*running + momentum*batch. */
+ * torch convention running = (1-momentum)*running + momentum*batch.  num_batches_tracked (nullable): the
+ * BatchNorm module's int64 device counter, incremented by one (saves the separate torch `+= 1` launch). */
 int vp_norm_finalize(const double* sums, const float* gamma, const float* beta,
                      float* running_mean, float* running_var, float momentum, float eps,
                      float* mean, float* invstd, float* scale, float* shift,
-                     int64_t groups, int64_t rows_per_group, int c, void* stream);
+                     int64_t groups, int64_t rows_per_group, int c, int64_t* num_batches_tracked, void* stream);
 /* a = act(x*scale + shift) (scale/shift may be NULL = identity; bias-free pointwise activation). */
 int vp_norm_apply_act(const void* x, const float* scale, const float* shift, void* a, int dtype,
                       int64_t groups, int64_t rows_per_group, int c, int act, float slope, void* stream);
@@ -125,7 +127,7 @@ int vp_norm_bwd_apply(const void* x, const void* da, const float* mean, const fl
  * (backward).  Same outputs as the vp_norm_* sequence; c a multiple of 4, tensors 16-byte aligned. */
 int vp_bn_rows_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float momentum, float eps, void* a, float* mean, float* invstd, float* scale, float* shift,
-                   int dtype, int64_t rows, int c, int act, float slope, void* stream);
+                   int dtype, int64_t rows, int c, int act, float slope, int64_t* num_batches_tracked, void* stream);
 int vp_bn_rows_bwd(const void* x, const void* da, const float* mean, const float* invstd, const float* scale,
                    const float* shift, void* dx, float* dgamma, float* dbeta, int dtype, int64_t rows, int c,
                    int act, float slope, void* stream);
@@ -204,7 +206,8 @@ int vp_conv_fwd_cl_stats(const VpConvGeom* g, const void* x, const void* w_cl, v
 /* vp_norm_finalize from such partial sums (added in double, fixed order) */
 int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, float momentum, float eps,
-                           float* mean, float* invstd, float* scale, float* shift, int64_t rows, int c, void* stream);
+                           float* mean, float* invstd, float* scale, float* shift, int64_t rows, int c,
+                           int64_t* num_batches_tracked, void* stream);
 int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int prezeroed, void* stream);
 /* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
 int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
@@ -239,8 +242,6 @@ int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const*
                            const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay,
                            int zero_grads, void* stream);
 
-/* debug: tcgen05 operand-window probe (tools/probe_umma.py); x bf16 [256][64], ident bf16 [64][64], out fp32 [128][64] */
-int vp_debug_umma_probe(const void* x, const void* ident, float* out, int off_rows, int sbo_rows, int base_offset, void* stream);
 
 /* number of kernels this library has launched in this process (the bench's gpu_launches claim) */
 uint64_t vp_launch_count(void);

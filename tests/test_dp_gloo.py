@@ -56,6 +56,7 @@ def _worker(rank, world, port, q):
     ok = ok and all(gb.slot[id(p)][2] % 4 == 0 for p in params)
     # the pipelined exchange of bench.py: all buckets queued at once, consumed one by one (update of bucket i while
     # bucket i+1 is still being reduced); result identical to allreduce()
+    gb.overlap = False          # graph-replay mode of bench.py: the hooks only place gradients, the caller issues the collectives
     torch.manual_seed(500 + rank)
     x = torch.randn(4, 7)
     net.zero_grad(set_to_none=True)
@@ -73,6 +74,40 @@ def _worker(rank, world, port, q):
         dist.all_reduce(g)
     ok = ok and all(torch.allclose(p.grad, g, atol=1e-6) for p, g in zip(params, summed))
     ok = ok and all(b["handle"] is None and b["ready"] == 0 for b in gb.buckets)
+    # several backward calls per step (reference train.py:68-73): all but the last inside no_sync(); with overlap on, a
+    # second synchronising backward must raise instead of reducing a bucket twice
+    gb.overlap = True
+    torch.manual_seed(700 + rank)
+    x = torch.randn(4, 7)
+    net.zero_grad(set_to_none=True)
+    y = net(x)
+    l1, l2 = y.pow(2).mean() / world, y.sum()
+    with gb.no_sync():
+        l1.backward(retain_graph=True)
+    l2.backward()
+    gb.allreduce()
+    got = [p.grad.clone() for p in params]
+    net.zero_grad(set_to_none=True)
+    with gb.no_sync():
+        (net(x).pow(2).mean() / world + net(x).sum()).backward()
+    want = [p.grad.clone() for p in params]
+    for g in want:
+        dist.all_reduce(g)
+    ok = ok and all(torch.allclose(a, b, atol=1e-5) for a, b in zip(got, want))
+    net.zero_grad(set_to_none=True)
+    y = net(x)
+    y.sum().backward(retain_graph=True)
+    raised = False
+    try:
+        y.pow(2).mean().backward()
+    except RuntimeError:
+        raised = True
+    ok = ok and raised
+    for b in gb.buckets:            # drain what the first backward launched
+        if b["handle"] is not None:
+            b["handle"].wait()
+            b["handle"] = None
+        b["ready"] = 0
     q.put((rank, ok))
     gb.remove()
     dist.destroy_process_group()

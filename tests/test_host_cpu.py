@@ -26,11 +26,48 @@ def test_library_builds_and_exports_every_header_symbol():
     assert len(names) >= 25
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vaeplay_b200.h but not exported"
-    # and the ctypes table covers exactly the header
+    # the ctypes table is generated from the header prototypes and covers exactly the header
     bound = set(_lib.SIGNATURES) | set(_lib.PLAIN)
     assert bound == set(names), (bound ^ set(names))
-    assert lib.vp_abi_version() == 1
+    assert lib.vp_abi_version() == _lib.ABI_VERSION == 2
     assert lib.vp_launch_count() == 0
+    # debug probes are not part of the release ABI
+    assert not any(n.startswith("vp_debug") for n in names)
+    assert not hasattr(lib, "vp_debug_umma_probe")
+
+
+def test_ctypes_signatures_follow_header_prototypes():
+    """Argument TYPES, not just names: the binding is derived from the prototypes, and a few hand-written expectations pin
+    the derivation itself (pointer / int64 / float / size_t / host out-parameter)."""
+    import ctypes as C
+    from vae_play_b200 import _lib
+    G, p, i, i64, u64, f = C.POINTER(_lib.VpConvGeom), C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float
+    expect = {
+        "vp_conv_fwd": [G, p, p, p, p, i, i, i, f, i, p],
+        "vp_pack_weight": [p, p, i, i, i, i, i64, i64, i64, p],
+        "vp_reparam_kl_fwd": [p, p, i64, p, u64, u64, p, i, p, i, p, p, i64, i, p],
+        "vp_set_workspace": [p, C.c_size_t],
+        "vp_conv_fwd_cl_stats": [G, p, p, p, p, i, C.POINTER(C.c_int), p],
+        "vp_axpy": [f, p, p, i64, p],
+        "vp_rmsprop_step_shadow": [p, p, p, p, p, i, f, f, f, f, i, p],
+    }
+    for name, want in expect.items():
+        assert _lib.SIGNATURES[name] == want, name
+    lib = _lib.load()
+    for name, args in _lib.SIGNATURES.items():
+        assert list(getattr(lib, name).argtypes) == args and getattr(lib, name).restype is C.c_int, name
+    # every prototype in the header has as many parameters as the parser found (no silently skipped declaration)
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "vaeplay_b200.h")).read(), flags=re.S)
+    for name, args in _lib.SIGNATURES.items():
+        m = re.search(name + r"\s*\(([^)]*)\)", src)
+        assert m and len([a for a in m.group(1).split(",") if a.strip() and a.strip() != "void"]) == len(args), name
+
+
+def test_stale_library_is_detected(tmp_path, monkeypatch):
+    from vae_play_b200 import build
+    assert not build.is_stale()
+    monkeypatch.setattr(build, "DIGEST", str(tmp_path / "none.sha256"))
+    assert build.is_stale()
 
 
 def test_no_cpu_path():

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libvaeplay_b200.so")
 F32, BF16 = 0, 1
 ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4}
 ENGINE_AUTO, ENGINE_SIMT, ENGINE_TC = 0, 1, 2
+ABI_VERSION = 2
 
 
 class VpConvGeom(C.Structure):
@@ -24,72 +25,70 @@ class VaePlayError(RuntimeError):
     pass
 
 
-_p = C.c_void_p
 _i = C.c_int
-_i64 = C.c_int64
 _u64 = C.c_uint64
-_f = C.c_float
 
-# name -> argtypes, exactly as declared in include/vaeplay_b200.h
-SIGNATURES = {
-    "vp_pack_weight": [_p, _p, _i, _i, _i, _i, _i64, _i64, _i64, _p],
-    "vp_unpack_wgrad": [_p, _p, _i, _i, _i, _i64, _i64, _i64, _p],
-    "vp_conv_fwd": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _i, _f, _i, _p],
-    "vp_conv_dgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _i, _i, _p],
-    "vp_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _i, _p],
-    "vp_norm_stats": [_p, _p, _i, _i64, _i64, _i, _p],
-    "vp_norm_finalize": [_p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i64, _i64, _i, _p],
-    "vp_norm_apply_act": [_p, _p, _p, _p, _i, _i64, _i64, _i, _i, _f, _p],
-    "vp_norm_bwd_reduce": [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i64, _i, _i, _f, _p],
-    "vp_norm_bwd_apply": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i64, _i, _i, _f, _p],
-    "vp_bn_rows_fwd": [_p, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _f, _p],
-    "vp_bn_rows_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _f, _p],
-    "vp_colsum": [_p, _p, _p, _i, _i64, _i, _p],
-    "vp_reparam_kl_fwd": [_p, _p, _i64, _p, _u64, _u64, _p, _i, _p, _i, _p, _p, _i64, _i, _p],
-    "vp_reparam_kl_bwd": [_p, _p, _i64, _p, _p, _i, _p, _p, _p, _i, _i64, _i64, _i, _p],
-    "vp_philox_normal": [_p, _i64, _u64, _u64, _p, _i, _p],
-    "vp_philox_advance": [_p, _u64, _p],
-    "vp_recon_loss_fwd": [_p, _p, _i64, _i, _p, _p, _p, _p],
-    "vp_recon_loss_bwd": [_p, _p, _i64, _i, _p, _p, _p],
-    "vp_bce_dice_fwd": [_p, _p, _i64, _i64, _f, _p, _p, _p, _p],
-    "vp_bce_dice_bwd": [_p, _p, _i64, _i64, _f, _p, _p, _p, _p],
-    "vp_nchw_to_nhwc": [_p, _p, _i, _i, _i, _i, _i, _p],
-    "vp_nhwc_to_nchw": [_p, _p, _i, _i, _i, _i, _i, _p],
-    "vp_cast": [_p, _i, _p, _i, _i64, _p],
-    "vp_axpy": [_f, _p, _p, _i64, _p],
-    "vp_sum_into": [_p, _i64, _f, _p, _p],
-    "vp_fill_from": [_p, _f, _p, _i64, _p],
-    "vp_debug_umma_probe": [_p, _p, _p, _i, _i, _i, _p],
-    "vp_set_workspace": [_p, C.c_size_t],
-    "vp_conv_fwd_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
-    "vp_conv_fwd_cl_stats": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, C.POINTER(C.c_int), _p],
-    "vp_thin_conv_fwd_stats": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, C.POINTER(C.c_int), _p],
-    "vp_norm_finalize_parts": [_p, _i, _p, _p, _p, _p, _f, _f, _p, _p, _p, _p, _i64, _i, _p],
-    "vp_conv_dgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
-    "vp_conv_wgrad_cl": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
-    "vp_transpose_bt": [_p, _p, _i, _i, _i, _i, _p],
-    "vp_thin_conv_fwd": [C.POINTER(VpConvGeom), _p, _p, _p, _p, _i, _i, _f, _p],
-    "vp_thin_conv_dgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
-    "vp_thin_conv_wgrad": [C.POINTER(VpConvGeom), _p, _p, _p, _i, _p],
-    "vp_rmsprop_step": [_p, _p, _p, _p, _i, _f, _f, _f, _f, _p],
-    "vp_rmsprop_step_shadow": [_p, _p, _p, _p, _p, _i, _f, _f, _f, _f, _i, _p],
-}
-PLAIN = {"vp_last_error": (C.c_char_p, []), "vp_abi_version": (_i, []), "vp_device_arch": (_i, []),
-         "vp_launch_count": (_u64, [])}
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vaeplay_b200.h")
+
+_CTYPE = {"int": C.c_int, "int32_t": C.c_int32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "size_t": C.c_size_t,
+          "float": C.c_float, "double": C.c_double, "unsigned int": C.c_uint, "unsigned": C.c_uint}
+
+
+def _arg_ctype(decl: str):
+    """ctypes type of one C parameter declaration of include/vaeplay_b200.h."""
+    decl = decl.strip()
+    if "*" in decl:
+        base = decl[: decl.index("*")].replace("const", "").strip()
+        if base == "VpConvGeom":
+            return C.POINTER(VpConvGeom)
+        if base == "int" and decl.count("*") == 1:
+            return C.POINTER(C.c_int)          # host out-parameter (int* nparts)
+        return C.c_void_p                      # device / host arrays passed as raw addresses
+    words = decl.replace("const", "").split()
+    base = " ".join(words[:-1]) if len(words) > 1 else words[0]
+    if base not in _CTYPE:
+        raise VaePlayError(f"include/vaeplay_b200.h: unknown parameter type in '{decl}'")
+    return _CTYPE[base]
+
+
+def parse_header(path: str = HEADER_PATH):
+    """name -> (restype, [argtypes]) for every prototype the header declares: the ctypes table is GENERATED from the
+    header, so an ABI change cannot drift silently past the binding."""
+    import re
+    src = open(path).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    out = {}
+    for m in re.finditer(r"(const\s+char\s*\*|uint64_t|int)\s+(vp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        res = C.c_char_p if "char" in ret else (_u64 if ret == "uint64_t" else _i)
+        out[name] = (res, [] if args in ("", "void") else [_arg_ctype(a) for a in args.split(",")])
+    return out
+
+
+_PROTOS = parse_header()
+PLAIN = {k: v for k, v in _PROTOS.items() if k in ("vp_last_error", "vp_abi_version", "vp_device_arch", "vp_launch_count")}
+SIGNATURES = {k: v[1] for k, v in _PROTOS.items() if k not in PLAIN}     # compute entry points: int return code
 
 _lib = None
 
 
 def load(build_if_missing: bool = True):
-    """Load (building first if needed) the CUDA library.  Raises if it cannot be had."""
+    """Load the CUDA library, (re)building it first when it is missing or older than its sources (content hash, see
+    build.sources_digest).  Raises if it cannot be had: there is no CPU fallback."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if not build_if_missing:
+    from . import build as _build
+    if not os.path.exists(LIB_PATH) or _build.is_stale():
+        if not build_if_missing and not os.path.exists(LIB_PATH):
             raise VaePlayError(f"{LIB_PATH} is missing; run `python -m vae_play_b200.build`")
-        from . import build as _build
-        _build.build()
+        try:
+            _build.build()
+        except Exception as e:       # no nvcc on this machine, ...
+            if not os.path.exists(LIB_PATH):
+                raise VaePlayError(f"cannot build {LIB_PATH}: {e}") from e
+            raise VaePlayError(f"{LIB_PATH} is older than its sources and cannot be rebuilt: {e}") from e
     lib = C.CDLL(LIB_PATH)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
@@ -99,7 +98,7 @@ def load(build_if_missing: bool = True):
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = res
-    if lib.vp_abi_version() != 1:
+    if lib.vp_abi_version() != ABI_VERSION:
         raise VaePlayError("libvaeplay_b200.so ABI version mismatch; rebuild with `python -m vae_play_b200.build --force`")
     _lib = lib
     return lib
@@ -109,7 +108,7 @@ _workspace = {}
 
 
 def ensure_workspace(device, nbytes: int = 32 << 20):
-    """Register a per-device scratch buffer for split-K partial sums (vp_set_workspace)."""
+    """Register a per-device scratch buffer for split-K partial sums (vp_set_workspace keeps one pointer per device)."""
     import torch
     key = (device.type, device.index)
     if key not in _workspace:

@@ -7,6 +7,7 @@ vae_play_b200/lib/libvaeplay_b200.so.  The .so is git-ignored but travels to the
 """
 from __future__ import annotations
 
+import hashlib
 import os
 import shutil
 import subprocess
@@ -18,6 +19,7 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libvaeplay_b200.so")
 HEADER = os.path.join(os.path.dirname(HERE), "include", "vaeplay_b200.h")
+DIGEST = os.path.join(LIBDIR, "sources.sha256")     # digest of the sources the .so was built from (travels with it)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -32,6 +34,32 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found (set NVCC or install the CUDA toolkit)")
 
 
+def _source_files():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))) + [HEADER]
+
+
+def sources_digest() -> str:
+    """sha256 over the CUDA sources + the public header + the compile flags.  Content-based, so that it survives copies
+    that do not preserve mtimes (the snapshot pushed to the GPU box)."""
+    h = hashlib.sha256()
+    for f in _source_files():
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    h.update(" ".join(_flags()).encode())
+    return h.hexdigest()
+
+
+def is_stale() -> bool:
+    """True when the library is missing or was built from other sources than the ones in the tree."""
+    if not os.path.exists(LIB) or not os.path.exists(DIGEST):
+        return True
+    return open(DIGEST).read().strip() != sources_digest()
+
+
+def _flags():
+    return NVCC_FLAGS + (["-DVP_DEBUG_PROBES"] if os.environ.get("VP_DEBUG_PROBES") == "1" else [])
+
+
 def _stale(target: str, deps) -> bool:
     if not os.path.exists(target):
         return True
@@ -41,6 +69,12 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
+    digest = sources_digest()
+    if not force and not is_stale():
+        return LIB
+    flagfile = os.path.join(LIBDIR, "flags.txt")
+    if not os.path.exists(flagfile) or open(flagfile).read() != " ".join(_flags()):
+        force = True                     # other compile flags (debug <-> release): every object is stale
     nvcc = _nvcc()
     sources = sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + [HEADER]
@@ -50,7 +84,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         obj = os.path.join(OBJDIR, src[:-3] + ".o")
         objs.append(obj)
         if force or _stale(obj, [os.path.join(CSRC, src)] + headers):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [nvcc, *_flags(), "-c", os.path.join(CSRC, src), "-o", obj]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")
@@ -71,6 +105,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stdout)
+    with open(os.path.join(LIBDIR, "flags.txt"), "w") as f:
+        f.write(" ".join(_flags()))
+    with open(DIGEST, "w") as f:
+        f.write(digest + "\n")
     return LIB
 
 

@@ -1,6 +1,7 @@
 // extern "C" entry points of libvaeplay_b200: geometry -> tap-GEMM problems -> engine dispatch.
 #include <atomic>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -17,6 +18,11 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("VP_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v == 1;
+}
 
 namespace {
 

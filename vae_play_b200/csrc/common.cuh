@@ -4,6 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/vaeplay_b200.h"
 
@@ -13,6 +16,33 @@ typedef __nv_bfloat16 bf16;
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+
+// ---- programmatic dependent launch ------------------------------------------------------------------------------------
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled while
+// the previous kernel of the stream is still draining, run their prologue (shared-memory carve-up, mbarrier init, TMEM
+// allocation, tensor-map prefetch) and then block in pdl_wait() until the previous grid has completed and flushed.  Inside a
+// captured CUDA graph the launches become programmatic dependency edges.  RULE: a kernel launched through launch_k() must
+// execute pdl_wait() in every thread before its first global-memory access (reads of what the predecessor wrote AND writes
+// to what it may still read); pdl_trigger() right after it lets the successor pre-launch in turn (at most one kernel ahead).
+// VP_PDL=0 in the environment launches everything fully serialised (A/B measurements, debugging).
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at;
+    memset(&at, 0, sizeof(at));
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 #define VP_CHECK_ARG(cond, ...)                  \
     do {                                         \

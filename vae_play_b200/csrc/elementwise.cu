@@ -53,12 +53,14 @@ __host__ __device__ inline int64_t aten_threads(int64_t n, int num_sms) {
 
 __global__ void philox_normal_kernel(float* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset,
                                      const uint64_t* __restrict__ offset_dev, int64_t nthreads) {
+    pdl_sync();
     if (offset_dev) offset += *offset_dev;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = aten_normal_element(i, nthreads, seed, offset);
 }
 
-__global__ void philox_advance_kernel(uint64_t* o, uint64_t inc) { *o += inc; }
+__global__ void philox_advance_kernel(uint64_t* o, uint64_t inc) {
+    pdl_sync(); *o += inc; }
 
 // one warp per row: z = eps*exp(.5*lv)+mu ; kl_row = -0.5*sum(-exp(lv) - mu^2 + lv + 1)
 template <typename TZ>
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(256) reparam_kl_fwd_kernel(const float* __rest
                                                              const uint64_t* __restrict__ offset_dev, int64_t nthreads,
                                                              TZ* __restrict__ z, float* __restrict__ eps_out,
                                                              float* __restrict__ kl, int64_t rows, int zdim) {
+    pdl_sync();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(256) reparam_kl_bwd_kernel(const float* __rest
                                                              const TZ* __restrict__ dz, const float* __restrict__ dkl,
                                                              TO* __restrict__ dmu, TO* __restrict__ dlv,
                                                              int64_t ldo, int64_t rows, int zdim) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * zdim) return;
     const int64_t row = i / zdim;
@@ -120,6 +124,7 @@ __device__ __forceinline__ double block_sum_double(double v) {
 __global__ void __launch_bounds__(256) recon_fwd_kernel(const float* __restrict__ x, const float* __restrict__ xt,
                                                         int64_t n, int kind, double* acc, unsigned int* counter,
                                                         float* loss) {
+    pdl_sync();
     float s = 0.f;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
@@ -152,6 +157,7 @@ __global__ void __launch_bounds__(256) recon_fwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) recon_bwd_kernel(const float* __restrict__ x, const float* __restrict__ xt,
                                                         int64_t n, int kind, const float* __restrict__ gscale,
                                                         float* __restrict__ dxt) {
+    pdl_sync();
     const float g = (gscale ? *gscale : 1.f) / (float)n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float d = xt[i] - x[i];
@@ -163,6 +169,7 @@ __global__ void __launch_bounds__(256) recon_bwd_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) bce_dice_fwd_kernel(const float* __restrict__ z, const float* __restrict__ t,
                                                            int64_t rows, int64_t per, float wbce, double* acc,
                                                            unsigned int* counter, float* loss) {
+    pdl_sync();
     const int64_t row = blockIdx.y;
     float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per; i += (int64_t)gridDim.x * blockDim.x) {
@@ -199,6 +206,7 @@ __global__ void __launch_bounds__(256) bce_dice_bwd_kernel(const float* __restri
                                                            int64_t rows, int64_t per, float wbce,
                                                            const double* __restrict__ acc, const float* __restrict__ gscale,
                                                            float* __restrict__ dz) {
+    pdl_sync();
     const int64_t row = blockIdx.y;
     const float g = gscale ? *gscale : 1.f;
     const double inter = acc[row * 4 + 1], den = acc[row * 4 + 2] + acc[row * 4 + 3] + 1.0;
@@ -216,6 +224,7 @@ __global__ void __launch_bounds__(256) bce_dice_bwd_kernel(const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ x, T* __restrict__ y, int n, int c,
                                                            int64_t hw) {
+    pdl_sync();
     // y[(n*hw + p)*c + ch] = x[(n*c + ch)*hw + p]; tile-transpose through shared memory
     __shared__ float tile[32][33];
     const int img = blockIdx.z;
@@ -238,6 +247,7 @@ __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restri
 template <typename T>
 __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__ x, float* __restrict__ y, int n, int c,
                                                            int64_t hw) {
+    pdl_sync();
     __shared__ float tile[32][33];
     const int img = blockIdx.z;
     const int64_t p0 = (int64_t)blockIdx.x * 32;
@@ -258,11 +268,13 @@ __global__ void __launch_bounds__(256) nhwc_to_nchw_kernel(const T* __restrict__
 
 template <typename TS, typename TD>
 __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD* __restrict__ d, int64_t n) {
+    pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         Cvt<TD>::st(d + i, Cvt<TS>::ld(s + i));
 }
 
 __global__ void __launch_bounds__(256) axpy_kernel(float alpha, const float* __restrict__ a, float* __restrict__ sum, int64_t n) {
+    pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         sum[i] = fmaf(alpha, a[i], sum[i]);
 }
@@ -271,6 +283,7 @@ __global__ void __launch_bounds__(256) axpy_kernel(float alpha, const float* __r
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N,
                                                           int K, int64_t sn, int64_t sk, int64_t st) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
@@ -284,6 +297,7 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __restrict__ w, T* __restrict__ wp, int taps, int N,
                                                                 int K, int64_t sn, int64_t sk) {
+    pdl_sync();
     extern __shared__ float tile[];   // [32][taps+1]
     const int n = blockIdx.y, k0 = blockIdx.x * 32;
     const int ld = taps + 1;
@@ -300,6 +314,7 @@ __global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __r
 
 __global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int taps,
                                                                  int N, int K, int64_t sn, int64_t sk) {
+    pdl_sync();
     extern __shared__ float tile[];
     const int n = blockIdx.y, k0 = blockIdx.x * 32;
     const int ld = taps + 1;
@@ -316,6 +331,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_tiled_kernel(const float* __
 
 __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int taps,
                                                            int N, int K, int64_t sn, int64_t sk, int64_t st) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)N * K) return;
     const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
@@ -324,6 +340,7 @@ __global__ void __launch_bounds__(256) unpack_wgrad_kernel(const float* __restri
 }
 
 __global__ void __launch_bounds__(256) sum_into_kernel(const float* __restrict__ v, int64_t n, float scale, float* acc) {
+    pdl_sync();
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += (double)v[i];
     s = block_sum_double(s);
@@ -331,6 +348,7 @@ __global__ void __launch_bounds__(256) sum_into_kernel(const float* __restrict__
 }
 
 __global__ void __launch_bounds__(256) fill_from_kernel(const float* __restrict__ g, float scale, float* __restrict__ out, int64_t n) {
+    pdl_sync();
     const float v = scale * (g ? *g : 1.f);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
 }
@@ -352,14 +370,14 @@ extern "C" int vp_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t o
                                 int num_sms, void* stream) {
     VP_CHECK_ARG(out && n >= 0 && num_sms > 0, "vp_philox_normal: bad arguments");
     if (n == 0) return VP_OK;
-    philox_normal_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(out, n, seed, offset, offset_dev, aten_threads(n, num_sms));
+    launch_k(philox_normal_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, out, n, seed, offset, offset_dev, aten_threads(n, num_sms));
     VP_CHECK_LAUNCH("vp_philox_normal");
     return VP_OK;
 }
 
 extern "C" int vp_philox_advance(uint64_t* offset_dev, uint64_t inc, void* stream) {
     VP_CHECK_ARG(offset_dev, "vp_philox_advance: null");
-    philox_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(offset_dev, inc);
+    launch_k(philox_advance_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, offset_dev, inc);
     VP_CHECK_LAUNCH("vp_philox_advance");
     return VP_OK;
 }
@@ -372,9 +390,9 @@ extern "C" int vp_reparam_kl_fwd(const float* mu, const float* logvar, int64_t l
     const int64_t nthreads = aten_threads(rows * zdim, num_sms);
     const unsigned grid = (unsigned)((rows + 7) / 8);
     if (z_dtype == VP_F32)
-        reparam_kl_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(mu, logvar, ld, eps_in, seed, offset, offset_dev, nthreads, (float*)z, eps_out, kl, rows, zdim);
+        launch_k(reparam_kl_fwd_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, mu, logvar, ld, eps_in, seed, offset, offset_dev, nthreads, (float*)z, eps_out, kl, rows, zdim);
     else
-        reparam_kl_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(mu, logvar, ld, eps_in, seed, offset, offset_dev, nthreads, (bf16*)z, eps_out, kl, rows, zdim);
+        launch_k(reparam_kl_fwd_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, mu, logvar, ld, eps_in, seed, offset, offset_dev, nthreads, (bf16*)z, eps_out, kl, rows, zdim);
     VP_CHECK_LAUNCH("vp_reparam_kl_fwd");
     return VP_OK;
 }
@@ -387,13 +405,13 @@ extern "C" int vp_reparam_kl_bwd(const float* mu, const float* logvar, int64_t l
     const unsigned grid = (unsigned)((rows * zdim + 255) / 256);
     cudaStream_t s = (cudaStream_t)stream;
     if (dz_dtype == VP_F32 && out_dtype == VP_F32)
-        reparam_kl_bwd_kernel<float, float><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const float*)dz, dkl, (float*)dmu, (float*)dlogvar, ld_out, rows, zdim);
+        launch_k(reparam_kl_bwd_kernel<float, float>, dim3(grid), dim3(256), 0, s, mu, logvar, ld, eps, (const float*)dz, dkl, (float*)dmu, (float*)dlogvar, ld_out, rows, zdim);
     else if (dz_dtype == VP_F32)
-        reparam_kl_bwd_kernel<float, bf16><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const float*)dz, dkl, (bf16*)dmu, (bf16*)dlogvar, ld_out, rows, zdim);
+        launch_k(reparam_kl_bwd_kernel<float, bf16>, dim3(grid), dim3(256), 0, s, mu, logvar, ld, eps, (const float*)dz, dkl, (bf16*)dmu, (bf16*)dlogvar, ld_out, rows, zdim);
     else if (out_dtype == VP_F32)
-        reparam_kl_bwd_kernel<bf16, float><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const bf16*)dz, dkl, (float*)dmu, (float*)dlogvar, ld_out, rows, zdim);
+        launch_k(reparam_kl_bwd_kernel<bf16, float>, dim3(grid), dim3(256), 0, s, mu, logvar, ld, eps, (const bf16*)dz, dkl, (float*)dmu, (float*)dlogvar, ld_out, rows, zdim);
     else
-        reparam_kl_bwd_kernel<bf16, bf16><<<grid, 256, 0, s>>>(mu, logvar, ld, eps, (const bf16*)dz, dkl, (bf16*)dmu, (bf16*)dlogvar, ld_out, rows, zdim);
+        launch_k(reparam_kl_bwd_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, s, mu, logvar, ld, eps, (const bf16*)dz, dkl, (bf16*)dmu, (bf16*)dlogvar, ld_out, rows, zdim);
     VP_CHECK_LAUNCH("vp_reparam_kl_bwd");
     return VP_OK;
 }
@@ -401,7 +419,7 @@ extern "C" int vp_reparam_kl_bwd(const float* mu, const float* logvar, int64_t l
 extern "C" int vp_recon_loss_fwd(const float* x, const float* xt, int64_t n, int kind, double* loss_acc,
                                  unsigned int* counter, float* loss, void* stream) {
     VP_CHECK_ARG(x && xt && loss_acc && counter && loss && n > 0 && (kind == 0 || kind == 1), "vp_recon_loss_fwd: bad arguments");
-    recon_fwd_kernel<<<grid_for(n, 4), 256, 0, (cudaStream_t)stream>>>(x, xt, n, kind, loss_acc, counter, loss);
+    launch_k(recon_fwd_kernel, dim3(grid_for(n, 4)), dim3(256), 0, (cudaStream_t)stream, x, xt, n, kind, loss_acc, counter, loss);
     VP_CHECK_LAUNCH("vp_recon_loss_fwd");
     return VP_OK;
 }
@@ -409,7 +427,7 @@ extern "C" int vp_recon_loss_fwd(const float* x, const float* xt, int64_t n, int
 extern "C" int vp_recon_loss_bwd(const float* x, const float* xt, int64_t n, int kind, const float* gscale, float* dxt,
                                  void* stream) {
     VP_CHECK_ARG(x && xt && dxt && n > 0 && (kind == 0 || kind == 1), "vp_recon_loss_bwd: bad arguments");
-    recon_bwd_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, xt, n, kind, gscale, dxt);
+    launch_k(recon_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, x, xt, n, kind, gscale, dxt);
     VP_CHECK_LAUNCH("vp_recon_loss_bwd");
     return VP_OK;
 }
@@ -419,7 +437,7 @@ extern "C" int vp_bce_dice_fwd(const float* logits, const float* target, int64_t
     VP_CHECK_ARG(logits && target && acc && counter && loss && rows > 0 && rows <= 65535 && per > 0, "vp_bce_dice_fwd: bad arguments");
     dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), (unsigned)rows);
     cudaMemsetAsync(acc, 0, sizeof(double) * 4 * rows, (cudaStream_t)stream);
-    bce_dice_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, rows, per, bce_weight, acc, counter, loss);
+    launch_k(bce_dice_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, logits, target, rows, per, bce_weight, acc, counter, loss);
     VP_CHECK_LAUNCH("vp_bce_dice_fwd");
     return VP_OK;
 }
@@ -428,7 +446,7 @@ extern "C" int vp_bce_dice_bwd(const float* logits, const float* target, int64_t
                                const double* acc, const float* gscale, float* dlogits, void* stream) {
     VP_CHECK_ARG(logits && target && acc && dlogits && rows > 0 && rows <= 65535 && per > 0, "vp_bce_dice_bwd: bad arguments");
     dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), (unsigned)rows);
-    bce_dice_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, target, rows, per, bce_weight, acc, gscale, dlogits);
+    launch_k(bce_dice_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, logits, target, rows, per, bce_weight, acc, gscale, dlogits);
     VP_CHECK_LAUNCH("vp_bce_dice_bwd");
     return VP_OK;
 }
@@ -437,8 +455,8 @@ extern "C" int vp_nchw_to_nhwc(const float* x, void* y, int dtype, int n, int c,
     VP_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "vp_nchw_to_nhwc: bad arguments");
     const int64_t hw = (int64_t)h * w;
     dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, n);
-    if (dtype == VP_F32) nchw_to_nhwc_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (float*)y, n, c, hw);
-    else nchw_to_nhwc_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n, c, hw);
+    if (dtype == VP_F32) launch_k(nchw_to_nhwc_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, (float*)y, n, c, hw);
+    else launch_k(nchw_to_nhwc_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)y, n, c, hw);
     VP_CHECK_LAUNCH("vp_nchw_to_nhwc");
     return VP_OK;
 }
@@ -447,8 +465,8 @@ extern "C" int vp_nhwc_to_nchw(const void* x, float* y, int dtype, int n, int c,
     VP_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "vp_nhwc_to_nchw: bad arguments");
     const int64_t hw = (int64_t)h * w;
     dim3 grid((unsigned)((hw + 31) / 32), (c + 31) / 32, n);
-    if (dtype == VP_F32) nhwc_to_nchw_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, y, n, c, hw);
-    else nhwc_to_nchw_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n, c, hw);
+    if (dtype == VP_F32) launch_k(nhwc_to_nchw_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, y, n, c, hw);
+    else launch_k(nhwc_to_nchw_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, y, n, c, hw);
     VP_CHECK_LAUNCH("vp_nhwc_to_nchw");
     return VP_OK;
 }
@@ -458,10 +476,10 @@ extern "C" int vp_cast(const void* src, int sd, void* dst, int dd, int64_t n, vo
     if (n == 0) return VP_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned g = grid_for(n);
-    if (sd == VP_F32 && dd == VP_BF16) cast_kernel<float, bf16><<<g, 256, 0, s>>>((const float*)src, (bf16*)dst, n);
-    else if (sd == VP_BF16 && dd == VP_F32) cast_kernel<bf16, float><<<g, 256, 0, s>>>((const bf16*)src, (float*)dst, n);
-    else if (sd == VP_F32 && dd == VP_F32) cast_kernel<float, float><<<g, 256, 0, s>>>((const float*)src, (float*)dst, n);
-    else cast_kernel<bf16, bf16><<<g, 256, 0, s>>>((const bf16*)src, (bf16*)dst, n);
+    if (sd == VP_F32 && dd == VP_BF16) launch_k(cast_kernel<float, bf16>, dim3(g), dim3(256), 0, s, (const float*)src, (bf16*)dst, n);
+    else if (sd == VP_BF16 && dd == VP_F32) launch_k(cast_kernel<bf16, float>, dim3(g), dim3(256), 0, s, (const bf16*)src, (float*)dst, n);
+    else if (sd == VP_F32 && dd == VP_F32) launch_k(cast_kernel<float, float>, dim3(g), dim3(256), 0, s, (const float*)src, (float*)dst, n);
+    else launch_k(cast_kernel<bf16, bf16>, dim3(g), dim3(256), 0, s, (const bf16*)src, (bf16*)dst, n);
     VP_CHECK_LAUNCH("vp_cast");
     return VP_OK;
 }
@@ -469,7 +487,7 @@ extern "C" int vp_cast(const void* src, int sd, void* dst, int dd, int64_t n, vo
 extern "C" int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream) {
     VP_CHECK_ARG(a && sum && n >= 0, "vp_axpy: bad arguments");
     if (n == 0) return VP_OK;
-    axpy_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(alpha, a, sum, n);
+    launch_k(axpy_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, alpha, a, sum, n);
     VP_CHECK_LAUNCH("vp_axpy");
     return VP_OK;
 }
@@ -480,14 +498,14 @@ extern "C" int vp_pack_weight(const float* w, void* wp, int dtype, int taps, int
     if (st == 1 && taps >= 4 && k >= 32 && n <= 65535) {
         dim3 grid((k + 31) / 32, n);
         const size_t smem = sizeof(float) * 32 * (taps + 1);
-        if (dtype == VP_F32) pack_weight_tiled_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (float*)wp, taps, n, k, sn, sk);
-        else pack_weight_tiled_kernel<bf16><<<grid, 256, smem, (cudaStream_t)stream>>>(w, (bf16*)wp, taps, n, k, sn, sk);
+        if (dtype == VP_F32) launch_k(pack_weight_tiled_kernel<float>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, w, (float*)wp, taps, n, k, sn, sk);
+        else launch_k(pack_weight_tiled_kernel<bf16>, dim3(grid), dim3(256), smem, (cudaStream_t)stream, w, (bf16*)wp, taps, n, k, sn, sk);
         VP_CHECK_LAUNCH("vp_pack_weight(tiled)");
         return VP_OK;
     }
     const unsigned g = (unsigned)(((int64_t)n * k + 255) / 256);
-    if (dtype == VP_F32) pack_weight_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>(w, (float*)wp, taps, n, k, sn, sk, st);
-    else pack_weight_kernel<bf16><<<g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)wp, taps, n, k, sn, sk, st);
+    if (dtype == VP_F32) launch_k(pack_weight_kernel<float>, dim3(g), dim3(256), 0, (cudaStream_t)stream, w, (float*)wp, taps, n, k, sn, sk, st);
+    else launch_k(pack_weight_kernel<bf16>, dim3(g), dim3(256), 0, (cudaStream_t)stream, w, (bf16*)wp, taps, n, k, sn, sk, st);
     VP_CHECK_LAUNCH("vp_pack_weight");
     return VP_OK;
 }
@@ -498,19 +516,19 @@ extern "C" int vp_unpack_wgrad(const float* dwp, float* dw, int taps, int n, int
     if (st == 1 && taps >= 4 && k >= 32 && n <= 65535) {
         dim3 grid((k + 31) / 32, n);
         const size_t smem = sizeof(float) * 32 * (taps + 1);
-        unpack_wgrad_tiled_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(dwp, dw, taps, n, k, sn, sk);
+        launch_k(unpack_wgrad_tiled_kernel, dim3(grid), dim3(256), smem, (cudaStream_t)stream, dwp, dw, taps, n, k, sn, sk);
         VP_CHECK_LAUNCH("vp_unpack_wgrad(tiled)");
         return VP_OK;
     }
     const unsigned g = (unsigned)(((int64_t)n * k + 255) / 256);
-    unpack_wgrad_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(dwp, dw, taps, n, k, sn, sk, st);
+    launch_k(unpack_wgrad_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, dwp, dw, taps, n, k, sn, sk, st);
     VP_CHECK_LAUNCH("vp_unpack_wgrad");
     return VP_OK;
 }
 
 extern "C" int vp_sum_into(const float* v, int64_t n, float scale, float* acc, void* stream) {
     VP_CHECK_ARG(v && acc && n >= 0, "vp_sum_into: bad arguments");
-    sum_into_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(v, n, scale, acc);
+    launch_k(sum_into_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, v, n, scale, acc);
     VP_CHECK_LAUNCH("vp_sum_into");
     return VP_OK;
 }
@@ -518,7 +536,7 @@ extern "C" int vp_sum_into(const float* v, int64_t n, float scale, float* acc, v
 extern "C" int vp_fill_from(const float* g, float scale, float* out, int64_t n, void* stream) {
     VP_CHECK_ARG(out && n >= 0, "vp_fill_from: bad arguments");
     if (n == 0) return VP_OK;
-    fill_from_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(g, scale, out, n);
+    launch_k(fill_from_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, g, scale, out, n);
     VP_CHECK_LAUNCH("vp_fill_from");
     return VP_OK;
 }
@@ -535,6 +553,7 @@ struct OptTable {
     int64_t n[kOptMax];
 };
 __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd, int zero_g) {
+    pdl_sync();
     const int ti = blockIdx.y;
     float* __restrict__ p = t.p[ti];
     bf16* __restrict__ sh = t.sh[ti];
@@ -599,7 +618,7 @@ extern "C" int vp_rmsprop_step_shadow(void* const* params, void* const* grads, v
         int64_t bx = (nmax / 4 + 255) / 256;
         if (bx > 148 * 2) bx = 148 * 2;
         if (bx < 1) bx = 1;
-        rmsprop_kernel<<<dim3((unsigned)bx, (unsigned)m), 256, 0, (cudaStream_t)stream>>>(t, lr, alpha, eps, weight_decay, zero_grads);
+        launch_k(rmsprop_kernel, dim3((unsigned)bx, (unsigned)m), dim3(256), 0, (cudaStream_t)stream, t, lr, alpha, eps, weight_decay, zero_grads);
         VP_CHECK_LAUNCH("vp_rmsprop_step");
     }
     return VP_OK;
@@ -613,6 +632,7 @@ namespace vp {
 namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_bt_kernel(const T* __restrict__ src, T* __restrict__ dst, int rows, int cols) {
+    pdl_sync();
     __shared__ T tile[32][33];
     const int b = blockIdx.z;
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -629,6 +649,7 @@ __global__ void __launch_bounds__(256) transpose_bt_kernel(const T* __restrict__
 // bf16, rows and cols multiples of 64: 64 x 64 tiles, every global access is a 4-byte pair, the 2 x 2 blocks are
 // transposed in registers on the way out (4x fewer, 2x wider memory instructions than the generic kernel)
 __global__ void __launch_bounds__(256) transpose_bt64_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int rows, int cols) {
+    pdl_sync();
     __shared__ uint32_t tile[64][33];
     const int b = blockIdx.z;
     const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
@@ -651,13 +672,13 @@ __global__ void __launch_bounds__(256) transpose_bt64_kernel(const uint32_t* __r
 extern "C" int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream) {
     VP_CHECK_ARG(src && dst && batch > 0 && rows > 0 && cols > 0 && batch <= 65535, "vp_transpose_bt: bad arguments");
     if (dtype == VP_BF16 && rows % 64 == 0 && cols % 64 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 3) == 0) {
-        transpose_bt64_kernel<<<dim3(cols / 64, rows / 64, batch), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)src, (uint32_t*)dst, rows, cols);
+        launch_k(transpose_bt64_kernel, dim3(cols / 64, rows / 64, batch), dim3(256), 0, (cudaStream_t)stream, (const uint32_t*)src, (uint32_t*)dst, rows, cols);
         VP_CHECK_LAUNCH("vp_transpose_bt");
         return VP_OK;
     }
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
-    if (dtype == VP_F32) transpose_bt_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)src, (float*)dst, rows, cols);
-    else transpose_bt_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)src, (bf16*)dst, rows, cols);
+    if (dtype == VP_F32) launch_k(transpose_bt_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)src, (float*)dst, rows, cols);
+    else launch_k(transpose_bt_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)src, (bf16*)dst, rows, cols);
     VP_CHECK_LAUNCH("vp_transpose_bt");
     return VP_OK;
 }

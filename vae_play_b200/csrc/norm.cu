@@ -87,6 +87,7 @@ constexpr int VR = 4;
 template <typename T>
 __global__ void __launch_bounds__(NT, 4) stats_kernel(const T* __restrict__ x, double* __restrict__ sums,
                                                       int64_t groups, int64_t rpg, int C, int tpr) {
+    pdl_sync();
     // tpr = threads per row (power of two <= 16): narrow tensors (C = 1, 3, ...) put more threads on the row axis
     __shared__ float s1[NT * VR], s2[NT * VR];
     const int cpb = tpr * VR;            // channels per block
@@ -134,8 +135,10 @@ __global__ void __launch_bounds__(NT, 4) stats_kernel(const T* __restrict__ x, d
 __global__ void finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float* running_mean, float* running_var,
                                 float momentum, float eps, float* mean, float* invstd, float* scale,
-                                float* shift, int64_t groups, int64_t rpg, int C) {
+                                float* shift, int64_t groups, int64_t rpg, int C, long long* nbt) {
+    pdl_sync();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0 && nbt) *nbt += 1;          // BatchNorm.num_batches_tracked, kept on the device by torch
     if (i >= groups * C) return;
     const int c = (int)(i % C);
     const double m = (double)rpg;
@@ -162,6 +165,7 @@ template <typename T>
 __global__ void __launch_bounds__(NT) apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                    const float* __restrict__ shift, T* __restrict__ a,
                                                    int64_t rpg, int C, int act, float slope) {
+    pdl_sync();
     const int cl = (threadIdx.x % (CPB / V)) * V;
     const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.y * CPB + cl;
@@ -201,6 +205,7 @@ __global__ void __launch_bounds__(NT, 3) bwd_reduce_kernel(const T* __restrict__
                                                            const float* __restrict__ shift,
                                                            double* __restrict__ sums, T* __restrict__ dxo,
                                                            int64_t groups, int64_t rpg, int C, int act, float slope, int tpr) {
+    pdl_sync();
     __shared__ float s1[NT * VR], s2[NT * VR];
     const int cpb = tpr * VR;
     const int rlanes = NT / tpr;
@@ -264,6 +269,7 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
                                                        const double* __restrict__ sums, T* __restrict__ dx,
                                                        float* dgamma, float* dbeta, int64_t groups, int64_t rpg,
                                                        int C, int act, float slope) {
+    pdl_sync();
     const int cl = (threadIdx.x % (CPB / V)) * V;
     const int rl = threadIdx.x / (CPB / V);
     const int c = blockIdx.y * CPB + cl;
@@ -317,6 +323,7 @@ __global__ void __launch_bounds__(NT) bwd_apply_kernel(const T* __restrict__ x, 
 }
 
 __global__ void colsum_finish_kernel(const double* __restrict__ s, float* __restrict__ out, int C) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < C) out[i] = (float)s[i];
 }
@@ -359,20 +366,21 @@ extern "C" int vp_norm_stats(const void* x, double* sums, int dtype, int64_t gro
     const int tpr = threads_per_row(c);
     const int ctiles = (c + tpr * VR - 1) / (tpr * VR);
     dim3 grid(ctiles, slab_blocks(rpg, ctiles, groups), (unsigned)groups);
-    if (dtype == VP_F32) stats_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, sums, groups, rpg, c, tpr);
-    else stats_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, sums, groups, rpg, c, tpr);
+    if (dtype == VP_F32) launch_k(stats_kernel<float>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const float*)x, sums, groups, rpg, c, tpr);
+    else launch_k(stats_kernel<bf16>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const bf16*)x, sums, groups, rpg, c, tpr);
     VP_CHECK_LAUNCH("vp_norm_stats");
     return VP_OK;
 }
 
 extern "C" int vp_norm_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean,
                                 float* running_var, float momentum, float eps, float* mean, float* invstd,
-                                float* scale, float* shift, int64_t groups, int64_t rpg, int c, void* stream) {
+                                float* scale, float* shift, int64_t groups, int64_t rpg, int c, int64_t* num_batches_tracked,
+                                void* stream) {
     VP_CHECK_ARG(sums && mean && invstd && scale && shift && groups > 0 && rpg > 0 && c > 0,
                  "vp_norm_finalize: bad arguments");
     const int64_t n = groups * c;
-    finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        sums, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd, scale, shift, groups, rpg, c);
+    launch_k(finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, 
+        sums, gamma, beta, running_mean, running_var, momentum, eps, mean, invstd, scale, shift, groups, rpg, c, (long long*)num_batches_tracked);
     VP_CHECK_LAUNCH("vp_norm_finalize");
     return VP_OK;
 }
@@ -382,7 +390,10 @@ namespace {
 // block = 16 channels x 64 part lanes: every part row is read by one lane, all loads of a thread are independent
 __global__ void __launch_bounds__(1024) finalize_parts_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* running_mean, float* running_var, float momentum,
-                                                             float eps, float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C) {
+                                                             float eps, float* mean, float* invstd, float* scale, float* shift, int64_t rows, int C,
+                                                             long long* nbt) {
+    pdl_sync();
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
     __shared__ double sh1[64][17], sh2[64][17];
     const int cl = threadIdx.x & 15, pl = threadIdx.x >> 4;
     const int c = blockIdx.x * 16 + cl;
@@ -422,10 +433,10 @@ __global__ void __launch_bounds__(1024) finalize_parts_kernel(const float* __res
  * vp_thin_conv_fwd_stats): parts[nparts][2][c] fp32, added in double in a fixed order (deterministic). */
 extern "C" int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta, float* running_mean,
                                       float* running_var, float momentum, float eps, float* mean, float* invstd, float* scale,
-                                      float* shift, int64_t rows, int c, void* stream) {
+                                      float* shift, int64_t rows, int c, int64_t* num_batches_tracked, void* stream) {
     VP_CHECK_ARG(parts && nparts > 0 && mean && invstd && scale && shift && rows > 0 && c > 0, "vp_norm_finalize_parts: bad arguments");
-    finalize_parts_kernel<<<(c + 15) / 16, 1024, 0, (cudaStream_t)stream>>>(parts, nparts, gamma, beta, running_mean, running_var, momentum, eps,
-                                                                         mean, invstd, scale, shift, rows, c);
+    launch_k(finalize_parts_kernel, dim3((c + 15) / 16), dim3(1024), 0, (cudaStream_t)stream, parts, nparts, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                         mean, invstd, scale, shift, rows, c, (long long*)num_batches_tracked);
     VP_CHECK_LAUNCH("vp_norm_finalize_parts");
     return VP_OK;
 }
@@ -441,9 +452,9 @@ extern "C" int vp_norm_apply_act(const void* x, const float* scale, const float*
     }
     dim3 grid((unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB, (unsigned)groups);
     if (dtype == VP_F32)
-        apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, scale, shift, (float*)a, rpg, c, act, slope);
+        launch_k(apply_kernel<float>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const float*)x, scale, shift, (float*)a, rpg, c, act, slope);
     else
-        apply_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, scale, shift, (bf16*)a, rpg, c, act, slope);
+        launch_k(apply_kernel<bf16>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const bf16*)x, scale, shift, (bf16*)a, rpg, c, act, slope);
     VP_CHECK_LAUNCH("vp_norm_apply_act");
     return VP_OK;
 }
@@ -477,6 +488,7 @@ template <> __device__ __forceinline__ void stv4<bf16>(bf16* p, const float* v) 
 template <typename T>
 __global__ void __launch_bounds__(256) act_bwd_flat_kernel(const T* __restrict__ x, const T* __restrict__ da, T* __restrict__ dxo, double* sums,
                                                            int64_t n8, int C, int act, float slope) {
+    pdl_sync();
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         float v[8], d[8];
@@ -516,8 +528,8 @@ extern "C" int vp_norm_bwd_reduce(const void* x, const void* da, const float* me
         const int64_t n8 = rpg * c / 8;
         int64_t blocks = (n8 + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        if (dtype == VP_F32) act_bwd_flat_kernel<float><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, (float*)dxo, sums, n8, c, act, slope);
-        else act_bwd_flat_kernel<bf16><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, (bf16*)dxo, sums, n8, c, act, slope);
+        if (dtype == VP_F32) launch_k(act_bwd_flat_kernel<float>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const float*)x, (const float*)da, (float*)dxo, sums, n8, c, act, slope);
+        else launch_k(act_bwd_flat_kernel<bf16>, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)da, (bf16*)dxo, sums, n8, c, act, slope);
         VP_CHECK_LAUNCH("vp_norm_bwd_reduce");
         return VP_OK;
     }
@@ -530,9 +542,9 @@ extern "C" int vp_norm_bwd_reduce(const void* x, const void* da, const float* me
     const int ctiles = (c + tpr * VR - 1) / (tpr * VR);
     dim3 grid(ctiles, slab_blocks(rpg, ctiles, groups), (unsigned)groups);
     if (dtype == VP_F32)
-        bwd_reduce_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dxo, groups, rpg, c, act, slope, tpr);
+        launch_k(bwd_reduce_kernel<float>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dxo, groups, rpg, c, act, slope, tpr);
     else
-        bwd_reduce_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, sums, (bf16*)dxo, groups, rpg, c, act, slope, tpr);
+        launch_k(bwd_reduce_kernel<bf16>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, sums, (bf16*)dxo, groups, rpg, c, act, slope, tpr);
     VP_CHECK_LAUNCH("vp_norm_bwd_reduce");
     return VP_OK;
 }
@@ -551,9 +563,9 @@ extern "C" int vp_norm_bwd_apply(const void* x, const void* da, const float* mea
     }
     dim3 grid((unsigned)((rpg + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), (c + CPB - 1) / CPB, (unsigned)groups);
     if (dtype == VP_F32)
-        bwd_apply_kernel<float><<<grid, NT, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dx, dgamma, dbeta, groups, rpg, c, act, slope);
+        launch_k(bwd_apply_kernel<float>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const float*)x, (const float*)da, mean, invstd, scale, shift, sums, (float*)dx, dgamma, dbeta, groups, rpg, c, act, slope);
     else
-        bwd_apply_kernel<bf16><<<grid, NT, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, sums, (bf16*)dx, dgamma, dbeta, groups, rpg, c, act, slope);
+        launch_k(bwd_apply_kernel<bf16>, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, sums, (bf16*)dx, dgamma, dbeta, groups, rpg, c, act, slope);
     VP_CHECK_LAUNCH("vp_norm_bwd_apply");
     return VP_OK;
 }
@@ -563,7 +575,7 @@ extern "C" int vp_colsum(const void* x, float* out, double* scratch_c, int dtype
     // scratch_c: double [2][c], zero on entry; reuse the statistics kernel (sum column)
     int rc = vp_norm_stats(x, scratch_c, dtype, 1, rows, c, stream);
     if (rc) return rc;
-    colsum_finish_kernel<<<(c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(scratch_c, out, c);
+    launch_k(colsum_finish_kernel, dim3((c + 255) / 256), dim3(256), 0, (cudaStream_t)stream, scratch_c, out, c);
     VP_CHECK_LAUNCH("vp_colsum");
     return VP_OK;
 }
@@ -582,7 +594,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) bn_rows_fwd_kernel(const T* __restrict__ y, const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* running_mean, float* running_var, float momentum, float eps, T* __restrict__ a,
                                                           float* mean, float* invstd, float* scale, float* shift, int rows, int C, int act,
-                                                          float slope) {
+                                                          float slope, long long* nbt) {
+    pdl_sync();
+    if (nbt && blockIdx.x == 0 && threadIdx.x == 0) *nbt += 1;
     typedef typename AccT<T>::type Acc;
     __shared__ double red[2][SM_RS][SM_CG * SM_V];
     __shared__ float par[2][SM_CG * SM_V];
@@ -640,6 +654,7 @@ __global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const T* __restrict__ 
                                                           const float* __restrict__ invstd, const float* __restrict__ scale,
                                                           const float* __restrict__ shift, T* __restrict__ dy, float* dgamma, float* dbeta, int rows,
                                                           int C, int act, float slope) {
+    pdl_sync();
     typedef typename AccT<T>::type Acc;
     __shared__ double red[2][SM_RS][SM_CG * SM_V];
     __shared__ float par[2][SM_CG * SM_V];
@@ -703,16 +718,16 @@ __global__ void __launch_bounds__(256) bn_rows_bwd_kernel(const T* __restrict__ 
  * c must be a multiple of 4 and the tensors 16-byte aligned.  The BatchNorm1d of models/networks.py:66,89. */
 extern "C" int vp_bn_rows_fwd(const void* x, const float* gamma, const float* beta, float* running_mean, float* running_var, float momentum,
                               float eps, void* a, float* mean, float* invstd, float* scale, float* shift, int dtype, int64_t rows, int c,
-                              int act, float slope, void* stream) {
+                              int act, float slope, int64_t* num_batches_tracked, void* stream) {
     VP_CHECK_ARG(x && a && mean && invstd && scale && shift && rows > 0 && rows <= 8192 && c > 0 && c % 4 == 0, "vp_bn_rows_fwd: bad arguments");
     VP_CHECK_ARG((((uintptr_t)x | (uintptr_t)a) & 15) == 0, "vp_bn_rows_fwd: 16-byte alignment");
     const unsigned grid = (unsigned)((c + SM_CG * SM_V - 1) / (SM_CG * SM_V));
     if (dtype == VP_F32)
-        bn_rows_fwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, gamma, beta, running_mean, running_var, momentum, eps,
-                                                                         (float*)a, mean, invstd, scale, shift, (int)rows, c, act, slope);
+        launch_k(bn_rows_fwd_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                         (float*)a, mean, invstd, scale, shift, (int)rows, c, act, slope, (long long*)num_batches_tracked);
     else
-        bn_rows_fwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, gamma, beta, running_mean, running_var, momentum, eps,
-                                                                        (bf16*)a, mean, invstd, scale, shift, (int)rows, c, act, slope);
+        launch_k(bn_rows_fwd_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, gamma, beta, running_mean, running_var, momentum, eps,
+                                                                        (bf16*)a, mean, invstd, scale, shift, (int)rows, c, act, slope, (long long*)num_batches_tracked);
     VP_CHECK_LAUNCH("vp_bn_rows_fwd");
     return VP_OK;
 }
@@ -725,10 +740,10 @@ extern "C" int vp_bn_rows_bwd(const void* x, const void* da, const float* mean, 
     VP_CHECK_ARG((((uintptr_t)x | (uintptr_t)da | (uintptr_t)dx) & 15) == 0, "vp_bn_rows_bwd: 16-byte alignment");
     const unsigned grid = (unsigned)((c + SM_CG * SM_V - 1) / (SM_CG * SM_V));
     if (dtype == VP_F32)
-        bn_rows_bwd_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (const float*)da, mean, invstd, scale, shift, (float*)dx,
+        launch_k(bn_rows_bwd_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, (const float*)da, mean, invstd, scale, shift, (float*)dx,
                                                                          dgamma, dbeta, (int)rows, c, act, slope);
     else
-        bn_rows_bwd_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, (bf16*)dx,
+        launch_k(bn_rows_bwd_kernel<bf16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (const bf16*)da, mean, invstd, scale, shift, (bf16*)dx,
                                                                         dgamma, dbeta, (int)rows, c, act, slope);
     VP_CHECK_LAUNCH("vp_bn_rows_bwd");
     return VP_OK;

@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_sync();
 
     float sc[V], sh[V], mu[V], is[V], m1[V], m2[V], a[V], b[V];
 #pragma unroll
@@ -262,7 +263,7 @@ int launch_stream(const StreamArgs& a, cudaStream_t s) {
     const int ctas_per_sm = 2;                     // ~97 KB / ~82 KB of smem per CTA
     int64_t grid = 148 * ctas_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
-    norm_stream_kernel<MODE, T, RELU><<<(unsigned)grid, NT, smem, s>>>(a);
+    launch_k(norm_stream_kernel<MODE, T, RELU>, dim3((unsigned)grid), dim3(NT), smem, s, a);
     VP_CHECK_LAUNCH("norm_stream");
     return VP_OK;
 }

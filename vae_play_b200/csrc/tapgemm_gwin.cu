@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ===== halo producer: per (tile, k-block, class) two boxes {64 ch, Wh_c, Hh_c, 1 image} of the class sub-lattice =====
@@ -239,7 +240,7 @@ int launch_gwin(const InMaps& mA, const CUtensorMap& mB, const CUtensorMap& mD, 
         attr_set = smem_bytes;
     }
     const int grid = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
-    tapgemm_gwin_kernel<BN, BSTAGES><<<grid, kGThreads, smem_bytes, s>>>(mA, mB, mD, gp);
+    launch_k(tapgemm_gwin_kernel<BN, BSTAGES>, dim3(grid), dim3(kGThreads), smem_bytes, s, mA, mB, mD, gp);
     VP_CHECK_LAUNCH("tapgemm_gwin");
     return VP_OK;
 }

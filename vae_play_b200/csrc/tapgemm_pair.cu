@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(kPThreads, 1) tapgemm_pair_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ===== halo producer: per (tile, k-block) two 4-D boxes {64 ch, Wh, Hh, 1 image} =====
@@ -345,7 +346,7 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
         if (e != cudaSuccess) { set_error("tapgemm_pair: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = smem_bytes;
     }
-    tapgemm_pair_kernel<<<grid, kPThreads, smem_bytes, s>>>(mA, mB, om, pp);
+    launch_k(tapgemm_pair_kernel, dim3(grid), dim3(kPThreads), smem_bytes, s, mA, mB, om, pp);
     VP_CHECK_LAUNCH("tapgemm_pair");
     return VP_OK;
 }

@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0 || warp == 6) {
         // ===== TMA producers: warp 0 streams the A bricks, warp 6 the weight panels (two issuing threads) =====
@@ -376,7 +377,7 @@ int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const OutMaps& om, 
     const int slots = num_sms() * CTAS;
     const int grid = tp.total_tiles < slots ? tp.total_tiles : slots;
     if (grid_out) *grid_out = grid;
-    tapgemm_tc_kernel<BN, STAGES, CTAS, BMN><<<grid, kFwdThreads, smem_bytes, s>>>(mA, mB, om, tp);
+    launch_k(tapgemm_tc_kernel<BN, STAGES, CTAS, BMN>, dim3(grid), dim3(kFwdThreads), smem_bytes, s, mA, mB, om, tp);
     VP_CHECK_LAUNCH("tapgemm_tc");
     return VP_OK;
 }
@@ -391,14 +392,28 @@ int tc_variant() {
 }  // namespace
 
 // ---- split-K support ------------------------------------------------------------------------------------------------
-static void* g_ws = nullptr;
-static size_t g_ws_bytes = 0;
-void set_splitk_workspace(void* ptr, size_t bytes) { g_ws = ptr; g_ws_bytes = bytes; }
-void* splitk_workspace(size_t bytes) { return bytes <= g_ws_bytes ? g_ws : nullptr; }
+// one registered buffer per device (a process may drive several GPUs); selected by the current device of the calling thread
+constexpr int kMaxDevices = 64;
+static void* g_ws[kMaxDevices] = {};
+static size_t g_ws_bytes[kMaxDevices] = {};
+static int current_device_slot() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
+void set_splitk_workspace(void* ptr, size_t bytes) {
+    const int d = current_device_slot();
+    if (d >= 0) { g_ws[d] = ptr; g_ws_bytes[d] = bytes; }
+}
+void* splitk_workspace(size_t bytes) {
+    const int d = current_device_slot();
+    return (d >= 0 && bytes <= g_ws_bytes[d]) ? g_ws[d] : nullptr;
+}
 
 namespace {
 __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restrict__ ws, void* __restrict__ D, const float* __restrict__ bias, int act,
                                                             float slope, int64_t n, int N, int out_f32) {
+    pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float x = ws[i];
         if (bias) x += bias[i % N];
@@ -411,7 +426,7 @@ __global__ void __launch_bounds__(256) splitk_finish_kernel(const float* __restr
 int launch_splitk_finish(const float* ws, void* D, const float* bias, int act, float slope, int64_t n, int N, bool out_f32, cudaStream_t s) {
     int64_t blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    splitk_finish_kernel<<<(unsigned)blocks, 256, 0, s>>>(ws, D, bias, act, slope, n, N, out_f32 ? 1 : 0);
+    launch_k(splitk_finish_kernel, dim3((unsigned)blocks), dim3(256), 0, s, ws, D, bias, act, slope, n, N, out_f32 ? 1 : 0);
     VP_CHECK_LAUNCH("splitk_finish");
     return VP_OK;
 }
@@ -661,6 +676,7 @@ __global__ void __launch_bounds__(kFwdThreads) tapwgrad_tc_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0 || warp == 6) {
         // two TMA issuing threads: warp 0 streams the G (grid-side) boxes, warp 6 the shifted A boxes
@@ -757,7 +773,7 @@ int launch_wgrad_cfg(const CUtensorMap& mG, const CUtensorMap& mA, const TcWgrad
         if (e != cudaSuccess) { set_error("tapwgrad_tc: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = true;
     }
-    tapwgrad_tc_kernel<BN, STAGES><<<grid, kFwdThreads, smem_bytes, s>>>(mG, mA, tp);
+    launch_k(tapwgrad_tc_kernel<BN, STAGES>, grid, dim3(kFwdThreads), smem_bytes, s, mG, mA, tp);
     VP_CHECK_LAUNCH("tapwgrad_tc");
     return VP_OK;
 }
@@ -826,6 +842,7 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
 
 }  // namespace vp
 
+#ifdef VP_DEBUG_PROBES   // debug builds only (VP_DEBUG_PROBES=1 python -m vae_play_b200.build --force): not part of the release ABI
 // =====================================================================================================
 // Hardware-semantics probe (debug entry point, used by tools/probe_umma.py): does tcgen05.mma accept a K-major
 // SW128 A operand whose start address is NOT 1024-byte aligned (a window into a larger TMA-written tile), with an
@@ -912,3 +929,4 @@ extern "C" int vp_debug_umma_probe(const void* x, const void* ident, float* out,
     VP_CHECK_LAUNCH("umma_probe");
     return VP_OK;
 }
+#endif  // VP_DEBUG_PROBES

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ===== halo producer: per (tile, k-block) two 4-D boxes {64 ch, Wh, Hh, 1 image} =====
@@ -285,7 +286,7 @@ int launch_win(const CUtensorMap& mA, const CUtensorMap& mB, const OutMaps& om, 
         attr_set = smem_bytes;
     }
     const int grid = wp.total_tiles < num_sms() ? wp.total_tiles : num_sms();
-    tapgemm_win_kernel<BN, BSTAGES, BMN><<<grid, kWThreads, smem_bytes, s>>>(mA, mB, om, wp);
+    launch_k(tapgemm_win_kernel<BN, BSTAGES, BMN>, dim3(grid), dim3(kWThreads), smem_bytes, s, mA, mB, om, wp);
     VP_CHECK_LAUNCH("tapgemm_win");
     return VP_OK;
 }

@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(kRThreads, 1) tapwgrad_row_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();     // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
     if (warp == 0) {
         // ===== G producer: two {64 gc, 8, 8, 1} boxes per brick =====
@@ -334,7 +335,7 @@ int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t
     }
     if (!p.accumulate) cudaMemsetAsync(p.dWp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     dim3 grid((unsigned)sets, (unsigned)nsplit);
-    tapwgrad_row_kernel<<<grid, kRThreads, smem_bytes, s>>>(mG, maps[0], maps[1], maps[2], maps[3], rp);
+    launch_k(tapwgrad_row_kernel, grid, dim3(kRThreads), smem_bytes, s, mG, maps[0], maps[1], maps[2], maps[3], rp);
     VP_CHECK_LAUNCH("tapwgrad_row");
     return VP_OK;
 }

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_sync();     // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory only from here on
     // weight tile B[n][k] = W[n, kmap[k]] (zero for padding K), K-major SWIZZLE_128B
     for (int i = threadIdx.x; i < p.N * 64; i += kKThreads) {
         const int n = i >> 6, k = i & 63;
@@ -364,7 +365,7 @@ int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* st
     }
     const int slots = 2 * num_sms();
     const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-    thin_k_kernel<<<grid, kKThreads, kKSmem, s>>>(mD, p);
+    launch_k(thin_k_kernel, dim3(grid), dim3(kKThreads), kKSmem, s, mD, p);
     VP_CHECK_LAUNCH("thin_k");
     return VP_OK;
 }
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(kWThreads, 2) thin_w_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_sync();
     const int my_tiles = (p.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp < 4) {
@@ -491,7 +493,7 @@ int launch_thin_w(const CUtensorMap& mw, const ThinWParams& p, int cblocks, cuda
     int slots = 2 * num_sms() / cblocks;
     if (slots < 1) slots = 1;
     dim3 grid((unsigned)(p.total_tiles < slots ? p.total_tiles : slots), (unsigned)cblocks);
-    thin_w_kernel<<<grid, kWThreads, kWSmem, s>>>(mw, p);
+    launch_k(thin_w_kernel, dim3(grid), dim3(kWThreads), kWSmem, s, mw, p);
     VP_CHECK_LAUNCH("thin_w");
     return VP_OK;
 }
@@ -547,6 +549,7 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_sync();     // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory only from here on
     // weight tiles: per 64-channel k-block, 32 rows j = t*CT + c of 64 input channels (K-major SW128)
     for (int i = threadIdx.x; i < p.kblocks * 32 * 64; i += kNThreads) {
         const int k = i & 63, j = (i >> 6) & 31, kb = i >> 11;
@@ -772,7 +775,7 @@ static int thin_conv_fwd_impl(const VpConvGeom* g, const void* x, const float* w
         }
         const int slots = num_sms() * (2 * smem_bytes <= 227 * 1024 ? 2 : 1);
         const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-        thin_n_kernel<<<grid, kNThreads, smem_bytes, s>>>(mA, p);
+        launch_k(thin_n_kernel, dim3(grid), dim3(kNThreads), smem_bytes, s, mA, p);
         VP_CHECK_LAUNCH("thin_n");
         return VP_OK;
     }

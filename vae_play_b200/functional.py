@@ -24,12 +24,22 @@ _GRAD_SINKS = {}   # param.data_ptr() -> (bucket view, param): where wgrad write
 _SHADOWS = {}      # weight.data_ptr() -> (TapLayer, bf16 copy): lets a fused optimiser refresh the copy while it updates the master
 
 
+_SINK_HOOKS = []   # post-accumulate hooks that re-arm a slot once autograd has consumed the tensor handed out for it
+
+
 def set_grad_sinks(sinks_by_param_id, params=None):
     """Register persistent slots for parameter gradients: param.data_ptr() -> (flat fp32 buffer, element offset, param).
     The weight-gradient kernels write straight into them (flat data-parallel buckets, ``persistent_grads``)."""
+    for h in _SINK_HOOKS:
+        h.remove()
+    _SINK_HOOKS.clear()
     _GRAD_SINKS.clear()
     for k, v in sinks_by_param_id.items():
-        _GRAD_SINKS[k] = [v[0], int(v[1]), v[2], False]        # [flat, offset, param, slot is known to hold zeros]
+        # [flat, offset, param, slot is known to hold zeros, slot handed out and not yet accumulated by autograd]
+        entry = [v[0], int(v[1]), v[2], False, False]
+        _GRAD_SINKS[k] = entry
+        if hasattr(v[2], "register_post_accumulate_grad_hook"):
+            _SINK_HOOKS.append(v[2].register_post_accumulate_grad_hook(lambda p, e=entry: e.__setitem__(4, False)))
 
 
 def persistent_grads(params):
@@ -59,13 +69,16 @@ def sinks_zeroed(params):
 
 def _grad_target(weight):
     """Where a weight gradient is written: (tensor, holds_zeros).  A registered slot is used when it can become the
-    parameter's .grad as is (no gradient accumulated yet this step).  The view is created afresh and referenced by nobody
-    else, so that autograd's AccumulateGrad adopts it instead of cloning it."""
+    parameter's .grad as is: no gradient accumulated yet this step AND the slot not already handed to an earlier use of
+    the same weight in this backward (a weight used twice -- the decoder on z and z_p, the discriminator in REC and GAN
+    mode, reference train.py:43-73 -- gets a fresh buffer for the later uses; autograd sums them into the slot).  The
+    view is created afresh and referenced by nobody else, so that autograd's AccumulateGrad adopts it instead of cloning."""
     hit = _GRAD_SINKS.get(weight.data_ptr())
     if hit is not None:
-        flat, off, param, zeroed = hit
-        if param.grad is None and param.shape == weight.shape and param.stride() == weight.stride():
+        flat, off, param, zeroed, handed = hit
+        if param.grad is None and not handed and param.shape == weight.shape and param.stride() == weight.stride():
             hit[3] = False
+            hit[4] = True
             return torch.as_strided(flat, weight.shape, weight.stride(), storage_offset=off), zeroed
     return torch.empty_like(weight, dtype=torch.float32), False
 
@@ -377,32 +390,30 @@ class _FusedLayerFn(torch.autograd.Function):
         few_rows = norm.kind == "batch" and training and not fuse_stats and rpg <= 8192 and cc % 4 == 0 and out_dtype == dt
         ctx.few_rows = few_rows
         if few_rows:
-            rm = rv = None
+            rm = rv = nbt = None
             if bn_module is not None and bn_module.track_running_stats:
-                rm, rv = bn_module.running_mean, bn_module.running_var
-                bn_module.num_batches_tracked += 1
+                rm, rv, nbt = bn_module.running_mean, bn_module.running_var, bn_module.num_batches_tracked
             a = torch.empty_like(y)
             _lib.call("vp_bn_rows_fwd", _ptr(y), _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum), float(norm.eps), _ptr(a),
-                      _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _code(dt), rpg, cc, ACT[act], float(slope), _stream())
+                      _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), _code(dt), rpg, cc, ACT[act], float(slope), _ptr(nbt), _stream())
             ctx.save_for_backward(x, weight, y, stats)
             ctx.dims = (groups, rpg, cc, c)
             ctx.train_stats = True
             ctx.has_affine = gamma is not None
             return a, y
         if training or norm.kind == "instance":
-            rm = rv = None
+            rm = rv = nbt = None
             if norm.kind == "batch" and bn_module is not None and bn_module.track_running_stats:
-                rm, rv = bn_module.running_mean, bn_module.running_var
+                # running statistics AND the num_batches_tracked counter are updated by the finalize kernel
+                rm, rv, nbt = bn_module.running_mean, bn_module.running_var, bn_module.num_batches_tracked
             if fuse_stats:
                 _lib.call("vp_norm_finalize_parts", _ptr(parts), nparts, _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum),
-                          float(norm.eps), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), rpg, cc, _stream())
+                          float(norm.eps), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), rpg, cc, _ptr(nbt), _stream())
             else:
                 sums = torch.empty(2 * groups * cc, dtype=torch.float64, device=dev)
                 _lib.call("vp_norm_stats", _ptr(y), _ptr(sums), _code(dt), groups, rpg, cc, _stream())
                 _lib.call("vp_norm_finalize", _ptr(sums), _ptr(g_), _ptr(b_), _ptr(rm), _ptr(rv), float(norm.momentum), float(norm.eps),
-                          _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), groups, rpg, cc, _stream())
-            if rm is not None:
-                bn_module.num_batches_tracked += 1
+                          _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift), groups, rpg, cc, _ptr(nbt), _stream())
         else:
             # eval-mode BatchNorm: running statistics (not on the training hot path; tiny [C] vectors)
             rm, rv = bn_module.running_mean, bn_module.running_var
@@ -424,7 +435,7 @@ class _FusedLayerFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, da, dy_extra):
         layer, norm, act, slope = ctx.layer, ctx.norm, ctx.act, ctx.slope
-        dev = da.device
+        dev = ctx.saved_tensors[0].device
         dgamma = dbeta = dbias = None
         if norm.kind is None:
             x, weight, a = ctx.saved_tensors

@@ -14,6 +14,7 @@ summed -- no post-scaling pass.
 """
 from __future__ import annotations
 
+from contextlib import contextmanager
 from typing import List
 
 import torch
@@ -52,8 +53,22 @@ class GradBuckets:
                 view = torch.as_strided(b["buf"], p.shape, p.stride(), storage_offset=off)
                 self.slot[id(p)] = (bi, view, off)
                 off += self._padded(p)
+        self._sync = True
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
         self._install_sinks()
+
+    @contextmanager
+    def no_sync(self):
+        """Backward calls inside this context only accumulate into the buckets (no readiness counting, no collective), like
+        ``DistributedDataParallel.no_sync``.  The reference step runs five ``backward(retain_graph=True)`` calls
+        (train.py:68-73): wrap the first four, run the last one outside, then call ``allreduce()``.  With ``overlap=True``
+        exactly ONE backward per step may run outside ``no_sync`` -- a gradient arriving for a bucket whose all-reduce is
+        already in flight raises instead of silently diverging the ranks."""
+        old, self._sync = self._sync, False
+        try:
+            yield self
+        finally:
+            self._sync = old
 
     @staticmethod
     def _padded(p):
@@ -82,6 +97,11 @@ class GradBuckets:
             view.copy_(g)
             p.grad = view
         b = self.buckets[bi]
+        if b["handle"] is not None:
+            raise RuntimeError("GradBuckets: a gradient arrived for a bucket whose all-reduce is already in flight; run a single "
+                               "backward per step, or wrap the accumulating backward calls in no_sync()")
+        if not self._sync:
+            return
         b["ready"] += 1
         if b["ready"] == len(b["params"]) and self.world > 1 and self.overlap:
             b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
