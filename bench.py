@@ -86,12 +86,80 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _load_reference_modules():
+    """The UNMODIFIED reference modules, vendored by oracle/build_ref.py into the git-ignored oracle/_ref/ (they travel to
+    the GPU box like the built .so; /root/reference itself does not exist there).  None when the recipe has not run."""
+    import importlib.util
+    path = os.path.join(ROOT, "oracle", "_ref", "models", "networks.py")
+    if not os.path.exists(path):
+        return None
+    spec = importlib.util.spec_from_file_location("vaeplay_reference_networks", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+class _ReferenceCpuStep:
+    """The reference's own CPU path for the VAE terms of train.py:43-78: its Encoder / Decoder / VaeGan.reparameterize
+    modules (models/networks.py), F.mse_loss + sum(kl), backward, torch.optim.RMSprop(lr=1e-4) per sub-network (:136-140)."""
+
+    def __init__(self, networks, img, cin):
+        import torch
+        from oracle import vae_numpy as vn
+        L = int(math.log2(img // 8))
+        P = vn.synth_vae_params(img, 128, cin, cin, 0)
+        self.enc = networks.Encoder(channel_in=cin, z_size=128, iter_level=L)
+        self.dec = networks.Decoder(z_size=128, size=self.enc.size, channel_out=cin, iter_level=L)
+        self.enc.load_state_dict({k[8:]: torch.from_numpy(v) for k, v in P.items() if k.startswith("encoder.")}, strict=False)
+        self.dec.load_state_dict({k[8:]: torch.from_numpy(v) for k, v in P.items() if k.startswith("decoder.")}, strict=False)
+        self.enc.train(); self.dec.train()
+        self.networks = networks
+        self.opts = [torch.optim.RMSprop(self.enc.parameters(), lr=1e-4), torch.optim.RMSprop(self.dec.parameters(), lr=1e-4)]
+
+    def step(self, x):
+        import torch
+        import torch.nn.functional as F
+        self.enc.zero_grad(); self.dec.zero_grad()
+        mus, log_variances = self.enc(x)
+        z = self.networks.VaeGan.reparameterize(None, mus, log_variances)
+        x_tilde = self.dec(z)
+        kl = -0.5 * torch.sum(-log_variances.exp() - torch.pow(mus, 2) + log_variances + 1, 1)
+        loss = F.mse_loss(x, x_tilde) + torch.sum(kl)
+        loss.backward()
+        for o in self.opts:
+            o.step()
+        return loss.detach()
+
+
+def _cpu_stepper(img, cin):
+    """(stepper with .step(x), kind, description): the unmodified reference when oracle/_ref exists, else the line-by-line port."""
+    import torch
+    from oracle import vae_numpy as vn
+    ref = _load_reference_modules()
+    if ref is not None:
+        return _ReferenceCpuStep(ref, img, cin), "reference", "unmodified reference models/networks.py (oracle/_ref) Encoder+reparameterize+Decoder, F.mse_loss+sum(kl), RMSprop"
+    from oracle.vae_torch import VaeTorchPort
+    P = vn.synth_vae_params(img, 128, cin, cin, 0)
+    return VaeTorchPort(P, torch.float32), "port", "oracle/vae_torch.py (torch-CPU restatement of models/networks.py + train.py step)"
+
+
 def cpu_baseline_sample(img, cin, steps=5, warmup=2, batch=16):
-    from oracle.vae_torch import time_cpu_steps
-    ips, ms, threads = time_cpu_steps(img=img, cin=cin, batch=batch, steps=steps, warmup=warmup)
-    return {"value": round(ips, 2), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"oracle/vae_torch.py (torch-CPU restatement of models/networks.py + train.py step), fp32, batch {batch}, "
-                      f"median of {steps} steps after {warmup} warm-up, {ms:.1f} ms/step"}
+    import torch
+    from oracle import vae_numpy as vn
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    stepper, kind, what = _cpu_stepper(img, cin)
+    x = torch.from_numpy(vn.synth_batch(batch, img, cin, 128, 0)[0])
+    for _ in range(warmup):
+        stepper.step(x)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        stepper.step(x)
+        ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return {"value": round(batch / med, 2), "unit": "images/s", "cores": threads, "kind": kind,
+            "sample": f"{what}, fp32, batch {batch}, median of {steps} steps after {warmup} warm-up, {med * 1e3:.1f} ms/step"}
 
 
 def run_reference(args):
@@ -101,18 +169,16 @@ def run_reference(args):
         return
     import torch
     from oracle import vae_numpy as vn
-    from oracle.vae_torch import VaeTorchPort
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     sample_b = args.ref_batch
-    P = vn.synth_vae_params(args.img, 128, args.cin, args.cin, 0)
-    port = VaeTorchPort(P, torch.float32)
+    stepper, kind, what = _cpu_stepper(args.img, args.cin)
     x = torch.from_numpy(vn.synth_batch(sample_b, args.img, args.cin, 128, 0)[0])
     for _ in range(args.warmup):
-        port.step(x)
+        stepper.step(x)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        port.step(x)
+        stepper.step(x)
     dt = time.perf_counter() - t0
     ips = sample_b * args.steps / dt
     line = {
@@ -120,8 +186,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, sample_b, note=f"CPU sample: each step is one train step on {sample_b} images"),
-        "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle/vae_torch.py fp32, {sample_b} images per step, {args.steps} steps"},
+        "cpu_baseline": {"value": round(ips, 2), "unit": "images/s", "cores": threads, "kind": kind,
+                         "sample": f"{what}, fp32, {sample_b} images per step, {args.steps} steps"},
         "e2e": {"value": round(ips, 2), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

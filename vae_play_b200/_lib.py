@@ -10,6 +10,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libvaeplay_b200.so")
+_EXPERIMENT_LIB = os.environ.get("VP_LIB_PATH")       # A/B experiments only: load another build of the same sources
 
 F32, BF16 = 0, 1
 ACT = {None: 0, "none": 0, "relu": 1, "lrelu": 2, "tanh": 3, "sigmoid": 4}
@@ -80,7 +81,9 @@ def load(build_if_missing: bool = True):
     if _lib is not None:
         return _lib
     from . import build as _build
-    if not os.path.exists(LIB_PATH) or _build.is_stale():
+    if _EXPERIMENT_LIB:
+        pass
+    elif not os.path.exists(LIB_PATH) or _build.is_stale():
         if not build_if_missing and not os.path.exists(LIB_PATH):
             raise VaePlayError(f"{LIB_PATH} is missing; run `python -m vae_play_b200.build`")
         try:
@@ -89,7 +92,7 @@ def load(build_if_missing: bool = True):
             if not os.path.exists(LIB_PATH):
                 raise VaePlayError(f"cannot build {LIB_PATH}: {e}") from e
             raise VaePlayError(f"{LIB_PATH} is older than its sources and cannot be rebuilt: {e}") from e
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(_EXPERIMENT_LIB or LIB_PATH)
     for name, args in SIGNATURES.items():
         fn = getattr(lib, name)
         fn.argtypes = args

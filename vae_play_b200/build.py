@@ -57,7 +57,8 @@ def is_stale() -> bool:
 
 
 def _flags():
-    return NVCC_FLAGS + (["-DVP_DEBUG_PROBES"] if os.environ.get("VP_DEBUG_PROBES") == "1" else [])
+    extra = os.environ.get("VP_EXTRA_NVCC_FLAGS", "").split()       # experiments (A/B builds); empty for the product build
+    return NVCC_FLAGS + (["-DVP_DEBUG_PROBES"] if os.environ.get("VP_DEBUG_PROBES") == "1" else []) + extra
 
 
 def _stale(target: str, deps) -> bool:

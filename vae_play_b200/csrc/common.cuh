@@ -26,8 +26,23 @@ void count_launch(int n = 1);
 // to what it may still read); pdl_trigger() right after it lets the successor pre-launch in turn (at most one kernel ahead).
 // VP_PDL=0 in the environment launches everything fully serialised (A/B measurements, debugging).
 bool pdl_enabled();
+// Dynamic shared memory to request so that AT MOST `ctas_per_sm` CTAs of a kernel fit on an SM.  A persistent kernel sized as
+// "one CTA per SM" must also be unable to double up: CTAs that are scheduled while the previous kernel is still draining
+// (programmatic dependent launch) land on whichever SMs free up first, and two of them on one SM (while another SM gets
+// none) would double the kernel's run time -- or serialise on the SM's 512 TMEM columns.
+inline int smem_for_occupancy(int bytes, int ctas_per_sm) {
+    const int floor_bytes = 233472 / (ctas_per_sm + 1) - 1024 + 1;       // 228 KB per SM, 1 KB reserved per CTA
+    return bytes > floor_bytes ? bytes : floor_bytes;
+}
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#ifndef VP_PDL_MODE
+#define VP_PDL_MODE 1      // 1: wait + early trigger; 2: wait only (dependents launch when this grid's CTAs exit)
+#endif
+__device__ __forceinline__ void pdl_trigger() {
+#if VP_PDL_MODE == 1
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
 __device__ __forceinline__ void pdl_sync() { pdl_wait(); pdl_trigger(); }
 
 template <typename... KArgs, typename... Args>

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
 
 template <int BN, int BSTAGES>
 int launch_gwin(const InMaps& mA, const CUtensorMap& mB, const CUtensorMap& mD, const GwinParams& gp, cudaStream_t s) {
-    const int smem_bytes = kAStages * 2 * gp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 + (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024;
+    const int smem_bytes = smem_for_occupancy(kAStages * 2 * gp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 + (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024, 1);
     if (smem_bytes > 227 * 1024) return VP_EUNSUPPORTED;
     static int attr_set = 0;
     if (attr_set < smem_bytes) {

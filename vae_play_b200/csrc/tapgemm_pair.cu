@@ -338,7 +338,7 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
         if (p.stat_nparts) *p.stat_nparts = grid;
         pp.stat_parts = p.stat_parts;
     }
-    const int smem_bytes = kAStages * 2 * pp.halo_bytes + kBStages * kBStage + 4 * 2 * 2048 + 128 * 4 + (2 * kAStages + 2 * kBStages + 4) * 8 + 16 + 1024;
+    const int smem_bytes = smem_for_occupancy(kAStages * 2 * pp.halo_bytes + kBStages * kBStage + 4 * 2 * 2048 + 128 * 4 + (2 * kAStages + 2 * kBStages + 4) * 8 + 16 + 1024, 1);
     if (smem_bytes > 227 * 1024) return VP_EUNSUPPORTED;
     static int attr_set = 0;
     if (attr_set < smem_bytes) {

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(kFwdThreads, CTAS_PER_SM) tapgemm_tc_kernel(co
 template <int BN, int STAGES, int CTAS, bool BMN = false>
 int launch_cfg(const CUtensorMap& mA, const CUtensorMap& mB, const OutMaps& om, const TcParams& tp, cudaStream_t s, int* grid_out = nullptr) {
     using L = SmemLayout<BN, STAGES>;
-    constexpr int smem_bytes = L::kTotal + 1024;  // + alignment slack
+    const int smem_bytes = smem_for_occupancy(L::kTotal + 1024, CTAS);  // + alignment slack; never more than CTAS CTAs per SM
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_tc_kernel<BN, STAGES, CTAS, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

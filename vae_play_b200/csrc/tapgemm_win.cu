@@ -276,8 +276,8 @@ __global__ void __launch_bounds__(kWThreads, 1) tapgemm_win_kernel(const __grid_
 
 template <int BN, int BSTAGES, bool BMN = false>
 int launch_win(const CUtensorMap& mA, const CUtensorMap& mB, const OutMaps& om, const WinParams& wp, cudaStream_t s) {
-    const int smem_bytes = kAStages * 2 * wp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 +
-                           (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024;
+    const int smem_bytes = smem_for_occupancy(kAStages * 2 * wp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 +
+                                              (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024, 1);
     if (smem_bytes > 227 * 1024) { set_error("windowed tap GEMM: %d bytes of shared memory", smem_bytes); return VP_EUNSUPPORTED; }
     static int attr_set = 0;
     if (attr_set < smem_bytes) {

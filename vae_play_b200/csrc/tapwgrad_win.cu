@@ -325,7 +325,7 @@ int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t
                 return VP_EUNSUPPORTED;
         }
     }
-    const int smem_bytes = kGStages * kGBytes + kHStages * rp.halo_stage_bytes + (2 * kGStages + 2 * kHStages + 1) * 8 + 16 + 1024;
+    const int smem_bytes = smem_for_occupancy(kGStages * kGBytes + kHStages * rp.halo_stage_bytes + (2 * kGStages + 2 * kHStages + 1) * 8 + 16 + 1024, 1);
     if (smem_bytes > 227 * 1024) return VP_EUNSUPPORTED;
     static int attr_set = 0;
     if (attr_set < smem_bytes) {

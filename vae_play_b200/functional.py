@@ -641,7 +641,8 @@ class _ReparamKL(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, mu, logvar, eps, z_dtype, rng):
-        _require_cuda(mu, "reparameterize mu")
+        if not mu.is_cuda:
+            raise _lib.VaePlayError(f"reparameterize mu: tensor is on {mu.device}; vae_play_b200 has no CPU path")
         ctx.set_materialize_grads(False)
         ctx.packed = logvar is None
         if ctx.packed:  # mu is the fused head output [B, 2Z] = (mu | logvar)

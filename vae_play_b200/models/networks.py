@@ -255,13 +255,19 @@ class VaeGan(nn.Module):
         z, _ = VF.reparam_kl(mu, logvar, eps=eps)
         return z
 
-    def forward(self, x, gen_size=10):
+    def forward(self, x, gen_size=10, eps=None, z_p=None):
+        """Reference VaeGan.forward (networks.py:233-258): train -> (x_tilde, disc_class [3B,1], disc_layer [3B,F], mus,
+        log_variances, params [B,3]); eval -> (x_tilde, params) or, with x None, decoded samples.  ``eps`` / ``z_p`` (tests)
+        replace the two random draws; by default both come from the device generator's Philox stream exactly as the
+        reference's ``normal_()`` / ``torch.randn(...).cuda()`` would consume it."""
         if self.training:
             mus, log_variances = self.encoder(x)
-            z = self.reparameterize(mus, log_variances)
+            z = self.reparameterize(mus, log_variances, eps)
             x_tilde = self.decoder(z)
             params = self.param_encoder(z)
-            z_p = VF.philox_normal((len(x), self.z_size), x.device).requires_grad_(True)   # torch.randn(...).cuda(), :241
+            if z_p is None:
+                z_p = VF.philox_normal((len(x), self.z_size), x.device)            # torch.randn(...).cuda(), :241
+            z_p = z_p.detach().requires_grad_(True)
             x_p = self.decoder(z_p)
             disc_layer = self.discriminator(x, x_tilde, x_p, "REC")
             disc_class = self.discriminator(x, x_tilde, x_p, "GAN")
@@ -272,7 +278,7 @@ class VaeGan(nn.Module):
                 z_p = VF.philox_normal((gen_size, self.z_size), dev)
                 return self.decoder(z_p)
             mus, log_variances = self.encoder(x)
-            z = self.reparameterize(mus, log_variances)
+            z = self.reparameterize(mus, log_variances, eps)
             x_tilde = self.decoder(z)
             params = self.param_encoder(z)
             return x_tilde, params
