@@ -68,6 +68,11 @@ int vp_device_arch(void);
  * contractions run unsplit on a few SMs.  >= 4 * (rows * out_features) bytes to be useful. */
 int vp_set_workspace(void* ptr, size_t bytes);
 
+/* Cap the SMs the persistent kernels size their grids for (n <= 0: all of them).  Used while a collective (the
+ * data-parallel gradient all-reduce, vae_play_b200/parallel.py) runs next to the rest of backward: a persistent grid must be
+ * fully resident, so the SMs the collective's CTAs occupy are left out.  Read at launch time on the host. */
+int vp_set_sm_limit(int n);
+
 /* ---- weight layout ------------------------------------------------------------------------------- */
 /* Wp[t][n][k] = (dtype) w[n*stride_n + k*stride_k + t*stride_t],  t in [0,taps).  `w` fp32 (torch layout).
  * (Conv2d: stride_t = 1.  The NCHW-flatten Linear layers of models/networks.py:65,88 are expressed as
@@ -242,6 +247,60 @@ int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const*
                            const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay,
                            int zero_grads, void* stream);
 
+
+/* torch.optim.Adam (no amsgrad; train_BE.py:131, train_Style_GAN.py) as one multi-tensor kernel over fp32 masters:
+ *   g <- g + wd p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).
+ * t = `step` (1-based) or *step_dev when non-NULL (a device counter the caller advances with vp_philox_advance: CUDA-graph
+ * replay).  shadows / zero_grads as vp_rmsprop_step_shadow. */
+int vp_adam_step(void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, void* const* shadows,
+                 const int64_t* numel, int count, float lr, float beta1, float beta2, float eps, float weight_decay,
+                 int64_t step, const uint64_t* step_dev, int zero_grads, void* stream);
+
+/* ---- operators of models/blocks.py / models/network_Style_GAN.py around the contractions (channels-last, `dtype`) ----------
+ * All one-pass, HBM-bound kernels; forward / backward pairs as the autograd wrappers of vae_play_b200/functional_blocks.py
+ * call them.  rows = n*h*w pixels. */
+/* dst[r, dst_off : dst_off+nc] (+)= src[r, src_off : src_off+nc]: torch.cat on the channel axis (StyleUp, network_Style_GAN.py:62;
+ * Generator.encode :140; Discriminator :222) is two calls, its backward (a slice) one call each; accumulate != 0 adds. */
+int vp_copy_channels(const void* src, int src_c, int src_off, void* dst, int dst_c, int dst_off, int nc, int64_t rows,
+                     int dtype, int accumulate, void* stream);
+/* AddCoords (blocks.py:97-112): out[..., :c] = x, out[..., c] = column index, out[..., c+1] = row index
+ * (normalize != 0: (i / extent - 0.5) / 0.5).  out has c + 2 channels.  Backward = vp_copy_channels of the first c. */
+int vp_add_coords(const void* x, void* out, int dtype, int64_t n, int h, int w, int c, int normalize, void* stream);
+/* F.interpolate(scale_factor=2, mode='bilinear') (align_corners=False; blocks.py:145): y [n,2h,2w,c]; bwd is the exact adjoint */
+int vp_upsample2x_fwd(const void* x, void* y, int dtype, int64_t n, int h, int w, int c, void* stream);
+int vp_upsample2x_bwd(const void* dy, void* dx, int dtype, int64_t n, int h, int w, int c, void* stream);
+/* nn.AdaptiveAvgPool2d((oh, ow)) (SCSEBlock blocks.py:56; networks_BE_GAN.py:99; networks_BP.py:53): y [n,oh,ow,c] */
+int vp_avgpool_fwd(const void* x, void* y, int dtype, int64_t n, int h, int w, int c, int oh, int ow, void* stream);
+int vp_avgpool_bwd(const void* dy, void* dx, int dtype, int64_t n, int h, int w, int c, int oh, int ow, void* stream);
+/* SCSE gate (blocks.py:64-65): y = x * cse[n, c] + x * sse[n, pixel].  bwd: dx = dy * (cse + sse), dsse[pixel] = sum_c dy*x,
+ * dcse_f32[n, c] = sum_pixels dy*x (fp32, zeroed by the call). */
+int vp_scse_fwd(const void* x, const void* cse, const void* sse, void* y, int dtype, int64_t n, int64_t hw, int c, void* stream);
+int vp_scse_bwd(const void* x, const void* cse, const void* sse, const void* dy, void* dx, float* dcse_f32, void* dsse,
+                int dtype, int64_t n, int64_t hw, int c, void* stream);
+/* myConv2d blend (network_Style_GAN.py:78-79): y = a1 * (1 - label[n]) + a2 * label[n]; label fp32 [n]; per = elements per sample */
+int vp_blend_fwd(const void* a1, const void* a2, const float* label, void* y, int dtype, int64_t n, int64_t per, void* stream);
+int vp_blend_bwd(const void* dy, const float* label, void* d1, void* d2, int dtype, int64_t n, int64_t per, void* stream);
+/* softmax over the last axis of [rows, cols] (blocks.py:73,87; network_Style_GAN.py:228); bwd: dx = y * (dy - sum(dy*y)) */
+int vp_softmax_fwd(const void* x, void* y, int dtype, int64_t rows, int cols, void* stream);
+int vp_softmax_bwd(const void* y, const void* dy, void* dx, int dtype, int64_t rows, int cols, void* stream);
+/* torch.bmm of the attention block (blocks.py:86,90): C[b] (+)= op(A[b]) . op(B[b]), C [batch, m, n] dense; element (i, k)
+ * of op(A) at a[b*sa_b + i*sa_i + k*sa_k], element (k, j) of op(B) at b[b*sb_b + k*sb_k + j*sb_j]; fp32 accumulation. */
+int vp_bmm(const void* a, const void* b, void* c, int dtype, int batch, int m, int n, int k, int64_t sa_b, int64_t sa_i,
+           int64_t sa_k, int64_t sb_b, int64_t sb_k, int64_t sb_j, int accumulate, void* stream);
+/* y = gamma[0] * a + x (attention residual, blocks.py:93; gamma a device fp32 scalar) */
+int vp_scale_add(const float* gamma, const void* a, const void* x, void* y, int dtype, int64_t n, void* stream);
+/* acc[0] = sum(a * b) in double (zeroed by the call): the gradient of gamma */
+int vp_dot(const void* a, const void* b, double* acc, int dtype, int64_t n, void* stream);
+/* compute_dice_loss on probabilities (tools/ops.py:12-19): 1 - mean_b (2 sum(p t) + smooth) / (sum p + sum t + smooth).
+ * acc: double [rows][3] (zeroed by the call, kept for the backward); counter u32[1] zero before first use; loss fp32[1]. */
+int vp_dice_fwd(const float* p, const float* t, int64_t rows, int64_t per, float smooth, double* acc, unsigned int* counter,
+                float* loss, void* stream);
+int vp_dice_bwd(const float* t, int64_t rows, int64_t per, float smooth, const double* acc, const float* gscale, float* dp,
+                void* stream);
+/* |depthwise 3x3 edge filter| of edge_loss (tools/ops.py:187-211): e = |conv(x, [[-1,-1,-1],[-1,8,-1],[-1,-1,-1]] / 8)|, zero
+ * padding, single-channel fp32 maps [n, h, w]; sign (nullable) receives the sign of the response for the backward. */
+int vp_edge_fwd(const float* x, float* e, float* sign_or_null, int64_t n, int h, int w, void* stream);
+int vp_edge_bwd(const float* de, const float* sign, float* dx, int64_t n, int h, int w, void* stream);
 
 /* number of kernels this library has launched in this process (the bench's gpu_launches claim) */
 uint64_t vp_launch_count(void);

@@ -126,17 +126,18 @@ def run_reference(networks, dtype, seed=0, b=4, img=64, z=128):
     return out, grads
 
 
-def main():
+def main(batch=4):
     import torch
     from oracle.gen_golden import import_reference
     networks, _, _ = import_reference()
-    out64, g64 = run_reference(networks, torch.float64)
-    out32, g32 = run_reference(networks, torch.float32)
+    out64, g64 = run_reference(networks, torch.float64, b=batch)
+    out32, g32 = run_reference(networks, torch.float32, b=batch)
     res = dict(out64)
     dev_keys, dev_vals = [], []
     for k, g in g64.items():
-        res["grad/" + k] = g if g.size <= FULL_LIMIT else digest(g)
-        res["gradfull/" + k] = np.array([g.size <= FULL_LIMIT])
+        full = g.size <= (FULL_LIMIT if batch <= 4 else 256)
+        res["grad/" + k] = g if full else digest(g)
+        res["gradfull/" + k] = np.array([full])
         a, b = g32[k], g
         dev_keys.append(k)
         dev_vals.append(float(np.abs(a - b).max() / (np.abs(b).max() + 1e-300)))
@@ -145,12 +146,13 @@ def main():
         dev_vals.append(float(np.abs(out32[k] - out64[k]).max() / (np.abs(out64[k]).max() + 1e-300)))
     res["ref_fp32_dev_keys"] = np.array(dev_keys)
     res["ref_fp32_dev_vals"] = np.array(dev_vals)
-    res["meta"] = np.array([64, 4, 128, 0])
-    path = os.path.join(ROOT, "tests", "golden", "vaegan64_b4.npz")
+    res["meta"] = np.array([64, batch, 128, 0])
+    path = os.path.join(ROOT, "tests", "golden", f"vaegan64_b{batch}.npz")
     np.savez_compressed(path, **res)
     print("wrote", path, os.path.getsize(path), "bytes;", len(g64), "gradients; worst fp32 deviation of the reference:",
           max(dev_vals), dev_keys[int(np.argmax(dev_vals))])
 
 
 if __name__ == "__main__":
-    main()
+    main(4)
+    main(16)      # bf16 fixture: BatchNorm1d over 16 / 48 samples instead of 4 / 12

@@ -1,0 +1,168 @@
+"""GPU parity of the block-level operators and the Style_GAN modules against
+tests/golden/blocks.npz, written by oracle/gen_golden_blocks.py from the UNMODIFIED reference modules in float64.
+
+Each case: the mirror module (same class name / state_dict keys) with the parameters ``synth_state`` draws from the
+state_dict shapes, the fixture's inputs, forward through the reference-facing NCHW fp32 API, backward of sum(y * probe).
+fp32 check mode: every stored tensor to max(2e-5, 3 x the reference's own fp32 deviation).  bf16 mode: outputs to 3e-2,
+gradients loosely (the tiny fixtures put whole channels on ReLU / InstanceNorm boundaries).  Run with ``pytest -m gpu``.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle.gen_golden_blocks import digest, hash_name, synth_input, synth_state
+from tests.util import load, rel, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def vp():
+    import vae_play_b200
+    return vae_play_b200
+
+
+def npy(t):
+    return t.detach().float().cpu().numpy().astype(np.float64)
+
+
+def mirror_cases():
+    import vae_play_b200.functional as VF
+    import vae_play_b200.functional_blocks as VB
+    from vae_play_b200.models import blocks as B
+    from vae_play_b200.models import network_Style_GAN as S
+
+    class _Fn(torch.nn.Module):
+        def __init__(self, fn):
+            super().__init__()
+            self.fn = fn
+
+    def lab(n, dev):
+        return torch.tensor([1.0, 0.0, 1.0][:n], device=dev)
+
+    def tgt(name, shape, dev):
+        return (torch.from_numpy(synth_input(name, shape)) > 0).float().to(dev)
+
+    cl = lambda f: (lambda m, x: VF.from_channels_last(f(VF.to_channels_last(x))))
+    return {
+        "scse": (lambda: B.SCSEBlock(64, 4), [("x", (2, 64, 6, 5))], lambda m, x: m(x)),
+        "attn": (lambda: B.SelfAttentionBlock(16), [("x", (2, 16, 5, 4))], lambda m, x: m(x)),
+        "addcoords": (lambda: B.AddCoords(False), [("x", (2, 3, 4, 5))], lambda m, x: m(x)),
+        "addcoords_norm": (lambda: B.AddCoords(True), [("x", (2, 3, 4, 5))], lambda m, x: m(x)),
+        "up": (lambda: B.Up(6, 8, if_add_coord=True), [("x", (3, 6, 5, 4))], lambda m, x: m(x)),
+        "down": (lambda: B.Down(5, 8, 3, True), [("x", (2, 5, 8, 6))], lambda m, x: m(x)),
+        "styleup": (lambda: S.StyleUp(64, 64), [("x", (2, 64, 4, 4)), ("skip", (2, 64, 8, 8))], lambda m, x, s: m(x, s)),
+        "myconv": (lambda: S.myConv2d(4, 8, 4, 2, bn="instance"), [("x", (3, 4, 8, 8))], lambda m, x: m(x, lab(3, x.device).reshape(3, 1, 1, 1))),
+        "generator": (lambda: S.Generator(32, 16), [("x", (2, 3, 32, 32)), ("style", (2, 16))], lambda m, x, s: m(x, s, lab(2, x.device))),
+        "styleenc": (lambda: S.StyleEncoder(16, 32), [("x", (2, 3, 32, 32))], lambda m, x: torch.cat(m(x), dim=1)),
+        "sdisc": (lambda: S.Discriminator(32, 3), [("x", (2, 3, 32, 32)), ("xc", (2, 3, 32, 32))], lambda m, x, xc: torch.cat(m(x, xc, None), dim=1)),
+        "avgpool4": (lambda: torch.nn.Identity(), [("x", (2, 8, 9, 10))], cl(lambda a: VB.adaptive_avgpool(a, 4, 4))),
+        "bilinear": (lambda: torch.nn.Identity(), [("x", (2, 3, 5, 7))], cl(VB.upsample2x)),
+        "dice": (lambda: torch.nn.Identity(), [("p", (3, 1, 8, 8))],
+                 lambda m, p: VB.dice_loss(VB.sigmoid(p), tgt("dice/t", (3, 1, 8, 8), p.device)).reshape(1)),
+        "edge": (lambda: torch.nn.Identity(), [("p", (2, 1, 9, 8))],
+                 lambda m, p: VB.edge_loss(VB.sigmoid(p), tgt("edge/t", (2, 1, 9, 8), p.device)).reshape(1)),
+    }
+
+
+CASES = ["scse", "attn", "addcoords", "addcoords_norm", "up", "down", "styleup", "myconv", "generator", "styleenc", "sdisc", "avgpool4",
+         "bilinear", "dice", "edge"]
+
+
+def run_mirror(vp, name, prec):
+    import vae_play_b200.functional as VF
+    vp.set_precision(prec)
+    vp.set_engine("auto")
+    VF.set_grad_sinks({})
+    build, inputs, fwd = mirror_cases()[name]
+    torch.manual_seed(0)
+    m = build()
+    m.load_state_dict(synth_state(m, hash_name(name) % 1000), strict=False)
+    m = m.cuda().train()
+    xs = [torch.from_numpy(synth_input(f"{name}/{nm}", shp)).cuda().requires_grad_(True) for nm, shp in inputs]
+    y = fwd(m, *xs)
+    probe = torch.from_numpy(synth_input(f"{name}/probe", tuple(y.shape))).cuda()
+    (y.float() * probe).sum().backward()
+    out = {"y": npy(y)}
+    for (nm, _), x in zip(inputs, xs):
+        out["d" + nm] = npy(x.grad)
+    for k, p in m.named_parameters():
+        if p.grad is not None:
+            out["g/" + k] = npy(p.grad)
+    return out
+
+
+def deviation(got, g, key):
+    want = g[key]
+    if bool(g["full/" + key][0]):
+        scale = np.abs(want).max()
+        return (float(np.abs(got.reshape(want.shape) - want).max() / scale) if scale > 1e-10 else None), float(np.abs(got).max())
+    d = digest(got)
+    return float(max(np.abs(d[3:] - want[3:]).max() / want[2], abs(d[1] - want[1]) / want[1])), float(np.abs(got).max())
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_blocks_golden_fp32(vp, name):
+    g = load("blocks.npz")
+    dev = dict(zip([str(k) for k in g["ref_fp32_dev_keys"]], [float(v) for v in g["ref_fp32_dev_vals"]]))
+    try:
+        out = run_mirror(vp, name, "fp32")
+        want_keys = [k[len(name) + 1:] for k in g.files if k.startswith(name + "/")]
+        assert sorted(want_keys) == sorted(out.keys()), (sorted(set(want_keys) ^ set(out.keys())))
+        bad = []
+        for k, got in out.items():
+            r, mag = deviation(got, g, f"{name}/{k}")
+            if r is None:          # the true gradient is identically zero (a bias in front of InstanceNorm): the reference holds round-off
+                assert mag < 1e-4, (k, mag)
+                continue
+            t = max(2e-5, 3 * dev[f"{name}/{k}"])
+            if r >= t:
+                bad.append((k, r, t))
+        assert not bad, "\n".join(f"{name}/{k}: rel {r:.3e} >= {t:.2e}" for k, r, t in bad)
+    finally:
+        vp.set_precision("bf16")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_blocks_golden_bf16(vp, name):
+    g = load("blocks.npz")
+    out = run_mirror(vp, name, "bf16")
+    r, _ = deviation(out["y"], g, f"{name}/y")
+    assert r < 3e-2, f"{name}/y: rel {r:.3e}"
+    # gradients: finite, right magnitude (l2 within 35 %); linear cases tight
+    linear = name in ("addcoords", "addcoords_norm", "avgpool4", "bilinear", "dice", "edge")
+    for k, got in out.items():
+        if k == "y":
+            continue
+        assert np.isfinite(got).all(), k
+        want = g[f"{name}/{k}"]
+        full = bool(g["full/" + f"{name}/{k}"][0])
+        if full and np.abs(want).max() < 1e-10:
+            continue
+        if full:
+            r2 = rel_l2(got.reshape(want.shape), want)
+        else:
+            r2 = abs(digest(got)[1] - want[1]) / want[1]
+        assert r2 < (2e-2 if linear else 0.35), f"{name}/{k}: l2 deviation {r2:.3e}"
+
+
+def test_fused_adam_matches_torch(vp):
+    """FusedAdam == torch.optim.Adam (the optimiser of train_BE.py:131 / train_Style_GAN.py) step for step, including the bf16
+    operand copies and gradient clearing of the fused kernel."""
+    from vae_play_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    shapes = [(64, 64, 3, 3), (128,), (1000, 37), (5,)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    for wd, betas in ((0.0, (0.9, 0.999)), (1e-2, (0.5, 0.9))):
+        a = FusedAdam(ps, lr=2e-3, betas=betas, eps=1e-8, weight_decay=wd)
+        b = torch.optim.Adam(qs, lr=2e-3, betas=betas, eps=1e-8, weight_decay=wd)
+        for step in range(4):
+            for p, q in zip(ps, qs):
+                gr = torch.randn_like(p)
+                p.grad = gr.clone()
+                q.grad = gr.clone()
+            a.step()
+            b.step()
+            for p, q in zip(ps, qs):
+                assert rel(npy(p), npy(q)) < 2e-6, (step, tuple(p.shape))

@@ -176,5 +176,33 @@ def test_bench_reference_arm_line():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "train_images_per_sec" and line["unit"] == "images/s"
     assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    # "reference": the unmodified reference modules vendored into the git-ignored oracle/_ref by oracle/build_ref.py
+    # (__graft_entry__.build() runs it where /root/reference exists); "port": oracle/vae_torch.py when they are absent
+    have_ref = os.path.exists(os.path.join(root, "oracle", "_ref", "models", "networks.py"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_reference_and_port_cpu_steps_agree():
+    """The unmodified reference modules (oracle/_ref, when vendored) and the line-by-line port give the same loss on the same
+    weights / batch / eps: the two possible CPU-baseline legs of bench.py time the same computation."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = os.path.join(root, "oracle", "_ref", "models", "networks.py")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref not vendored here (python oracle/build_ref.py needs /root/reference)")
+    import bench
+    from oracle import vae_numpy as vn
+    from oracle.vae_torch import VaeTorchPort
+    ref = bench._ReferenceCpuStep(bench._load_reference_modules(), 64, 1)
+    port = VaeTorchPort(vn.synth_vae_params(64, 128, 1, 1, 0), torch.float32)
+    x_np, eps_np = vn.synth_batch(4, 64, 1, 128, 0)
+    x, eps = torch.from_numpy(x_np), torch.from_numpy(eps_np)
+    orig = torch.Tensor.normal_
+    torch.Tensor.normal_ = lambda self, *a, **k: self.copy_(eps)
+    try:
+        l_ref = float(ref.step(x))
+    finally:
+        torch.Tensor.normal_ = orig
+    l_port = float(port.step(x, eps)[0])
+    assert abs(l_ref - l_port) / abs(l_port) < 1e-5

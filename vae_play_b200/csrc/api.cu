@@ -166,6 +166,14 @@ extern "C" int vp_set_workspace(void* ptr, size_t bytes) {
     return VP_OK;
 }
 
+/* Cap the number of SMs the persistent kernels size their grids for (0 = all): leaves SMs to a collective that runs next to
+ * them (data-parallel gradient exchange overlapped with the rest of backward).  Host-side setting read at launch time; a
+ * captured CUDA graph keeps the value it was captured with. */
+extern "C" int vp_set_sm_limit(int n) {
+    vp::set_sm_limit(n);
+    return VP_OK;
+}
+
 extern "C" int vp_device_arch(void) {
     int dev = 0, maj = 0, min = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return VP_ECUDA; }

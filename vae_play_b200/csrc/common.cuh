@@ -195,5 +195,7 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s);
 // stride-2 gather form with per-parity sub-lattice halos shared by the taps of a class; VP_EUNSUPPORTED otherwise
 int launch_tapgemm_gwin(const TapGemm& p, cudaStream_t s);
 bool tc_available();
+int num_sms();            // SMs persistent grids are sized for (device count, or the vp_set_sm_limit cap)
+void set_sm_limit(int n);
 
 }  // namespace vp

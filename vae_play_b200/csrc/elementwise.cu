@@ -624,6 +624,73 @@ extern "C" int vp_rmsprop_step_shadow(void* const* params, void* const* grads, v
     return VP_OK;
 }
 
+// ---- Adam (torch.optim.Adam without amsgrad; train_BE.py:131, train_Style_GAN.py) as ONE multi-tensor kernel --------------------
+namespace vp {
+namespace {
+struct AdamTable {
+    float* p[kOptMax];
+    const float* g[kOptMax];
+    float* m[kOptMax];
+    float* v[kOptMax];
+    bf16* sh[kOptMax];
+    int64_t n[kOptMax];
+};
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable t, float lr, float b1, float b2, float eps, float wd, int64_t step,
+                                                   const unsigned long long* __restrict__ step_dev, int zero_g) {
+    pdl_sync();
+    const int ti = blockIdx.y;
+    float* __restrict__ p = t.p[ti];
+    float* __restrict__ g = const_cast<float*>(t.g[ti]);
+    float* __restrict__ m = t.m[ti];
+    float* __restrict__ v = t.v[ti];
+    bf16* __restrict__ sh = t.sh[ti];
+    const int64_t n = t.n[ti];
+    const double tt = (double)(step_dev ? (int64_t)*step_dev : step);
+    const float bc1 = (float)(1.0 - pow((double)b1, tt)), bc2s = (float)sqrt(1.0 - pow((double)b2, tt));
+    const float step_size = lr / bc1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float pv = p[i];
+        const float gg = g[i] + wd * pv;
+        const float mn = b1 * m[i] + (1.f - b1) * gg;
+        const float vn = b2 * v[i] + (1.f - b2) * gg * gg;
+        m[i] = mn; v[i] = vn;
+        const float pn = pv - step_size * (mn / (sqrtf(vn) / bc2s + eps));
+        p[i] = pn;
+        if (zero_g) g[i] = 0.f;
+        if (sh) sh[i] = __float2bfloat16_rn(pn);
+    }
+}
+}  // namespace
+}  // namespace vp
+
+/* torch.optim.Adam (no amsgrad) over fp32 masters: m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ * p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps), g <- g + wd p first.  t = `step` (1-based), or *step_dev when
+ * non-NULL (a device counter the caller advances: CUDA-graph replay).  shadows / zero_grads as vp_rmsprop_step_shadow. */
+extern "C" int vp_adam_step(void* const* params, void* const* grads, void* const* exp_avg, void* const* exp_avg_sq, void* const* shadows,
+                            const int64_t* numel, int count, float lr, float beta1, float beta2, float eps, float weight_decay, int64_t step,
+                            const uint64_t* step_dev, int zero_grads, void* stream) {
+    VP_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && numel && count >= 0 && (step >= 1 || step_dev), "vp_adam_step: bad arguments");
+    for (int base = 0; base < count; base += kOptMax) {
+        AdamTable t;
+        const int mcount = count - base < kOptMax ? count - base : kOptMax;
+        int64_t nmax = 0;
+        for (int i = 0; i < mcount; ++i) {
+            t.p[i] = (float*)params[base + i]; t.g[i] = (const float*)grads[base + i];
+            t.m[i] = (float*)exp_avg[base + i]; t.v[i] = (float*)exp_avg_sq[base + i];
+            t.sh[i] = shadows ? (bf16*)shadows[base + i] : nullptr;
+            t.n[i] = numel[base + i];
+            nmax = numel[base + i] > nmax ? numel[base + i] : nmax;
+        }
+        int64_t bx = (nmax + 1023) / 1024;
+        if (bx > 148 * 2) bx = 148 * 2;
+        if (bx < 1) bx = 1;
+        launch_k(adam_kernel, dim3((unsigned)bx, (unsigned)mcount), dim3(256), 0, (cudaStream_t)stream, t, lr, beta1, beta2, eps, weight_decay, step,
+                 (const unsigned long long*)step_dev, zero_grads);
+        VP_CHECK_LAUNCH("vp_adam_step");
+    }
+    return VP_OK;
+}
+
 // ---- batched transpose (same dtype): dst[b][c][r] = src[b][r][c] ---------------------------------------------------------
 // The NCHW-flatten Linear layers (models/networks.py:65,74-75 and :88,110) see the 8x8 map in (c, y, x) order while the
 // activations are channels-last: a [B][64][C] <-> [B][C][64] transpose on either side lets them run as plain Linear layers

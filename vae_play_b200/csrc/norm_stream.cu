@@ -10,12 +10,22 @@
 namespace vp {
 namespace {
 
-constexpr int STAGES = 4;
-// one-tensor passes (stats, apply): 256 threads, 16 KB tiles, 2 CTAs/SM.  Two-tensor passes (the backward ones) do
-// ~3x the arithmetic per byte: 512 threads and 8 KB tiles per tensor so that two CTAs (1024 threads) fit an SM.
+#ifndef VP_NORM_STAGES
+#define VP_NORM_STAGES 4
+#endif
+// ring depth: 4 stages (6 measured no better: the two-tensor passes are issue-bound, not bound by bytes in flight)
+constexpr int STAGES = VP_NORM_STAGES;
+// one-tensor passes (stats, apply): 256 threads, 16 KB tiles, 2 CTAs/SM.  Two-tensor passes (the backward ones): 256 threads
+// and 8 KB tiles per tensor, three CTAs per SM -- each thread then owns 4 rows of a tile, which halves the per-tile overhead
+// (barrier wait, index arithmetic) per element against the 512-thread version (ncu: these passes are issue-bound, 0.7 warp
+// instructions per element; measured -20 us per step).
+#ifndef VP_NORM_TWO_NT
+#define VP_NORM_TWO_NT 256
+#endif
 template <int MODE> struct Cfg {
     static constexpr bool TWO = (MODE == 2 || MODE == 3);
-    static constexpr int NT = TWO ? 512 : 256;
+    static constexpr int NT = TWO ? VP_NORM_TWO_NT : 256;
+    static constexpr int CTAS = (TWO && VP_NORM_TWO_NT == 256) ? 3 : 2;
     static constexpr int TILE_BYTES = TWO ? 8 * 1024 : 16 * 1024;   // per tensor per stage
     static constexpr int V = TWO ? 4 : 8;   // channels per thread; the backward passes carry 8 per-channel vectors
 };
@@ -110,7 +120,7 @@ __device__ __forceinline__ float dact(float pre, int act, float slope) {
 }
 
 template <int MODE, typename T, bool RELU>
-__global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const StreamArgs p) {
+__global__ void __launch_bounds__(Cfg<MODE>::NT, Cfg<MODE>::CTAS) norm_stream_kernel(const StreamArgs p) {
     constexpr bool TWO = Cfg<MODE>::TWO;     // streams x and da
     constexpr int NT = Cfg<MODE>::NT;
     constexpr int TILE_BYTES = Cfg<MODE>::TILE_BYTES;
@@ -185,23 +195,28 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
         const int64_t tile = blockIdx.x + i * gridDim.x;
         const int64_t r0 = tile * p.rows_per_tile;
         const int nrows = (int)min((int64_t)p.rows_per_tile, p.rows - r0);
-        const T* xs = reinterpret_cast<const T*>(smem + s * STAGE_BYTES);
-        const T* ds = reinterpret_cast<const T*>(smem + s * STAGE_BYTES + TILE_BYTES);
+        // 32-bit offsets inside the tile, one pointer bump per row step: the streaming passes are issue-bound, not
+        // byte-bound (ncu: 0.7 warp instructions per element with 64-bit index arithmetic in the row loop)
+        const T* xs = reinterpret_cast<const T*>(smem + s * STAGE_BYTES) + (rl * C + cl);
+        const T* ds = reinterpret_cast<const T*>(smem + s * STAGE_BYTES + TILE_BYTES) + (rl * C + cl);
+        T* outp = (MODE == M_APPLY || MODE == M_BWD_APPLY || MODE == M_BWD_REDUCE) && p.out
+                      ? reinterpret_cast<T*>(p.out) + ((r0 + rl) * C + cl) : nullptr;
+        const int rstep = rlanes * C;
         if (active) {
-#pragma unroll 2
-            for (int r = rl; r < nrows; r += rlanes) {
+#pragma unroll 4
+            for (int r = rl; r < nrows; r += rlanes, xs += rstep, ds += rstep, outp += rstep) {
                 float v[V];
-                SV<T, V>::ld(xs + (int64_t)r * C + cl, v);
+                SV<T, V>::ld(xs, v);
                 if (MODE == M_STATS) {
 #pragma unroll
                     for (int j = 0; j < V; ++j) { a[j] += v[j]; b[j] = fmaf(v[j], v[j], b[j]); }
                 } else if (MODE == M_APPLY) {
 #pragma unroll
                     for (int j = 0; j < V; ++j) { const float t = fmaf(v[j], sc[j], sh[j]); v[j] = RELU ? fmaxf(t, 0.f) : act_fwd(t, p.act, p.slope); }
-                    SV<T, V>::st(reinterpret_cast<T*>(p.out) + (r0 + r) * C + cl, v);
+                    SV<T, V>::st(outp, v);
                 } else {
                     float d[V];
-                    SV<T, V>::ld(ds + (int64_t)r * C + cl, d);
+                    SV<T, V>::ld(ds, d);
                     if (MODE == M_BWD_REDUCE) {
                         // b accumulates sum d*(x - mean); the common factor invstd is applied once, after the loop
 #pragma unroll
@@ -211,7 +226,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
                             a[j] += d[j];
                             b[j] = fmaf(d[j], v[j] - mu[j], b[j]);
                         }
-                        if (p.out) SV<T, V>::st(reinterpret_cast<T*>(p.out) + (r0 + r) * C + cl, d);
+                        if (p.out) SV<T, V>::st(outp, d);
                     } else {
                         // dx = scale*(dd - m1 - xhat*m2) = scale*dd + (ka*x + kb), ka/kb per channel (held in m1/m2 from here on)
 #pragma unroll
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::NT, 2) norm_stream_kernel(const Str
                             const float dd = RELU ? (pre > 0.f ? d[j] : 0.f) : d[j] * act_grad(pre, p.act, p.slope);
                             d[j] = fmaf(sc[j], dd, fmaf(m1[j], v[j], m2[j]));
                         }
-                        SV<T, V>::st(reinterpret_cast<T*>(p.out) + (r0 + r) * C + cl, d);
+                        SV<T, V>::st(outp, d);
                     }
                 }
             }
@@ -260,8 +275,8 @@ int launch_stream(const StreamArgs& a, cudaStream_t s) {
         }
         attr = true;
     }
-    const int ctas_per_sm = 2;                     // ~97 KB / ~82 KB of smem per CTA
-    int64_t grid = 148 * ctas_per_sm;
+    const int ctas_per_sm = Cfg<MODE>::CTAS;       // ~97 KB / ~82 KB of smem per CTA
+    int64_t grid = (int64_t)num_sms() * ctas_per_sm;
     if (grid > a.ntiles) grid = a.ntiles;
     launch_k(norm_stream_kernel<MODE, T, RELU>, dim3((unsigned)grid), dim3(NT), smem, s, a);
     VP_CHECK_LAUNCH("norm_stream");

@@ -72,6 +72,10 @@ int encode_out_map(CUtensorMap* m, void* D, int N, int hd, int wd, int n, int ds
 int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 
+// SMs the persistent kernels size their grids for: the device's count, or the caller's cap (vp_set_sm_limit) while a
+// collective runs next to them -- a persistent grid must be fully resident, so the SMs the collective's CTAs hold are left out.
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -80,7 +84,7 @@ int num_sms() {
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
     }
-    return n;
+    return (g_sm_limit > 0 && g_sm_limit < n) ? g_sm_limit : n;
 }
 
 

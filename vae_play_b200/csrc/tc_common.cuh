@@ -19,7 +19,6 @@ int launch_splitk_finish(const float* ws, void* D, const float* bias, int act, f
 int encode_out_map(CUtensorMap* m, void* D, int N, int hd, int wd, int n, int ds, int doy, int dox, int bw, int bh, int bb);
 int pow2_floor(int v);
 int pow2_ceil(int v);
-int num_sms();
 
 namespace tc {
 

@@ -509,6 +509,10 @@ class _FusedLayerFn(torch.autograd.Function):
                 if dt != torch.float32:
                     raise _lib.VaePlayError("gradient into the pre-norm output is supported in fp32 mode only")
                 _lib.call("vp_axpy", 1.0, _ptr(dy_extra.contiguous()), _ptr(dy), dy.numel(), _stream())
+            if ctx.has_bias:
+                # a bias directly in front of Batch/InstanceNorm (StyleUp's ConvTranspose2d, network_Style_GAN.py:49-50) is
+                # removed by the mean subtraction: its gradient is identically zero (the reference computes round-off noise)
+                dbias = torch.zeros(cc if norm.kind == "batch" else c, dtype=torch.float32, device=dev)
         dw = layer.wgrad(x, dy, weight)
         dx = layer.dgrad(dy, weight, ctx.x_shape) if ctx.needs_input_grad[0] else None
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
