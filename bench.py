@@ -230,14 +230,23 @@ class StepRunner:
             # the kernel also refreshes the bf16 operand copies of the weights and clears each gradient after use, so the
             # next step's weight-gradient kernels accumulate into known-zero persistent slots (no cast pass, no memsets)
             opt = FusedRMSprop(params, lr=1e-4, zero_grads=True)
-        buckets = GradBuckets(params, world, overlap=not use_graph) if world > 1 else None
+        wire_bf16 = world > 1 and args.grad_wire == "bf16" and not args.torch_optim
+        buckets = GradBuckets(params, world, overlap=not use_graph, wire_dtype=torch.bfloat16 if wire_bf16 else None) if world > 1 else None
         if buckets is None and not args.torch_optim:
             VF.persistent_grads(params)
+        if wire_bf16:
+            # bf16 on the wire: pack() converts + clears the fp32 buckets, the optimiser reads the reduced bf16 values directly
+            views = {}
+            for bi in range(len(buckets.buckets)):
+                views.update(buckets.wire_views(bi))
+            opt = FusedRMSprop(params, lr=1e-4, zero_grads=False, wire=views)
         # data parallel: one optimiser per gradient bucket, so that the update of bucket i runs while NCCL reduces bucket i+1
         bucket_opts = None
         if buckets is not None and not args.torch_optim and not args.no_bucket_pipeline:
             from vae_play_b200.optim import FusedRMSprop
-            bucket_opts = [FusedRMSprop(b["params"], lr=1e-4, zero_grads=True) for b in buckets.buckets]
+            bucket_opts = [FusedRMSprop(b["params"], lr=1e-4, zero_grads=not wire_bf16, wire=buckets.wire_views(bi))
+                           for bi, b in enumerate(buckets.buckets)]
+        self.wire = "bf16" if wire_bf16 else "fp32"
         torch.manual_seed(1234 + rank)
         self.x_host = torch.rand(B, cin, img, img).pin_memory()
         self.x_dev = self.x_host.to(dev)
@@ -315,20 +324,26 @@ class StepRunner:
             if split_backward:
                 early = buckets.buckets_within(stage1_params)
                 graph_a2 = torch.cuda.CUDAGraph()
+                late = [i for i in range(len(buckets.buckets)) if i not in early]
                 with torch.cuda.graph(graph_a):
                     static_loss = fwd_bwd_stage1(static_x)
+                    buckets.pack(early)
                 nsm = torch.cuda.get_device_properties(dev).multi_processor_count
                 _lib.call("vp_set_sm_limit", max(nsm - args.sm_reserve, nsm // 2))
                 try:
                     with torch.cuda.graph(graph_a2, pool=graph_a.pool()):
                         bwd_stage2()
+                        buckets.pack(late)
                 finally:
                     _lib.call("vp_set_sm_limit", 0)
             else:
                 with torch.cuda.graph(graph_a):
                     static_loss = fwd_bwd(static_x)
+                    if buckets is not None:
+                        buckets.pack()
             launches_per_replay = _lib.launch_count() - l0
             if buckets is not None:
+                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)
                 buckets.allreduce(check_missing=False)
             l0 = _lib.launch_count()
             if bucket_opts is not None:
@@ -353,15 +368,16 @@ class StepRunner:
                 static_x.copy_(x, non_blocking=True)
             graph_a.replay()
             if graph_a2 is not None:
-                buckets.allreduce_subset(early)      # overlaps the encoder-conv backward below
+                buckets.allreduce_subset(early, pre_packed=True)      # overlaps the encoder-conv backward below
                 graph_a2.replay()
             if bucket_opts is not None:
-                buckets.allreduce_subset(range(len(buckets.buckets)))      # all buckets queued on NCCL's stream, in order
+                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)      # all buckets queued on NCCL's stream, in order
                 for bi, gb_ in enumerate(graph_bs):
                     buckets.wait_bucket(bi)                                 # update of bucket bi overlaps the all-reduce of bi+1
                     gb_.replay()
                 return static_loss
             if buckets is not None:
+                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)
                 buckets.allreduce(check_missing=False)
             graph_b.replay()
             return static_loss
@@ -429,6 +445,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: the driver reads ONE JSON line
         try:
             # NCCL's kernels get a bounded number of CTAs (the SMs our persistent grids leave free while the exchange overlaps
             # backward) and a high-priority stream (their CTAs are placed first when SMs free up)
@@ -482,10 +499,10 @@ def run_ours(args):
                            timing=f"median of {args.repeats} timed regions of {args.steps} steps each (CUDA events, barrier + synchronize on both sides, max over ranks)",
                            cuda_graph=run.graph, pdl=os.environ.get("VP_PDL", "1") != "0",
                            allreduce=(None if world == 1 else
-                                      f"bucketed fp32 NCCL all-reduce (<= {args.sm_reserve} CTAs, high-priority stream); the decoder / fc / heads buckets "
+                                      f"bucketed NCCL all-reduce, {run.wire} on the wire (<= {args.sm_reserve} CTAs, high-priority stream); the decoder / fc / heads buckets "
                                       f"(94 % of the bytes) run next to the encoder-conv backward graph, whose persistent grids are capped at "
                                       f"#SMs - {args.sm_reserve}; per-bucket optimiser graphs start as each bucket completes"
-                                      if run.split else "bucketed NCCL all-reduce between backward and optimiser")),
+                                      if run.split else f"bucketed NCCL all-reduce ({run.wire} on the wire) between backward and optimiser")),
             "clocks": clocks,
             "region_ms_per_step": [round(r / args.steps, 4) for r in regions],
             "e2e": {"value": round(e2e_ips, 1), "unit": "images/s", "h2d_bytes_per_step": run.x_host.numel() * 4,
@@ -784,7 +801,9 @@ def main():
     ap.add_argument("--no-bucket-pipeline", action="store_true", help="data parallel: one optimiser launch after all all-reduces")
     ap.add_argument("--no-split-backward", action="store_true",
                     help="data parallel: do NOT cut the backward graph at the encoder conv stack (all-reduce fully exposed between backward and optimiser)")
-    ap.add_argument("--sm-reserve", type=int, default=16, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
+    ap.add_argument("--grad-wire", default="bf16", choices=["bf16", "fp32"],
+                    help="data parallel: gradient buckets cross NVLink in bf16 (half the bytes; the optimiser reads the reduced bf16 values) or fp32")
+    ap.add_argument("--sm-reserve", type=int, default=32, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -247,6 +247,40 @@ int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const*
                            const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay,
                            int zero_grads, void* stream);
 
+/* ---- channel padding: layers whose channel counts are not multiples of 64 on the tcgen05 kernels ---------------------------
+ * (blocks.Conv2d with 3 / 4 / 6 / 16 / 32 ... channels; the VAE-GAN discriminator's 1 -> 32 -> 64 layers)
+ * The activation is copied into a zero-padded [rows, cp] tensor, the weight into a zero-padded bf16 channels-last panel
+ * [d0p][taps][d1p] (d0 / d1 = the weight's first two axes, so the panel is what vp_conv_*_cl expect for the padded layer), the
+ * vp_conv_*_cl kernels run on the padded geometry, and the fp32 weight gradient is gathered back into the parameter's layout.
+ * Zero channels contribute exact zeros: results equal the unpadded contraction. */
+int vp_pad_channels(const void* src, int c, void* dst, int cp, int64_t rows, int dtype, void* stream);
+int vp_pad_weight_cl(const float* w, void* dst_bf16, int d0, int d1, int taps, int64_t s0, int64_t s1, int64_t st, int d0p,
+                     int d1p, void* stream);
+int vp_unpad_wgrad_cl(const float* dwp, float* dw, int d0, int d1, int taps, int64_t s0, int64_t s1, int64_t st, int d1p,
+                      void* stream);
+
+/* Data-parallel exchange in bf16: dst_bf16[i] = src[i] (round to nearest even) and, with zero_src != 0, src[i] = 0 in the same
+ * pass (the fp32 gradient bucket is cleared for the next step's accumulating weight-gradient kernels).  n % 4 == 0, 16-byte
+ * aligned.  After the all-reduce, vp_rmsprop_step_wire reads the bf16 buffers directly. */
+int vp_pack_grads_bf16(float* src, void* dst_bf16, int64_t n, int zero_src, void* stream);
+int vp_rmsprop_step_wire(void* const* params, void* const* grads, void* const* sq, void* const* shadows,
+                         const void* const* wire_grads, const int64_t* numel, int count, float lr, float alpha, float eps,
+                         float weight_decay, int zero_grads, void* stream);
+
+/* ---- the remaining terms of VaeGan.loss / the train.py step (models/networks.py:264-281, train.py:62-67), fp32 ------------ */
+/* out[r] = 0.5 * sum_j (a[r,j] - b[r,j])^2 (feature MSE between discriminator layers, :273); bwd: da = g[r] (a - b), db = -da */
+int vp_feature_mse_fwd(const float* a, const float* b, float* out, int64_t rows, int64_t cols, void* stream);
+int vp_feature_mse_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t rows, int64_t cols,
+                       void* stream);
+/* out = -log(sign * p + offset): (1, 1e-3) for -log(D(x) + 1e-3), (-1, 1 + 1e-3) for -log(1 - D(.) + 1e-3) (:276-278) */
+int vp_neglog_fwd(const float* p, float* out, int64_t n, float sign, float offset, void* stream);
+int vp_neglog_bwd(const float* p, const float* g, float* dp, int64_t n, float sign, float offset, void* stream);
+/* out[0] = scale * sum smooth_l1(a - b) with beta = 1 (F.smooth_l1_loss(reduction="sum") / B, :279); g: device scalar or NULL */
+int vp_smooth_l1_sum_fwd(const float* a, const float* b, float* out, int64_t n, float scale, void* stream);
+int vp_smooth_l1_sum_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t n, float scale,
+                         void* stream);
+/* kl[r] = -0.5 * sum_j(-exp(lv) - mu^2 + lv + 1) (:270); backward = vp_reparam_kl_bwd with dz = NULL */
+int vp_kl_fwd(const float* mu, const float* logvar, int64_t ld, float* kl, int64_t rows, int zdim, void* stream);
 
 /* torch.optim.Adam (no amsgrad; train_BE.py:131, train_Style_GAN.py) as one multi-tensor kernel over fp32 masters:
  *   g <- g + wd p;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).

@@ -839,3 +839,41 @@ def test_discriminator_golden(vp, prec):
             assert rel_l2(npy(d.fc[3].weight.grad), want["grad_fc3"]) < 0.1
     finally:
         vp.set_precision("bf16")
+
+
+def test_bf16_wire_pack_and_optimizer(vp):
+    """Data-parallel exchange in bf16: GradBuckets.pack() writes bf16(grad) into the wire buffer and clears the fp32 slots in
+    the same pass; FusedRMSprop(wire=...) then gives exactly torch.optim.RMSprop on the bf16-rounded gradients."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200.optim import FusedRMSprop
+    from vae_play_b200.parallel import GradBuckets
+    torch.manual_seed(0)
+    shapes = [(64, 64, 3, 3), (130,), (257, 33), (7,)]
+    ps = [torch.nn.Parameter(torch.randn(*s, device="cuda")) for s in shapes]
+    ps[0].data = ps[0].data.contiguous(memory_format=torch.channels_last)
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    gb = GradBuckets(ps, world_size=1, bucket_mb=0.05, overlap=False, wire_dtype=torch.bfloat16)
+    try:
+        assert len(gb.buckets) >= 2
+        views = {}
+        for bi in range(len(gb.buckets)):
+            views.update(gb.wire_views(bi))
+        opt = FusedRMSprop(ps, lr=1e-3, zero_grads=False, wire=views)
+        ref = torch.optim.RMSprop(qs, lr=1e-3)
+        for step in range(3):
+            grads = [torch.randn_like(p) for p in ps]
+            for p, q, g in zip(ps, qs, grads):
+                slot = gb.slot[id(p)][1]
+                slot.copy_(g)
+                p.grad = slot
+                q.grad = g.to(torch.bfloat16).float()
+            gb.pack()
+            for p, g in zip(ps, grads):
+                assert torch.equal(views[id(p)].float(), g.to(torch.bfloat16).float())         # bf16(grad), element for element (strided views too)
+                assert float(p.grad.abs().max()) == 0.0                                       # fp32 slot cleared by the same pass
+            opt.step()
+            ref.step()
+            for p, q in zip(ps, qs):
+                close(npy(p), npy(q), 1e-6, f"RMSprop on wire gradients, step {step}")
+    finally:
+        gb.remove()

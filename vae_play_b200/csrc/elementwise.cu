@@ -273,6 +273,55 @@ __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD*
         Cvt<TD>::st(d + i, Cvt<TS>::ld(s + i));
 }
 
+// ---- channel padding: layers whose channel counts are not multiples of 64 run on the 64-multiple tcgen05 kernels -------------
+// dst[r, j] = j < c ? src[r, j] : 0   (activations, channels-last rows)
+template <typename T>
+__global__ void __launch_bounds__(256) pad_channels_kernel(const T* __restrict__ src, int c, T* __restrict__ dst, int cp, int64_t rows) {
+    pdl_sync();
+    const int64_t total = rows * cp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cp;
+        const int j = (int)(i - r * cp);
+        Cvt<T>::st(dst + i, j < c ? Cvt<T>::ld(src + r * c + j) : 0.f);
+    }
+}
+// weight [d0][d1][taps] with element strides (s0, s1, st)  ->  bf16 [d0p][taps][d1p] (channels-last element order), zero padded
+__global__ void __launch_bounds__(256) pad_weight_cl_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int d0, int d1, int taps, int64_t s0,
+                                                            int64_t s1, int64_t st, int d0p, int d1p) {
+    pdl_sync();
+    const int64_t total = (int64_t)d0p * taps * d1p;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int i1 = (int)(i % d1p);
+        const int t = (int)((i / d1p) % taps);
+        const int i0 = (int)(i / ((int64_t)d1p * taps));
+        dst[i] = __float2bfloat16_rn((i0 < d0 && i1 < d1) ? w[i0 * s0 + i1 * s1 + t * st] : 0.f);
+    }
+}
+// the inverse gather for the fp32 weight gradient: dw[i0*s0 + i1*s1 + t*st] = dwp[(i0*taps + t)*d1p + i1]
+__global__ void __launch_bounds__(256) unpad_wgrad_cl_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int d0, int d1, int taps, int64_t s0,
+                                                             int64_t s1, int64_t st, int d1p) {
+    pdl_sync();
+    const int64_t total = (int64_t)d0 * taps * d1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int i1 = (int)(i % d1);
+        const int t = (int)((i / d1) % taps);
+        const int i0 = (int)(i / ((int64_t)d1 * taps));
+        dw[i0 * s0 + i1 * s1 + t * st] = dwp[((int64_t)i0 * taps + t) * d1p + i1];
+    }
+}
+
+// dst (bf16) = src (fp32); src <- 0 when zero_src: the gradient bucket goes onto the wire in bf16 and is cleared for the next step
+// in the same pass (n a multiple of 4, 16-byte aligned: bucket slots are)
+__global__ void __launch_bounds__(256) pack_grads_kernel(float* __restrict__ src, bf16* __restrict__ dst, int64_t n4, int zero_src) {
+    pdl_sync();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4*>(src)[i];
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+        reinterpret_cast<uint2*>(dst)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        if (zero_src) reinterpret_cast<float4*>(src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
 __global__ void __launch_bounds__(256) axpy_kernel(float alpha, const float* __restrict__ a, float* __restrict__ sum, int64_t n) {
     pdl_sync();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -484,6 +533,41 @@ extern "C" int vp_cast(const void* src, int sd, void* dst, int dd, int64_t n, vo
     return VP_OK;
 }
 
+extern "C" int vp_pad_channels(const void* src, int c, void* dst, int cp, int64_t rows, int dtype, void* stream) {
+    VP_CHECK_ARG(src && dst && c > 0 && cp >= c && rows >= 0, "vp_pad_channels: bad arguments");
+    VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_pad_channels: bad dtype %d", dtype);
+    if (rows == 0) return VP_OK;
+    if (dtype == VP_F32) launch_k(pad_channels_kernel<float>, dim3(grid_for(rows * cp)), dim3(256), 0, (cudaStream_t)stream, (const float*)src, c, (float*)dst, cp, rows);
+    else launch_k(pad_channels_kernel<bf16>, dim3(grid_for(rows * cp)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)src, c, (bf16*)dst, cp, rows);
+    VP_CHECK_LAUNCH("vp_pad_channels");
+    return VP_OK;
+}
+
+extern "C" int vp_pad_weight_cl(const float* w, void* dst_bf16, int d0, int d1, int taps, int64_t s0, int64_t s1, int64_t st, int d0p, int d1p,
+                                void* stream) {
+    VP_CHECK_ARG(w && dst_bf16 && d0 > 0 && d1 > 0 && taps > 0 && d0p >= d0 && d1p >= d1, "vp_pad_weight_cl: bad arguments");
+    launch_k(pad_weight_cl_kernel, dim3(grid_for((int64_t)d0p * taps * d1p)), dim3(256), 0, (cudaStream_t)stream, w, (bf16*)dst_bf16, d0, d1, taps, s0, s1,
+             st, d0p, d1p);
+    VP_CHECK_LAUNCH("vp_pad_weight_cl");
+    return VP_OK;
+}
+
+extern "C" int vp_unpad_wgrad_cl(const float* dwp, float* dw, int d0, int d1, int taps, int64_t s0, int64_t s1, int64_t st, int d1p, void* stream) {
+    VP_CHECK_ARG(dwp && dw && d0 > 0 && d1 > 0 && taps > 0 && d1p >= d1, "vp_unpad_wgrad_cl: bad arguments");
+    launch_k(unpad_wgrad_cl_kernel, dim3(grid_for((int64_t)d0 * taps * d1)), dim3(256), 0, (cudaStream_t)stream, dwp, dw, d0, d1, taps, s0, s1, st, d1p);
+    VP_CHECK_LAUNCH("vp_unpad_wgrad_cl");
+    return VP_OK;
+}
+
+extern "C" int vp_pack_grads_bf16(float* src, void* dst_bf16, int64_t n, int zero_src, void* stream) {
+    VP_CHECK_ARG(src && dst_bf16 && n >= 0 && (n & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst_bf16) & 15) == 0,
+                 "vp_pack_grads_bf16: n must be a multiple of 4 and the buffers 16-byte aligned");
+    if (n == 0) return VP_OK;
+    launch_k(pack_grads_kernel, dim3(grid_for(n / 4)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst_bf16, n / 4, zero_src);
+    VP_CHECK_LAUNCH("vp_pack_grads_bf16");
+    return VP_OK;
+}
+
 extern "C" int vp_axpy(float alpha, const float* a, float* sum, int64_t n, void* stream) {
     VP_CHECK_ARG(a && sum && n >= 0, "vp_axpy: bad arguments");
     if (n == 0) return VP_OK;
@@ -550,6 +634,7 @@ struct OptTable {
     const float* g[kOptMax];
     float* sq[kOptMax];
     bf16* sh[kOptMax];          // optional bf16 copy of the updated parameter (same element order), or null
+    const bf16* wire[kOptMax];  // optional: the gradient is read from this bf16 buffer (data-parallel wire format) instead of g
     int64_t n[kOptMax];
 };
 __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd, int zero_g) {
@@ -560,11 +645,18 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
     const float* __restrict__ g = t.g[ti];
     float* __restrict__ sq = t.sq[ti];
     const int64_t n = t.n[ti];
-    const int64_t n4 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)sq) & 15) == 0 && ((uintptr_t)sh & 7) == 0 ? n / 4 : 0;
+    const bf16* __restrict__ wire = t.wire[ti];
+    const int64_t n4 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)sq) & 15) == 0 && (((uintptr_t)sh | (uintptr_t)wire) & 7) == 0 ? n / 4 : 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pv = reinterpret_cast<float4*>(p)[i];
-        const float4 gv0 = reinterpret_cast<const float4*>(g)[i];
+        float4 gv0;
+        if (wire) {
+            const uint2 w2 = reinterpret_cast<const uint2*>(wire)[i];
+            gv0 = make_float4(__uint_as_float(w2.x << 16), __uint_as_float(w2.x & 0xffff0000u), __uint_as_float(w2.y << 16), __uint_as_float(w2.y & 0xffff0000u));
+        } else {
+            gv0 = reinterpret_cast<const float4*>(g)[i];
+        }
         float4 sv = reinterpret_cast<float4*>(sq)[i];
         float pe[4] = {pv.x, pv.y, pv.z, pv.w}, ge[4] = {gv0.x, gv0.y, gv0.z, gv0.w}, se[4] = {sv.x, sv.y, sv.z, sv.w};
 #pragma unroll
@@ -582,7 +674,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
         }
     }
     for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const float gg = g[i] + wd * p[i];
+        const float gg = (wire ? __bfloat162float(wire[i]) : g[i]) + wd * p[i];
         const float s2 = alpha * sq[i] + (1.f - alpha) * gg * gg;
         sq[i] = s2;
         const float pn = p[i] - lr * (gg / (sqrtf(s2) + eps));
@@ -602,8 +694,17 @@ extern "C" int vp_rmsprop_step(void* const* params, const void* const* grads, vo
     return vp_rmsprop_step_shadow(params, const_cast<void* const*>(grads), sq, nullptr, numel, count, lr, alpha, eps, weight_decay, 0, stream);
 }
 
+extern "C" int vp_rmsprop_step_wire(void* const* params, void* const* grads, void* const* sq, void* const* shadows, const void* const* wire_grads,
+                                    const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay, int zero_grads, void* stream);
 extern "C" int vp_rmsprop_step_shadow(void* const* params, void* const* grads, void* const* sq, void* const* shadows, const int64_t* numel,
                                       int count, float lr, float alpha, float eps, float weight_decay, int zero_grads, void* stream) {
+    return vp_rmsprop_step_wire(params, grads, sq, shadows, nullptr, numel, count, lr, alpha, eps, weight_decay, zero_grads, stream);
+}
+
+/* vp_rmsprop_step_shadow whose gradients are read from bf16 buffers (wire_grads[i] non-NULL): the data-parallel exchange in
+ * bf16 (vp_pack_grads_bf16 -> all-reduce -> this), without a conversion pass back to fp32. */
+extern "C" int vp_rmsprop_step_wire(void* const* params, void* const* grads, void* const* sq, void* const* shadows, const void* const* wire_grads,
+                                    const int64_t* numel, int count, float lr, float alpha, float eps, float weight_decay, int zero_grads, void* stream) {
     VP_CHECK_ARG(params && grads && sq && numel && count >= 0, "vp_rmsprop_step: bad arguments");
     for (int base = 0; base < count; base += kOptMax) {
         OptTable t;
@@ -613,6 +714,7 @@ extern "C" int vp_rmsprop_step_shadow(void* const* params, void* const* grads, v
             t.p[i] = (float*)params[base + i]; t.g[i] = (const float*)grads[base + i]; t.sq[i] = (float*)sq[base + i];
             t.n[i] = numel[base + i];
             t.sh[i] = shadows ? (bf16*)shadows[base + i] : nullptr;
+            t.wire[i] = wire_grads ? (const bf16*)wire_grads[base + i] : nullptr;
             nmax = numel[base + i] > nmax ? numel[base + i] : nmax;
         }
         int64_t bx = (nmax / 4 + 255) / 256;

@@ -1,0 +1,142 @@
+// The remaining terms of VaeGan.loss (reference models/networks.py:264-281) and of the train.py step (:62-67) as single
+// coalesced warp-shuffle kernels on fp32 tensors: feature MSE between discriminator layers, -log(s*p + c) on the sigmoid
+// scores, smooth-L1 on the auxiliary parameters and the per-sample KL.  All are a few KB..MB: latency-bound, one launch each.
+#include "common.cuh"
+
+namespace vp {
+namespace {
+
+// out[r] = 0.5 * sum_j (a[r,j] - b[r,j])^2   (one warp per row)          networks.py:273
+__global__ void __launch_bounds__(256) feat_mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t rows,
+                                                           int64_t cols) {
+    pdl_sync();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+        float s = 0.f;
+        for (int64_t j = lane; j < cols; j += 32) { const float d = a[r * cols + j] - b[r * cols + j]; s = fmaf(d, d, s); }
+        s = warp_sum(s);
+        if (lane == 0) out[r] = 0.5f * s;
+    }
+}
+// da = g[r] * (a - b), db = -da (either may be null)
+__global__ void __launch_bounds__(256) feat_mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g,
+                                                           float* __restrict__ da, float* __restrict__ db, int64_t rows, int64_t cols) {
+    pdl_sync();
+    const int64_t total = rows * cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = g[i / cols] * (a[i] - b[i]);
+        if (da) da[i] = d;
+        if (db) db[i] = -d;
+    }
+}
+// out = -log(s * p + c): (s, c) = (1, 1e-3) for the original images, (-1, 1 + 1e-3) for reconstructed / sampled    networks.py:276-278
+__global__ void __launch_bounds__(256) neglog_fwd_kernel(const float* __restrict__ p, float* __restrict__ out, int64_t n, float s, float c) {
+    pdl_sync();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = -logf(fmaf(s, p[i], c));
+}
+__global__ void __launch_bounds__(256) neglog_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ dp, int64_t n, float s,
+                                                         float c) {
+    pdl_sync();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dp[i] = -g[i] * s / fmaf(s, p[i], c);
+}
+// out[0] = scale * sum smooth_l1(a - b), beta = 1 (single block, deterministic)                                   networks.py:279
+__global__ void __launch_bounds__(256) smooth_l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n,
+                                                            float scale) {
+    pdl_sync();
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const float d = fabsf(a[i] - b[i]);
+        s += (double)(d < 1.f ? 0.5f * d * d : d - 0.5f);
+    }
+    s = warp_sum(s);
+    __shared__ double sh[8];
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int i = 0; i < 8; ++i) t += sh[i];
+        out[0] = (float)(t * (double)scale);
+    }
+}
+__global__ void __launch_bounds__(256) smooth_l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ g,
+                                                            float* __restrict__ da, float* __restrict__ db, int64_t n, float scale) {
+    pdl_sync();
+    const float gs = (g ? *g : 1.f) * scale;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float d = a[i] - b[i];
+        const float v = gs * fminf(fmaxf(d, -1.f), 1.f);
+        if (da) da[i] = v;
+        if (db) db[i] = -v;
+    }
+}
+// kl[r] = -0.5 * sum_j (-exp(lv) - mu^2 + lv + 1)   (one warp per row)                                           networks.py:270
+__global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ lv, int64_t ld, float* __restrict__ kl,
+                                                     int64_t rows, int zdim) {
+    pdl_sync();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < rows; r += warps) {
+        float acc = 0.f;
+        for (int j = lane; j < zdim; j += 32) {
+            const float m = mu[r * ld + j], l = lv[r * ld + j];
+            acc += -expf(l) - m * m + l + 1.f;
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) kl[r] = -0.5f * acc;
+    }
+}
+
+inline unsigned grid_for(int64_t n) {
+    int64_t b = (n + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+}  // namespace vp
+
+using namespace vp;
+
+extern "C" int vp_feature_mse_fwd(const float* a, const float* b, float* out, int64_t rows, int64_t cols, void* stream) {
+    VP_CHECK_ARG(a && b && out && rows > 0 && cols > 0, "vp_feature_mse_fwd: bad arguments");
+    launch_k(feat_mse_fwd_kernel, dim3(grid_for(rows * 32)), dim3(256), 0, (cudaStream_t)stream, a, b, out, rows, cols);
+    VP_CHECK_LAUNCH("vp_feature_mse_fwd");
+    return VP_OK;
+}
+extern "C" int vp_feature_mse_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t rows, int64_t cols, void* stream) {
+    VP_CHECK_ARG(a && b && g && (da || db) && rows > 0 && cols > 0, "vp_feature_mse_bwd: bad arguments");
+    launch_k(feat_mse_bwd_kernel, dim3(grid_for(rows * cols)), dim3(256), 0, (cudaStream_t)stream, a, b, g, da, db, rows, cols);
+    VP_CHECK_LAUNCH("vp_feature_mse_bwd");
+    return VP_OK;
+}
+extern "C" int vp_neglog_fwd(const float* p, float* out, int64_t n, float sign, float offset, void* stream) {
+    VP_CHECK_ARG(p && out && n > 0, "vp_neglog_fwd: bad arguments");
+    launch_k(neglog_fwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, p, out, n, sign, offset);
+    VP_CHECK_LAUNCH("vp_neglog_fwd");
+    return VP_OK;
+}
+extern "C" int vp_neglog_bwd(const float* p, const float* g, float* dp, int64_t n, float sign, float offset, void* stream) {
+    VP_CHECK_ARG(p && g && dp && n > 0, "vp_neglog_bwd: bad arguments");
+    launch_k(neglog_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, p, g, dp, n, sign, offset);
+    VP_CHECK_LAUNCH("vp_neglog_bwd");
+    return VP_OK;
+}
+extern "C" int vp_smooth_l1_sum_fwd(const float* a, const float* b, float* out, int64_t n, float scale, void* stream) {
+    VP_CHECK_ARG(a && b && out && n > 0, "vp_smooth_l1_sum_fwd: bad arguments");
+    launch_k(smooth_l1_fwd_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, a, b, out, n, scale);
+    VP_CHECK_LAUNCH("vp_smooth_l1_sum_fwd");
+    return VP_OK;
+}
+extern "C" int vp_smooth_l1_sum_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t n, float scale, void* stream) {
+    VP_CHECK_ARG(a && b && (da || db) && n > 0, "vp_smooth_l1_sum_bwd: bad arguments");
+    launch_k(smooth_l1_bwd_kernel, dim3(grid_for(n)), dim3(256), 0, (cudaStream_t)stream, a, b, g, da, db, n, scale);
+    VP_CHECK_LAUNCH("vp_smooth_l1_sum_bwd");
+    return VP_OK;
+}
+extern "C" int vp_kl_fwd(const float* mu, const float* logvar, int64_t ld, float* kl, int64_t rows, int zdim, void* stream) {
+    VP_CHECK_ARG(mu && logvar && kl && rows > 0 && zdim > 0 && ld >= zdim, "vp_kl_fwd: bad arguments");
+    launch_k(kl_fwd_kernel, dim3(grid_for(rows * 32)), dim3(256), 0, (cudaStream_t)stream, mu, logvar, ld, kl, rows, zdim);
+    VP_CHECK_LAUNCH("vp_kl_fwd");
+    return VP_OK;
+}

@@ -105,6 +105,12 @@ def set_epilogue_stats(on: bool):
     _STATE["epilogue_stats"] = bool(on)
 
 
+def set_pad_route(on: bool):
+    """bf16 layers whose channel counts are not multiples of 64: zero-pad onto the tcgen05 kernels (default) or fall back to the
+    packed route (CUDA-core kernel unless the shape happens to be tensor-core eligible) -- tests / A-B measurements."""
+    _STATE["pad_route"] = bool(on)
+
+
 def set_engine(name: str):
     """'auto' | 'simt' | 'tc' -- engine used for the contractions (tests force one or the other)."""
     _STATE["engine"] = {"auto": _lib.ENGINE_AUTO, "simt": _lib.ENGINE_SIMT, "tc": _lib.ENGINE_TC}[name]
@@ -169,7 +175,9 @@ class TapLayer:
     Three routes, chosen per call:
       * in place  (vp_conv_*_cl):  bf16, both channel counts multiples of 64, weight dense in channels-last order
       * thin      (vp_thin_conv_*): bf16, a single channel on one side
-      * packed    (vp_conv_*):      everything else, and the fp32 check mode (tap-major panels built by vp_pack_weight)
+      * padded    (vp_pad_* + vp_conv_*_cl): bf16, any other channel counts -- activations and weight are zero-padded to the next
+                  multiples of 64 and the in-place tcgen05 kernels run on the padded geometry (exact: zero channels add zeros)
+      * packed    (vp_conv_*):      the fp32 check mode and a forced CUDA-core engine (tap-major panels built by vp_pack_weight)
     """
 
     def __init__(self, kind, cin, cout, k=1, stride=1, pad=0, out_pad=0):
@@ -247,6 +255,57 @@ class TapLayer:
         """Called by an optimiser that has written the bf16 copy itself."""
         self._cache["shadow"] = ((weight.data_ptr(), weight._version, _EPOCH[0]), shadow, "optimiser")
 
+    # ---- padded route: channel counts that are not multiples of 64 on the 64-multiple tcgen05 kernels ------------------------
+    def _padded(self, dt, weight):
+        if dt != torch.bfloat16 or _STATE["engine"] == _lib.ENGINE_SIMT or _STATE.get("pad_route", True) is False:
+            return False
+        if weight.dim() == 4 and weight.shape[2] > 1 and weight.stride(2) != weight.shape[3] * weight.stride(3):
+            return False
+        return True
+
+    @staticmethod
+    def _up64(c):
+        return (c + 63) & ~63
+
+    def _pad_dims(self, weight):
+        """(d0, d1, taps, s0, s1, st, d0p, d1p) of the weight: axes 0 / 1 are (co, ci) for conv / linear, (ci, co) for convT."""
+        d0, d1 = weight.shape[0], weight.shape[1]
+        taps = self.k * self.k if weight.dim() == 4 else 1
+        st = weight.stride(3) if weight.dim() == 4 else 1
+        return d0, d1, taps, weight.stride(0), weight.stride(1), st, self._up64(d0), self._up64(d1)
+
+    def _padded_weight(self, weight):
+        key = (weight.data_ptr(), weight._version, _EPOCH[0], weight.stride())
+        hit = self._cache.get("padw")
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        d0, d1, taps, s0, s1, st, d0p, d1p = self._pad_dims(weight)
+        wp = hit[1] if hit is not None and hit[1].numel() == d0p * taps * d1p else torch.empty(d0p * taps * d1p, dtype=torch.bfloat16, device=weight.device)
+        _lib.call("vp_pad_weight_cl", _ptr(weight), _ptr(wp), d0, d1, taps, s0, s1, st, d0p, d1p, _stream())
+        self._cache["padw"] = (key, wp)
+        return wp
+
+    @staticmethod
+    def _pad_act(x, cp):
+        c = x.shape[-1]
+        if c == cp:
+            return x
+        out = torch.empty(x.shape[:-1] + (cp,), dtype=x.dtype, device=x.device)
+        _lib.call("vp_pad_channels", _ptr(x), c, _ptr(out), cp, x.numel() // c, _code(x.dtype), _stream())
+        return out
+
+    @staticmethod
+    def _slice_act(xp, c):
+        cp = xp.shape[-1]
+        if c == cp:
+            return xp
+        out = torch.empty(xp.shape[:-1] + (c,), dtype=xp.dtype, device=xp.device)
+        _lib.call("vp_copy_channels", _ptr(xp), cp, 0, _ptr(out), c, 0, c, xp.numel() // cp, _code(xp.dtype), 0, _stream())
+        return out
+
+    def _padded_geom(self, n, h, w, ho, wo):
+        return self._geom(n, h, w, self._up64(self.cin), ho, wo, self._up64(self.cout), self.k, self.stride, self.pad, int(self.kind == "convT"))
+
     # ---- thin layers (a single channel on one side): tcgen05 kernels that read the fp32 master weight directly ----
     def _thin(self, which, dt, weight):
         if self.kind != "conv" or dt != torch.bfloat16 or _STATE["engine"] == _lib.ENGINE_SIMT or not weight.is_contiguous():
@@ -275,6 +334,18 @@ class TapLayer:
         elif self._cl(dt, weight):
             _lib.call("vp_conv_fwd_cl", C.byref(g), _ptr(x), _ptr(self._shadow(weight)), _ptr(bias), _ptr(y), _code(out_dtype),
                       ACT[act], float(slope), _stream())
+        elif self._padded(dt, weight):
+            cip, cop = self._up64(self.cin), self._up64(self.cout)
+            gp = self._padded_geom(n, h, w, shp[1], shp[2])
+            bp = None
+            if bias is not None:
+                bp = torch.zeros(cop, dtype=torch.float32, device=x.device)
+                _lib.call("vp_cast", _ptr(bias.detach()), F32, _ptr(bp), F32, self.cout, _stream())
+            yp = y if cop == self.cout else torch.empty(shp[:3] + (cop,), dtype=out_dtype, device=x.device)
+            _lib.call("vp_conv_fwd_cl", C.byref(gp), _ptr(self._pad_act(x, cip)), _ptr(self._padded_weight(weight)), _ptr(bp), _ptr(yp),
+                      _code(out_dtype), ACT[act], float(slope), _stream())
+            if yp is not y:
+                _lib.call("vp_copy_channels", _ptr(yp), cop, 0, _ptr(y), self.cout, 0, self.cout, y.numel() // self.cout, _code(out_dtype), 0, _stream())
         else:
             wp = self._packed(weight, "fwd", dt)
             _lib.call("vp_conv_fwd", C.byref(g), _ptr(x), _ptr(wp), _ptr(bias), _ptr(y), _code(dt), _code(out_dtype),
@@ -318,6 +389,14 @@ class TapLayer:
             _lib.call("vp_thin_conv_dgrad", C.byref(g), _ptr(dy), _ptr(weight), _ptr(dx), _code(out_dtype), _stream())
         elif self._cl(dt, weight):
             _lib.call("vp_conv_dgrad_cl", C.byref(g), _ptr(dy), _ptr(self._shadow(weight)), _ptr(dx), _code(out_dtype), _stream())
+        elif self._padded(dt, weight):
+            cip, cop = self._up64(self.cin), self._up64(self.cout)
+            gp = self._padded_geom(n, h, w, dy.shape[1], dy.shape[2])
+            dxp = dx if cip == self.cin else torch.empty(tuple(x_shape[:3]) + (cip,), dtype=out_dtype, device=dy.device)
+            _lib.call("vp_conv_dgrad_cl", C.byref(gp), _ptr(self._pad_act(dy, cop)), _ptr(self._padded_weight(weight)), _ptr(dxp), _code(out_dtype),
+                      _stream())
+            if dxp is not dx:
+                _lib.call("vp_copy_channels", _ptr(dxp), cip, 0, _ptr(dx), self.cin, 0, self.cin, dx.numel() // self.cin, _code(out_dtype), 0, _stream())
         else:
             wp = self._packed(weight, "dgrad", dt)
             _lib.call("vp_conv_dgrad", C.byref(g), _ptr(dy), _ptr(wp), _ptr(dx), _code(dt), _code(out_dtype),
@@ -332,6 +411,26 @@ class TapLayer:
         if thin or cl:
             dw, zeroed = _grad_target(weight)       # same strides as the weight: the kernel writes the gradient in place
             _lib.call("vp_thin_conv_wgrad" if thin else "vp_conv_wgrad_cl", C.byref(g), _ptr(x), _ptr(dy), _ptr(dw), int(zeroed), _stream())
+            return dw
+        if (self._padded(dt, weight) and self.kind == "conv" and self.cin == 1 and self.k <= 8 and self.stride <= 3 and weight.is_contiguous()
+                and self.cout % 64 != 0):
+            # single-channel input, output channels not a multiple of 64 (the discriminator's 1 -> 32 first layer): pad only the
+            # wide side and use the thin weight-gradient kernel; the gradient rows of the padding channels are dropped
+            cop = self._up64(self.cout)
+            gp = self._geom(n, h, w, 1, dy.shape[1], dy.shape[2], cop, self.k, self.stride, self.pad, 0)
+            dwp = torch.empty((cop,) + tuple(weight.shape[1:]), dtype=torch.float32, device=x.device)
+            _lib.call("vp_thin_conv_wgrad", C.byref(gp), _ptr(x), _ptr(self._pad_act(dy, cop)), _ptr(dwp), 0, _stream())
+            dw, _ = _grad_target(weight)
+            _lib.call("vp_cast", _ptr(dwp), F32, _ptr(dw), F32, weight.numel(), _stream())
+            return dw
+        if self._padded(dt, weight):
+            cip, cop = self._up64(self.cin), self._up64(self.cout)
+            gp = self._padded_geom(n, h, w, dy.shape[1], dy.shape[2])
+            d0, d1, taps, s0, s1, st, d0p, d1p = self._pad_dims(weight)
+            dwp = torch.empty(d0p * taps * d1p, dtype=torch.float32, device=x.device)
+            _lib.call("vp_conv_wgrad_cl", C.byref(gp), _ptr(self._pad_act(x, cip)), _ptr(self._pad_act(dy, cop)), _ptr(dwp), 0, _stream())
+            dw, _ = _grad_target(weight)
+            _lib.call("vp_unpad_wgrad_cl", _ptr(dwp), _ptr(dw), d0, d1, taps, s0, s1, st, d1p, _stream())
             return dw
         p = self._recipe("wgrad", weight)
         dwp = torch.empty(p.taps * p.n * p.k, dtype=torch.float32, device=x.device)

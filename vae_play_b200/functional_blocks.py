@@ -419,3 +419,158 @@ def tanh(x):
 
 def sigmoid(x):
     return _Pointwise.apply(x, "sigmoid", 0.0)
+
+
+# ------------------------------------------------------------------------------------------------
+# the remaining terms of VaeGan.loss / the train.py step (models/networks.py:264-281, train.py:62-67)
+# ------------------------------------------------------------------------------------------------
+class _FeatureMse(torch.autograd.Function):
+    """out[r] = 0.5 * sum_j (a[r,j] - b[r,j])^2"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        _require_cuda(a, "feature_mse")
+        a, b = a.float().contiguous(), b.float().contiguous()
+        rows = a.shape[0]
+        cols = a.numel() // rows
+        out = torch.empty(rows, dtype=torch.float32, device=a.device)
+        _lib.call("vp_feature_mse_fwd", _ptr(a), _ptr(b), _ptr(out), rows, cols, _stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        rows = a.shape[0]
+        cols = a.numel() // rows
+        g = g.contiguous().float()
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        _lib.call("vp_feature_mse_bwd", _ptr(a), _ptr(b), _ptr(g), _ptr(da), _ptr(db), rows, cols, _stream())
+        return da, db
+
+
+def feature_mse(a, b):
+    """``torch.sum(0.5 * (a - b) ** 2, 1)`` (networks.py:273)."""
+    return _FeatureMse.apply(a, b)
+
+
+def half_sqdiff(a, b):
+    """``0.5 * (a - b) ** 2`` element-wise on [B, P] (the nle term, networks.py:267)."""
+    shp = a.shape
+    return _FeatureMse.apply(a.reshape(-1, 1), b.reshape(-1, 1)).reshape(shp)
+
+
+class _NegLog(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, sign, offset):
+        _require_cuda(p, "neglog")
+        p = p.float().contiguous()
+        out = torch.empty_like(p)
+        _lib.call("vp_neglog_fwd", _ptr(p), _ptr(out), p.numel(), float(sign), float(offset), _stream())
+        ctx.save_for_backward(p)
+        ctx.so = (float(sign), float(offset))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (p,) = ctx.saved_tensors
+        g = g.contiguous().float()
+        dp = torch.empty_like(p)
+        _lib.call("vp_neglog_bwd", _ptr(p), _ptr(g), _ptr(dp), p.numel(), ctx.so[0], ctx.so[1], _stream())
+        return dp, None, None
+
+
+def neglog(p, sign=1.0, offset=1e-3):
+    """``-log(sign * p + offset)``: -log(D + 1e-3) with (1, 1e-3), -log(1 - D + 1e-3) with (-1, 1 + 1e-3) (networks.py:276-278)."""
+    return _NegLog.apply(p, sign, offset)
+
+
+class _SmoothL1Sum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, scale):
+        _require_cuda(a, "smooth_l1_sum")
+        a, b = a.float().contiguous(), b.float().contiguous()
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
+        _lib.call("vp_smooth_l1_sum_fwd", _ptr(a), _ptr(b), _ptr(out), a.numel(), float(scale), _stream())
+        ctx.save_for_backward(a, b)
+        ctx.scale = float(scale)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous().float().reshape(1)
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        _lib.call("vp_smooth_l1_sum_bwd", _ptr(a), _ptr(b), _ptr(g), _ptr(da), _ptr(db), a.numel(), ctx.scale, _stream())
+        return da, db, None
+
+
+def smooth_l1_sum(a, b, scale=1.0):
+    """``scale * F.smooth_l1_loss(a, b, reduction="sum")`` (networks.py:279 with scale = 1 / batch)."""
+    return _SmoothL1Sum.apply(a, b, scale)
+
+
+class _KlPerSample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar):
+        _require_cuda(mu, "kl_per_sample")
+        if mu.stride(-1) != 1 or logvar.stride(-1) != 1 or mu.stride(0) != logvar.stride(0):
+            mu, logvar = mu.contiguous(), logvar.contiguous()
+        rows, z = mu.shape
+        kl = torch.empty(rows, dtype=torch.float32, device=mu.device)
+        _lib.call("vp_kl_fwd", _ptr(mu), _ptr(logvar), mu.stride(0), _ptr(kl), rows, z, _stream())
+        ctx.save_for_backward(mu, logvar)
+        return kl
+
+    @staticmethod
+    def backward(ctx, dkl):
+        mu, logvar = ctx.saved_tensors
+        rows, z = mu.shape
+        dkl = dkl.contiguous().float()
+        d = torch.empty((2, rows, z), dtype=torch.float32, device=mu.device)
+        # dmu = dkl * mu, dlogvar = dkl * 0.5 * (exp(logvar) - 1): the KL half of the fused reparameterisation backward
+        _lib.call("vp_reparam_kl_bwd", _ptr(mu), _ptr(logvar), mu.stride(0), _ptr(mu), None, F32, _ptr(dkl), _ptr(d[0]), _ptr(d[1]), F32, z, rows, z,
+                  _stream())
+        return d[0], d[1]
+
+
+def kl_per_sample(mu, logvar):
+    """``-0.5 * torch.sum(-logvar.exp() - mu ** 2 + logvar + 1, 1)`` (networks.py:270)."""
+    return _KlPerSample.apply(mu, logvar)
+
+
+class _WeightedSums(torch.autograd.Function):
+    """sum_i w_i * sum(t_i) as one scalar (the loss combinations of train.py:63-67); backward fills each t_i's gradient with w_i * g."""
+
+    @staticmethod
+    def forward(ctx, weights, *tensors):
+        dev = tensors[0].device
+        out = torch.zeros(1, dtype=torch.float32, device=dev)
+        flat = []
+        for w, t in zip(weights, tensors):
+            _require_cuda(t, "weighted_sums")
+            t = t.float().contiguous()
+            flat.append(t)
+            _lib.call("vp_sum_into", _ptr(t), t.numel(), float(w), _ptr(out), _stream())
+        ctx.weights = [float(w) for w in weights]
+        ctx.shapes = [t.shape for t in tensors]
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().float().reshape(1)
+        outs = []
+        for i, (w, shp) in enumerate(zip(ctx.weights, ctx.shapes)):
+            if not ctx.needs_input_grad[1 + i]:
+                outs.append(None)
+                continue
+            d = torch.empty(shp, dtype=torch.float32, device=g.device)
+            _lib.call("vp_fill_from", _ptr(g), w, _ptr(d), d.numel(), _stream())
+            outs.append(d)
+        return (None, *outs)
+
+
+def weighted_sums(tensors, weights):
+    return _WeightedSums.apply(list(weights), *tensors)

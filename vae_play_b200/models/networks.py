@@ -294,22 +294,17 @@ class VaeGan(nn.Module):
     @staticmethod
     def loss(x, x_tilde, disc_layer_original, disc_layer_predicted, disc_layer_sampled, disc_class_original,
              disc_class_predicted, disc_class_sampled, mus, variances, targets, params):
-        """Same 7-tuple as the reference's ``VaeGan.loss`` (networks.py:264-281).
-
-        (nle, kl, feature-mse, -log(D(x)+1e-3), -log(1-D(x~)+1e-3), -log(1-D(x_p)+1e-3), smooth-L1/B).
-        Only KL and the reconstruction term are on the hot path; ``functional.vae_loss`` /
-        ``functional.reparam_kl`` are their fused single-kernel forms.  The GAN terms are small
-        [B,1]/[B,F] expressions kept in torch until the discriminator step is brought in scope.
-        """
+        """Same 7-tuple as the reference's ``VaeGan.loss`` (networks.py:264-281):
+        (nle, kl, feature-mse, -log(D(x)+1e-3), -log(1-D(x~)+1e-3), -log(1-D(x_p)+1e-3), smooth-L1/B), every term one
+        kernel of libvaeplay_b200 (csrc/gan_losses.cu) with its own backward -- no ATen arithmetic on the step."""
+        from .. import functional_blocks as VB
         b = x.size(0)
         flat = lambda t: t.reshape(t.size(0), -1)
-        diff = flat(x) - flat(x_tilde)
-        nle = diff.square().mul(0.5)
-        kl = (variances.exp() + mus.square() - variances - 1.0).sum(dim=1).mul(0.5)
-        feat = (disc_layer_original - disc_layer_predicted).square().mul(0.5).sum(dim=1)
-        tiny = 1e-3
-        d_real = (disc_class_original + tiny).log().neg()
-        d_rec = (1.0 - disc_class_predicted + tiny).log().neg()
-        d_samp = (1.0 - disc_class_sampled + tiny).log().neg()
-        aux = torch.nn.functional.smooth_l1_loss(targets, params, reduction="sum") / b
+        nle = VB.half_sqdiff(flat(x), flat(x_tilde))
+        kl = VB.kl_per_sample(mus, variances)
+        feat = VB.feature_mse(disc_layer_original, disc_layer_predicted)
+        d_real = VB.neglog(disc_class_original, 1.0, 1e-3)
+        d_rec = VB.neglog(disc_class_predicted, -1.0, 1.0 + 1e-3)
+        d_samp = VB.neglog(disc_class_sampled, -1.0, 1.0 + 1e-3)
+        aux = VB.smooth_l1_sum(targets, params, 1.0 / b)
         return nle, kl, feat, d_real, d_rec, d_samp, aux

@@ -14,15 +14,18 @@ from . import _lib
 
 
 class FusedRMSprop(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0.0, zero_grads=False):
+    def __init__(self, params, lr=1e-2, alpha=0.99, eps=1e-8, weight_decay=0.0, zero_grads=False, wire=None):
         """zero_grads=True: ``step()`` also clears every gradient it has consumed (the tensors stay attached to the
         parameters).  Use with ``functional.persistent_grads`` / ``parallel.GradBuckets`` and do NOT call ``zero_grad()``:
-        the next backward then accumulates into known-zero memory without any memset."""
+        the next backward then accumulates into known-zero memory without any memset.
+        wire: {id(param): bf16 tensor} -- the gradient VALUES are read from these buffers (the bf16 data-parallel wire format,
+        ``GradBuckets.wire_views``) instead of ``param.grad``; ``param.grad`` must still exist (it names the slot)."""
         if lr < 0 or eps < 0 or alpha < 0 or weight_decay < 0:
             raise ValueError("invalid hyper-parameter")
         super().__init__(params, dict(lr=lr, alpha=alpha, eps=eps, weight_decay=weight_decay))
         self._tables = {}
         self.zero_grads = bool(zero_grads)
+        self.wire = wire
 
     def _table(self, gi, group):
         from . import functional as VF
@@ -43,9 +46,16 @@ class FusedRMSprop(torch.optim.Optimizer):
                 st["square_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         n = len(plist)
         arr = lambda vals: (C.c_void_p * n)(*vals)
+        wire = None
+        if self.wire is not None:
+            for p in plist:
+                w = self.wire.get(id(p))
+                if w is None or w.dtype != torch.bfloat16 or w.stride() != p.stride():
+                    raise _lib.VaePlayError("FusedRMSprop(wire=...): every parameter needs a bf16 wire view with its own strides")
+            wire = arr([self.wire[id(p)].data_ptr() for p in plist])
         tab = (arr([p.data_ptr() for p in plist]), arr([p.grad.data_ptr() for p in plist]),
                arr([self.state[p]["square_avg"].data_ptr() for p in plist]), (C.c_int64 * n)(*[p.numel() for p in plist]), n, plist,
-               arr([s[1].data_ptr() if s else None for s in shadows]), shadows)
+               arr([s[1].data_ptr() if s else None for s in shadows]), shadows, wire)
         self._tables[gi] = (key, tab)
         return tab
 
@@ -57,11 +67,11 @@ class FusedRMSprop(torch.optim.Optimizer):
                 loss = closure()
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for gi, group in enumerate(self.param_groups):
-            pa, ga, sa, na, n, plist, sha, shadows = self._table(gi, group)
+            pa, ga, sa, na, n, plist, sha, shadows, wire = self._table(gi, group)
             if n == 0:
                 continue
             # the bf16 operand copies of the weights (functional.TapLayer._shadow) are refreshed by the same kernel
-            _lib.call("vp_rmsprop_step_shadow", pa, ga, sa, sha, na, n, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
+            _lib.call("vp_rmsprop_step_wire", pa, ga, sa, sha, wire, na, n, float(group["lr"]), float(group["alpha"]), float(group["eps"]),
                       float(group["weight_decay"]), int(self.zero_grads), stream)
             # the parameters were modified by a kernel torch does not know about: bump their version counters so that
             # everything keyed on tensor._version (the packed-weight caches, autograd's saved-tensor checks) sees it

@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 class GradBuckets:
     def __init__(self, params: List[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0, group=None,
-                 overlap: bool = True):
+                 overlap: bool = True, wire_dtype=None):
         """overlap=True: each bucket's all-reduce is issued from the gradient hook as soon as the bucket is
         complete (overlaps the rest of backward).  overlap=False: hooks only place gradients into the buckets and
         ``allreduce()`` issues all collectives afterwards -- used when forward+backward is replayed as a CUDA
@@ -32,6 +32,12 @@ class GradBuckets:
         self.world = world_size
         self.group = group
         self.overlap = overlap
+        # wire_dtype=torch.bfloat16: the buckets are exchanged in bf16 (half the NVLink bytes).  pack() converts a bucket
+        # (and clears its fp32 slots for the next step) in one pass; the optimiser then reads the reduced bf16 values directly
+        # (FusedRMSprop(wire=...)).  None: fp32 on the wire, bit-identical to summing the per-rank gradients in fp32.
+        if wire_dtype not in (None, torch.float32, torch.bfloat16):
+            raise ValueError("wire_dtype must be None, torch.float32 or torch.bfloat16")
+        self.wire_dtype = wire_dtype if wire_dtype == torch.bfloat16 else None
         cap = int(bucket_mb * (1 << 20) / 4)
         # reverse registration order ~ the order gradients become ready in backward
         order = list(reversed(self.params))
@@ -79,7 +85,8 @@ class GradBuckets:
         n = sum(self._padded(p) for p in plist)
         dev = plist[0].device
         self.buckets.append({"buf": torch.zeros(n, dtype=torch.float32, device=dev), "params": list(plist),
-                             "ready": 0, "handle": None})
+                             "ready": 0, "handle": None, "packed": False,
+                             "wire": torch.zeros(n, dtype=torch.bfloat16, device=dev) if self.wire_dtype is not None else None})
 
     def _install_sinks(self):
         try:
@@ -87,6 +94,36 @@ class GradBuckets:
             VF.set_grad_sinks({p.data_ptr(): (self.buckets[self.slot[id(p)][0]]["buf"], self.slot[id(p)][2], p) for p in self.params})
         except Exception:  # pragma: no cover - CPU-only host-logic tests
             pass
+
+    # ---- bf16 wire format ---------------------------------------------------------------------------------------------
+    def pack(self, bucket_ids=None):
+        """fp32 bucket -> bf16 wire buffer, clearing the fp32 slots in the same pass (vp_pack_grads_bf16), stream-ordered on
+        the current stream.  No-op with an fp32 wire.  Called by the hooks (eager) or by the caller inside its captured graph."""
+        if self.wire_dtype is None:
+            return
+        import ctypes as C
+        from . import _lib
+        from . import functional as VF
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for bi in (range(len(self.buckets)) if bucket_ids is None else bucket_ids):
+            b = self.buckets[bi]
+            _lib.call("vp_pack_grads_bf16", C.c_void_p(b["buf"].data_ptr()), C.c_void_p(b["wire"].data_ptr()), b["buf"].numel(), 1, stream)
+            b["packed"] = True
+            VF.sinks_zeroed(b["params"])
+
+    def wire_views(self, bucket_id):
+        """param -> bf16 view of its reduced gradient inside the wire buffer (what FusedRMSprop(wire=...) reads), or None."""
+        if self.wire_dtype is None:
+            return None
+        b = self.buckets[bucket_id]
+        return {id(p): torch.as_strided(b["wire"], p.shape, p.stride(), storage_offset=self.slot[id(p)][2]) for p in b["params"]}
+
+    def _reduce(self, b):
+        if self.wire_dtype is not None and not b["packed"]:
+            self.pack([next(i for i, x in enumerate(self.buckets) if x is b)])
+        buf = b["wire"] if self.wire_dtype is not None else b["buf"]
+        b["packed"] = False
+        return dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     # ---- hook: called once per parameter per backward, after .grad has been accumulated -----------
     def _on_grad(self, p):
@@ -104,7 +141,7 @@ class GradBuckets:
             return
         b["ready"] += 1
         if b["ready"] == len(b["params"]) and self.world > 1 and self.overlap:
-            b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            b["handle"] = self._reduce(b)
 
     def allreduce(self, check_missing: bool = True):
         """Finish the step's exchange: launch whatever is still pending, wait for everything."""
@@ -114,14 +151,14 @@ class GradBuckets:
                 for p in b["params"]:
                     if check_missing and p.grad is None:
                         self.slot[id(p)][1].zero_()
-                b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                b["handle"] = self._reduce(b)
         for b in self.buckets:
             if b["handle"] is not None:
                 b["handle"].wait()
                 b["handle"] = None
             b["ready"] = 0
 
-    def allreduce_subset(self, bucket_ids):
+    def allreduce_subset(self, bucket_ids, pre_packed=False):
         """Issue (asynchronously, on NCCL's stream, ordered after the work already queued on the current stream) the
         all-reduce of the given buckets -- used when the caller knows from the structure of its step that they are
         complete (CUDA-graph replay, where the readiness hooks do not run).  ``allreduce()`` later waits for them."""
@@ -130,7 +167,9 @@ class GradBuckets:
         for bi in bucket_ids:
             b = self.buckets[bi]
             if b["handle"] is None:
-                b["handle"] = dist.all_reduce(b["buf"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                if self.wire_dtype is not None and pre_packed:
+                    b["packed"] = True          # the caller's captured graph ran pack() for this bucket
+                b["handle"] = self._reduce(b)
 
     def wait_bucket(self, bi):
         """Make the current stream wait for bucket ``bi``'s all-reduce (issued by ``allreduce_subset``)."""
