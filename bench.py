@@ -547,6 +547,12 @@ def run_ours(args):
         torch.cuda.empty_cache()
         # ---- the GPU-library bar: the same step through torch.nn.functional (cuDNN / cuBLAS), context only ---------------
         extra["gpu_library_baseline"] = gpu_library_baseline(img, cin, B, dev, args.steps)
+        # ---- config 4: the full train.py VAE-GAN step at 128x128 -------------------------------------------------------------
+        try:
+            extra["vaegan128"] = vaegan_bench(args, dev, peaks)
+        except Exception as e:       # an extra must not take the headline line down with it
+            extra["vaegan128"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
         line["extra"] = extra
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -554,6 +560,134 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def vaegan_flops_per_image(img, z=128):
+    """Forward MACs x 2 of one train.py step per input image: encoder, decoder on z and z_p, discriminator on the 3 images
+    (x, x~, x_p) in REC mode (conv stack up to the last block's convolution) and in GAN mode (full), DirectDecoder."""
+    L = int(math.log2(img // 8))
+    conv = lambda hw_out, cin, cout, k=5: hw_out * hw_out * cin * cout * k * k
+    enc, c, hw = 0, 1, img
+    chans = []
+    for i in range(L):
+        co = 64 if i == 0 else c * 2
+        hw //= 2
+        enc += conv(hw, c, co)
+        c = co
+        chans.append(co)
+    enc += 64 * c * 1024 + 1024 * 2 * z
+    dec, hw, cd = z * 64 * c, 8, c
+    for i in range(L):
+        co = cd if i == 0 else cd // 2
+        dec += conv(hw, cd, co)            # transposed conv: MAC = in-pixels * cin * cout * k*k
+        hw *= 2
+        cd = co
+    dec += conv(img, cd, 1)
+    disc_rec, cdi, hw = conv(img, 1, 32), 32, img
+    for i in range(L):
+        hw //= 2
+        disc_rec += conv(hw, cdi, cdi * 2)
+        cdi *= 2
+    disc_gan = disc_rec + 64 * cdi * 512 + 512
+    aux = z * 512 + 512 * 256 + 256 * 128 + 128 * 64 + 2 * 64 * 32 + 32 * 3
+    fwd_mac = enc + 2 * dec + 3 * (disc_rec + disc_gan) + aux
+    return 2.0 * fwd_mac
+
+
+def vaegan_bench(args, dev, peaks, img=128, B=64):
+    """Config 4 of BASELINE.json: the FULL train.py step (VaeGan forward with the decoder on z and z_p and the discriminator on
+    3B images in REC and GAN mode, VaeGan.loss, the summed-loss backward that equals the reference's five accumulating backward
+    calls, four RMSprop optimisers), CUDA-graph replay, timed like the main workload."""
+    import torch
+
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    from vae_play_b200 import train_steps as TS
+    from vae_play_b200.models.networks import VaeGan
+    from vae_play_b200.optim import FusedRMSprop
+    torch.manual_seed(0)
+    net = VaeGan(img, 128).to(dev).train()
+    groups = [net.encoder, net.decoder, net.discriminator, net.param_encoder]             # train.py:136-140
+    opts = [FusedRMSprop(list(m.parameters()), lr=1e-4, zero_grads=True) for m in groups]
+    VF.persistent_grads(list(net.parameters()))
+    x = torch.rand(B, 1, img, img, device=dev)
+    x_host = x.cpu().pin_memory()
+    targets = torch.rand(B, 3, device=dev)
+    off_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+    inc = VF.philox_policy(B * 128, torch.cuda.get_device_properties(dev).multi_processor_count)[1]
+    simt0 = _lib.simt_bf16_count()
+
+    def fwd_bwd():
+        b = x.size(0)
+        x_tilde, disc_class, disc_layer, mus, lv, params = net(x, rng=(0, off_dev))
+        VF.philox_advance(off_dev, 2 * inc)
+        nle, kl, mse, bo, bp, bs, l1 = VaeGan.loss(x, x_tilde, disc_layer[:b], disc_layer[b:-b], disc_layer[-b:], disc_class[:b],
+                                                    disc_class[b:-b], disc_class[-b:], mus, lv, targets, params)
+        parts = dict(recon=VF.mse_loss(x, x_tilde), kl=kl, mse=mse, bce_o=bo, bce_p=bp, bce_s=bs, l1=l1)
+        return TS.vaegan_backward(None, parts, fused=True)
+
+    def eager():
+        for o in opts:
+            o.zero_grad(set_to_none=True)
+        loss = fwd_bwd()
+        for o in opts:
+            o.step()
+        return loss
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    VF.invalidate_caches()
+    for o in opts:
+        o.zero_grad(set_to_none=True)
+    ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+    l0 = _lib.launch_count()
+    with torch.cuda.graph(ga):
+        static_loss = fwd_bwd()
+    with torch.cuda.graph(gb, pool=ga.pool()):
+        for o in opts:
+            o.step()
+    launches = _lib.launch_count() - l0
+
+    def step():
+        ga.replay()
+        gb.replay()
+    for _ in range(10):
+        step()
+    torch.cuda.synchronize()
+    regs = []
+    for _ in range(args.repeats):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        regs.append(e0.elapsed_time(e1) / args.steps)
+    ms = statistics.median(regs)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        x.copy_(x_host, non_blocking=True)
+        step()
+        lh = static_loss.item()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1) / args.steps
+    gf = vaegan_flops_per_image(img) * 3 / 1e9
+    ips = B / ms * 1e3
+    out = {"workload": f"train.py full step: VaeGan({img},128) fwd (decoder x2, discriminator on 3B images in REC+GAN mode) + VaeGan.loss + summed-loss "
+                       f"backward (== the five accumulating backward calls) + 4 x RMSprop, batch {B}",
+           "value": round(ips, 1), "unit": "images/s", "ms_per_step": round(ms, 4), "e2e_value": round(B / ms_e2e * 1e3, 1),
+           "gpu_launches_per_step": int(launches), "bf16_contractions_on_cuda_cores": int(_lib.simt_bf16_count() - simt0),
+           "approx_gflop_per_image": round(gf, 1), "approx_step_tflops": round(ips * gf / 1e3, 1),
+           "approx_frac_of_sustained_bf16": round(ips * gf / 1e3 / peaks["tf_sustained"], 4), "loss": lh,
+           "note": "FLOPs = 3 x forward MACs x 2 (an upper bound: first-layer data gradients are not computed)"}
+    VF.set_grad_sinks({})
+    return out
 
 
 def gpu_library_baseline(img, cin, B, dev, steps):

@@ -275,6 +275,10 @@ int vp_feature_mse_bwd(const float* a, const float* b, const float* g, float* da
 /* out = -log(sign * p + offset): (1, 1e-3) for -log(D(x) + 1e-3), (-1, 1 + 1e-3) for -log(1 - D(.) + 1e-3) (:276-278) */
 int vp_neglog_fwd(const float* p, float* out, int64_t n, float sign, float offset, void* stream);
 int vp_neglog_bwd(const float* p, const float* g, float* dp, int64_t n, float sign, float offset, void* stream);
+/* out[b] = -log(s[b, label[b]]): the pick of F.cross_entropy after its softmax (train_Style_GAN.py:219,226: applied to the
+ * discriminator's softmax PROBABILITIES, i.e. a second softmax -- vp_softmax_fwd -- comes first); label int64 [rows] */
+int vp_nll_pick_fwd(const float* s, const int64_t* label, float* out, int64_t rows, int cols, void* stream);
+int vp_nll_pick_bwd(const float* s, const int64_t* label, const float* g, float* ds, int64_t rows, int cols, void* stream);
 /* out[0] = scale * sum smooth_l1(a - b) with beta = 1 (F.smooth_l1_loss(reduction="sum") / B, :279); g: device scalar or NULL */
 int vp_smooth_l1_sum_fwd(const float* a, const float* b, float* out, int64_t n, float scale, void* stream);
 int vp_smooth_l1_sum_bwd(const float* a, const float* b, const float* g, float* da, float* db, int64_t n, float scale,
@@ -338,6 +342,9 @@ int vp_edge_bwd(const float* de, const float* sign, float* dx, int64_t n, int h,
 
 /* number of kernels this library has launched in this process (the bench's gpu_launches claim) */
 uint64_t vp_launch_count(void);
+/* number of bf16 contractions that ran on the CUDA-core engine instead of tcgen05 (0 on the bf16 hot path: every layer shape
+ * of the reference reaches a tensor-core kernel directly, through the thin kernels or through channel padding) */
+uint64_t vp_simt_bf16_count(void);
 
 #ifdef __cplusplus
 }

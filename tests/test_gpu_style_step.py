@@ -1,0 +1,95 @@
+"""GPU parity of config 5 (BASELINE.json): one ``train_random_gan`` iteration (train_Style_GAN.py:162-281) on the mirror
+StyleEncoder / Generator / Discriminator with FusedAdam, against tests/golden/style_step32_b2.npz (oracle/gen_golden_style_step.py:
+the unmodified reference modules, float64, image 32 / z 16 / batch 2).  Run on the B200 box with ``pytest -m gpu``."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.gen_golden_blocks import synth_state
+from oracle.gen_golden_style_step import B, IMG, NCLS, Z, digest, synth_step_inputs
+from tests.util import load
+
+pytestmark = pytest.mark.gpu
+NAMES = ("g_rec_kl_loss", "g_rec_d_loss", "g_rec_pixel_loss", "g_gen_d_loss", "loss_latent", "d_real_loss", "d_fake_loss")
+
+
+@pytest.fixture(scope="module")
+def vp():
+    import vae_play_b200
+    return vae_play_b200
+
+
+def run_step(vp, prec):
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import train_steps as TS
+    from vae_play_b200.models import network_Style_GAN as S
+    from vae_play_b200.optim import FusedAdam
+    vp.set_precision(prec)
+    vp.set_engine("auto")
+    VF.set_grad_sinks({})
+    G, E, D = S.Generator(IMG, Z), S.StyleEncoder(Z, IMG), S.Discriminator(IMG, NCLS)
+    for i, m in enumerate((G, E, D)):
+        m.load_state_dict(synth_state(m, 900 + i), strict=False)
+        m.cuda().train()
+    before = {n: {k: p.detach().clone() for k, p in m.named_parameters()} for n, m in (("G", G), ("E", E), ("D", D))}
+    g_opt, e_opt, d_opt = (FusedAdam(list(m.parameters()), lr=1e-4) for m in (G, E, D))
+    xt, xc, y, eps, sz = synth_step_inputs()
+    dev = "cuda"
+    losses = TS.style_gan_step(G, E, D, g_opt, e_opt, d_opt, torch.from_numpy(xt).to(dev), torch.from_numpy(xc).to(dev), torch.from_numpy(y).to(dev),
+                               torch.from_numpy(eps).to(dev), torch.from_numpy(sz).to(dev))
+    torch.cuda.synchronize()
+    out = {"losses": np.array([float(losses[k]) for k in NAMES])}
+    for n, m in (("G", G), ("E", E), ("D", D)):
+        for k, p in m.named_parameters():
+            out[f"upd/{n}/{k}"] = digest(((p.detach() - before[n][k]) / 1e-4).double().cpu().numpy())
+            out[f"grad/{n}/{k}"] = digest(p.grad.double().cpu().numpy()) if p.grad is not None else np.zeros(3)
+    return out
+
+
+def test_style_gan_step_golden_fp32(vp):
+    """Seven losses to 2e-5; every parameter gradient's l2 norm and strided samples to max(1e-4, 10 x the reference's fp32 deviation)
+    (InstanceNorm over 2x2 .. 16x16 maps and two soft-maxes in a row amplify round-off); Adam's first update g/(|g|+eps) matches in
+    l2 norm to 2 % (it is a sign function of the gradient wherever |g| >> 1e-8, so isolated sign flips of ~0 gradients are expected)."""
+    g = load("style_step32_b2.npz")
+    dev = dict(zip([str(k) for k in g["ref_fp32_dev_keys"]], [float(v) for v in g["ref_fp32_dev_vals"]]))
+    try:
+        out = run_step(vp, "fp32")
+        for i, k in enumerate(NAMES):
+            assert abs(out["losses"][i] - g["losses"][i]) <= 2e-5 * abs(g["losses"][i]), (k, out["losses"][i], g["losses"][i])
+        bad = []
+        for k in g.files:
+            if k.startswith("grad/"):
+                want, got = g[k], out[k]
+                if want[2] < 1e-12:
+                    assert got[2] < 1e-6, k                      # identically-zero gradients (biases in front of InstanceNorm)
+                    continue
+                t = max(1e-4, 10 * dev[k])
+                r = max(abs(got[1] - want[1]) / want[1], float(np.abs(got[3:] - want[3:]).max() / want[2]))
+                if r >= t:
+                    bad.append((k, r, t))
+            elif k.startswith("upd/"):
+                want, got = g[k], out[k]
+                if want[1] > 1e-6 and abs(got[1] - want[1]) / want[1] > 2e-2:
+                    bad.append((k, abs(got[1] - want[1]) / want[1], 2e-2))
+        assert not bad, "\n".join(f"{k}: {r:.3e} >= {t:.1e}" for k, r, t in bad)
+    finally:
+        vp.set_precision("bf16")
+
+
+def test_style_gan_step_bf16(vp):
+    """bf16 tensor-core mode: the seven losses within 3e-2, finite gradients of the right magnitude everywhere, and no
+    contraction on the CUDA-core engine (the 3 / 4 / 6 / 32-channel layers run zero-padded on tcgen05)."""
+    from vae_play_b200 import _lib
+    g = load("style_step32_b2.npz")
+    simt0 = _lib.simt_bf16_count()
+    out = run_step(vp, "bf16")
+    assert _lib.simt_bf16_count() == simt0
+    for i, k in enumerate(NAMES):
+        assert abs(out["losses"][i] - g["losses"][i]) <= 3e-2 * abs(g["losses"][i]), (k, out["losses"][i], g["losses"][i])
+    n = 0
+    for k in g.files:
+        if k.startswith("grad/") and g[k][2] > 1e-12:
+            assert np.isfinite(out[k]).all(), k
+            assert abs(out[k][1] - g[k][1]) / g[k][1] < 0.5, (k, out[k][1], g[k][1])
+            n += 1
+    assert n > 100

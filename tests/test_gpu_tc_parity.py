@@ -270,3 +270,89 @@ def test_blocks_conv2d_gradients_pinned_pattern_bf16(vp, name, ci, co, k, s, bn,
     for got, want, nm in checks:
         r = rel(npy(got), want)
         assert r < GRAD_TOL_BF16, f"{name} {nm}: rel {r:.3e}"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# channel counts that are not multiples of 64: the padded tcgen05 route (3, 4, 6, 16, 32 ... channels)
+# ---------------------------------------------------------------------------------------------------------------------
+PADDED_SHAPES = [
+    # kind, cin, cout, k, stride, pad, out_pad, hw, batch
+    ("conv", 3, 64, 5, 2, 2, 0, 32, 4),        # RGB first layer (BASELINE config 1)
+    ("conv", 32, 64, 5, 2, 2, 0, 32, 4),       # VAE-GAN discriminator conv.1 (networks.py:162)
+    ("conv", 32, 32, 3, 1, 1, 0, 24, 3),       # Style_GAN full-resolution 3x3 convs (network_Style_GAN.py:96,119-120)
+    ("conv", 4, 32, 3, 1, 1, 0, 20, 2),        # Generator.conv1 (:95)
+    ("conv", 6, 64, 5, 1, 2, 0, 16, 2),        # Style discriminator first layer (:205)
+    ("conv", 16, 48, 3, 2, 1, 0, 18, 3),
+    ("conv", 64, 96, 4, 2, 1, 0, 16, 2),       # k4 s2 p1 down-sampling (:98-101), ragged output channels
+    ("convT", 64, 32, 4, 2, 1, 0, 8, 3),       # Generator.final[0] (:116)
+    ("convT", 10, 6, 5, 2, 2, 1, 7, 2),
+    ("linear", 96, 40, 1, 1, 0, 0, 1, 48),
+    ("linear", 32, 2, 1, 1, 0, 0, 1, 64),      # DirectDecoder.xy_fc[1] (networks.py:136)
+]
+
+
+@pytest.mark.parametrize("kind,cin,cout,k,stride,pad,out_pad,hw,b", PADDED_SHAPES)
+def test_padded_route_vs_float64(vp, kind, cin, cout, k, stride, pad, out_pad, hw, b):
+    """fwd / dgrad / wgrad of layers with arbitrary channel counts in bf16 mode: zero-padded onto the tcgen05 kernels, compared
+    with float64 on the same bf16-quantised operands; no CUDA-core contraction is launched."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    VF.set_grad_sinks({})
+    g = torch.Generator(device="cuda").manual_seed(31)
+    r = lambda *s: torch.randn(*s, device="cuda", generator=g) * 0.1
+    if kind == "conv":
+        layer, w = VF.TapLayer("conv", cin, cout, k=k, stride=stride, pad=pad), r(cout, cin, k, k)
+    elif kind == "convT":
+        layer, w = VF.TapLayer("convT", cin, cout, k=k, stride=stride, pad=pad, out_pad=out_pad), r(cin, cout, k, k)
+    else:
+        layer, w = VF.TapLayer("linear", cin, cout), r(cout, cin)
+    x = torch.randn(b, hw, hw, cin, device="cuda", generator=g).to(torch.bfloat16)
+    bias = torch.randn(cout, device="cuda", generator=g)
+    simt0 = _lib.simt_bf16_count()
+    y32 = layer.fwd(x, w, bias, out_dtype=torch.float32)
+    y16 = layer.fwd(x, w, bias, "relu")
+    dy = torch.randn(y32.shape, device="cuda", generator=g).to(torch.bfloat16)
+    dx32 = layer.dgrad(dy, w, tuple(x.shape), out_dtype=torch.float32)
+    dw = layer.wgrad(x, dy, w)
+    assert _lib.simt_bf16_count() == simt0, "a bf16 contraction fell back to the CUDA-core engine"
+    xd, wd, dyd = x.double().permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), dy.double().permute(0, 3, 1, 2)
+    if kind == "conv":
+        want_y = F.conv2d(xd, wd, bias.double(), stride=stride, padding=pad)
+        want_dx = torch.nn.grad.conv2d_input(xd.shape, wd, dyd, stride=stride, padding=pad)
+        want_dw = torch.nn.grad.conv2d_weight(xd, wd.shape, dyd, stride=stride, padding=pad)
+    elif kind == "convT":
+        want_y = F.conv_transpose2d(xd, wd, bias.double(), stride=stride, padding=pad, output_padding=out_pad)
+        want_dx = F.conv2d(dyd, wd, None, stride=stride, padding=pad)
+        want_dw = torch.nn.grad.conv2d_weight(dyd, wd.shape, xd, stride=stride, padding=pad)
+    else:
+        x2, d2 = xd.reshape(b, cin), dyd.reshape(b, cout)
+        want_y = (x2 @ wd.T + bias.double()).reshape(b, cout, 1, 1)
+        want_dx = (d2 @ wd).reshape(b, cin, 1, 1)
+        want_dw = d2.T @ x2
+    assert rel(npy(y32), npy(want_y.permute(0, 2, 3, 1))) < TOL_FP32_OUT
+    assert rel(npy(y16), npy(torch.relu(want_y).permute(0, 2, 3, 1))) < TOL_BF16_STORE
+    assert rel(npy(dx32), npy(want_dx.permute(0, 2, 3, 1))) < TOL_FP32_OUT
+    assert rel(npy(dw), npy(want_dw)) < TOL_FP32_OUT
+
+
+def test_bf16_discriminator_step_runs_on_tensor_cores(vp):
+    """VAE-GAN Discriminator (networks.py:151-195: 1 -> 32 -> 64 -> 128 -> 256 channels) forward + backward in REC and GAN mode
+    in bf16: no contraction on the CUDA-core engine (round 1 ran the 1 -> 32 and 32 -> 64 layers there)."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    from vae_play_b200.models.networks import Discriminator
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    VF.set_grad_sinks({})
+    torch.manual_seed(0)
+    d = Discriminator(channel_in=1, recon_level=3, iter_level=3).cuda().train()
+    xs = [torch.rand(4, 1, 64, 64, device="cuda").requires_grad_(i > 0) for i in range(3)]
+    simt0 = _lib.simt_bf16_count()
+    rec = d(*xs, "REC")
+    gan = d(*xs, "GAN")
+    (rec.float().square().sum() * 1e-3 + gan.float().sum()).backward()
+    torch.cuda.synchronize()
+    assert _lib.simt_bf16_count() == simt0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in d.parameters())

@@ -68,7 +68,7 @@ def parse_header(path: str = HEADER_PATH):
 
 
 _PROTOS = parse_header()
-PLAIN = {k: v for k, v in _PROTOS.items() if k in ("vp_last_error", "vp_abi_version", "vp_device_arch", "vp_launch_count")}
+PLAIN = {k: v for k, v in _PROTOS.items() if k in ("vp_last_error", "vp_abi_version", "vp_device_arch", "vp_launch_count", "vp_simt_bf16_count")}
 SIGNATURES = {k: v[1] for k, v in _PROTOS.items() if k not in PLAIN}     # compute entry points: int return code
 
 _lib = None
@@ -133,3 +133,7 @@ def call(name: str, *args):
 
 def launch_count() -> int:
     return int(load().vp_launch_count())
+
+
+def simt_bf16_count() -> int:
+    return int(load().vp_simt_bf16_count())

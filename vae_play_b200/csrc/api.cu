@@ -18,6 +18,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+static std::atomic<uint64_t> g_simt_bf16{0};
+void count_simt_bf16() { g_simt_bf16.fetch_add(1, std::memory_order_relaxed); }
 bool pdl_enabled() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("VP_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -157,6 +159,7 @@ using namespace vp;
 extern "C" const char* vp_last_error(void) { return g_err; }
 extern "C" int vp_abi_version(void) { return VP_ABI_VERSION; }
 extern "C" uint64_t vp_launch_count(void) { return g_launches.load(); }
+extern "C" uint64_t vp_simt_bf16_count(void) { return g_simt_bf16.load(); }
 
 namespace vp { void set_splitk_workspace(void* ptr, size_t bytes); }
 /* Scratch memory for split-K partial sums (skinny contractions such as the fc layers): a device buffer owned by the caller,

@@ -16,6 +16,7 @@ typedef __nv_bfloat16 bf16;
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+void count_simt_bf16();      // a bf16 contraction that fell back to the CUDA-core engine (vp_simt_bf16_count: tests assert 0)
 
 // ---- programmatic dependent launch ------------------------------------------------------------------------------------
 // Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may be scheduled while

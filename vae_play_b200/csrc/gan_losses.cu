@@ -33,7 +33,8 @@ __global__ void __launch_bounds__(256) feat_mse_bwd_kernel(const float* __restri
 // out = -log(s * p + c): (s, c) = (1, 1e-3) for the original images, (-1, 1 + 1e-3) for reconstructed / sampled    networks.py:276-278
 __global__ void __launch_bounds__(256) neglog_fwd_kernel(const float* __restrict__ p, float* __restrict__ out, int64_t n, float s, float c) {
     pdl_sync();
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = -logf(fmaf(s, p[i], c));
+    // clamped at 100 like torch's binary_cross_entropy (log >= -100): only reachable when the argument underflows to 0
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = fminf(-logf(fmaf(s, p[i], c)), 100.f);
 }
 __global__ void __launch_bounds__(256) neglog_bwd_kernel(const float* __restrict__ p, const float* __restrict__ g, float* __restrict__ dp, int64_t n, float s,
                                                          float c) {
@@ -87,6 +88,23 @@ __global__ void __launch_bounds__(256) kl_fwd_kernel(const float* __restrict__ m
     }
 }
 
+// out[b] = -log(s[b, label[b]]) (the pick of F.cross_entropy after the softmax); bwd: ds[b, j] = -g[b] / s[b, label[b]] at j = label[b]
+__global__ void __launch_bounds__(256) nll_pick_fwd_kernel(const float* __restrict__ s, const long long* __restrict__ label, float* __restrict__ out, int64_t rows,
+                                                           int cols) {
+    pdl_sync();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) out[r] = -logf(s[r * cols + (int)label[r]]);
+}
+__global__ void __launch_bounds__(256) nll_pick_bwd_kernel(const float* __restrict__ s, const long long* __restrict__ label, const float* __restrict__ g,
+                                                           float* __restrict__ ds, int64_t rows, int cols) {
+    pdl_sync();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * cols) return;
+    const int64_t r = i / cols;
+    const int j = (int)(i - r * cols);
+    ds[i] = j == (int)label[r] ? -g[r] / s[i] : 0.f;
+}
+
 inline unsigned grid_for(int64_t n) {
     int64_t b = (n + 255) / 256;
     if (b > 148 * 8) b = 148 * 8;
@@ -138,5 +156,18 @@ extern "C" int vp_kl_fwd(const float* mu, const float* logvar, int64_t ld, float
     VP_CHECK_ARG(mu && logvar && kl && rows > 0 && zdim > 0 && ld >= zdim, "vp_kl_fwd: bad arguments");
     launch_k(kl_fwd_kernel, dim3(grid_for(rows * 32)), dim3(256), 0, (cudaStream_t)stream, mu, logvar, ld, kl, rows, zdim);
     VP_CHECK_LAUNCH("vp_kl_fwd");
+    return VP_OK;
+}
+
+extern "C" int vp_nll_pick_fwd(const float* s, const int64_t* label, float* out, int64_t rows, int cols, void* stream) {
+    VP_CHECK_ARG(s && label && out && rows > 0 && cols > 0, "vp_nll_pick_fwd: bad arguments");
+    launch_k(nll_pick_fwd_kernel, dim3(grid_for(rows)), dim3(256), 0, (cudaStream_t)stream, s, (const long long*)label, out, rows, cols);
+    VP_CHECK_LAUNCH("vp_nll_pick_fwd");
+    return VP_OK;
+}
+extern "C" int vp_nll_pick_bwd(const float* s, const int64_t* label, const float* g, float* ds, int64_t rows, int cols, void* stream) {
+    VP_CHECK_ARG(s && label && g && ds && rows > 0 && cols > 0, "vp_nll_pick_bwd: bad arguments");
+    launch_k(nll_pick_bwd_kernel, dim3(grid_for(rows * cols)), dim3(256), 0, (cudaStream_t)stream, s, (const long long*)label, g, ds, rows, cols);
+    VP_CHECK_LAUNCH("vp_nll_pick_bwd");
     return VP_OK;
 }

@@ -574,3 +574,40 @@ class _WeightedSums(torch.autograd.Function):
 
 def weighted_sums(tensors, weights):
     return _WeightedSums.apply(list(weights), *tensors)
+
+
+class _NllPick(torch.autograd.Function):
+    """out[b] = -log(s[b, label[b]])"""
+
+    @staticmethod
+    def forward(ctx, s, label):
+        _require_cuda(s, "nll_pick")
+        s = s.float().contiguous()
+        label = label.to(torch.int64).contiguous()
+        rows, cols = s.shape
+        out = torch.empty(rows, dtype=torch.float32, device=s.device)
+        _lib.call("vp_nll_pick_fwd", _ptr(s), _ptr(label), _ptr(out), rows, cols, _stream())
+        ctx.save_for_backward(s, label)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        s, label = ctx.saved_tensors
+        rows, cols = s.shape
+        ds = torch.empty_like(s)
+        _lib.call("vp_nll_pick_bwd", _ptr(s), _ptr(label), _ptr(g.contiguous().float()), _ptr(ds), rows, cols, _stream())
+        return ds, None
+
+
+def cross_entropy(inputs, labels):
+    """``F.cross_entropy(inputs, labels)`` (mean over the batch): log-softmax of ``inputs`` -- which in train_Style_GAN.py:219 are
+    already softmax probabilities: the reference's double softmax is preserved -- then the negative log-likelihood of the label."""
+    s = softmax_rows(inputs.float().contiguous())
+    nll = _NllPick.apply(s, labels)
+    return weighted_sums([nll], [1.0 / nll.numel()])
+
+
+def binary_cross_entropy_const(p, target_one: bool):
+    """``F.binary_cross_entropy(p, ones)`` / ``(p, zeros)`` (mean): -mean(log p) / -mean(log(1 - p)), log clamped at -100."""
+    t = neglog(p, 1.0, 0.0) if target_one else neglog(p, -1.0, 1.0)
+    return weighted_sums([t], [1.0 / t.numel()])

@@ -255,14 +255,22 @@ class VaeGan(nn.Module):
         z, _ = VF.reparam_kl(mu, logvar, eps=eps)
         return z
 
-    def forward(self, x, gen_size=10, eps=None, z_p=None):
+    def forward(self, x, gen_size=10, eps=None, z_p=None, rng=None):
         """Reference VaeGan.forward (networks.py:233-258): train -> (x_tilde, disc_class [3B,1], disc_layer [3B,F], mus,
         log_variances, params [B,3]); eval -> (x_tilde, params) or, with x None, decoded samples.  ``eps`` / ``z_p`` (tests)
         replace the two random draws; by default both come from the device generator's Philox stream exactly as the
-        reference's ``normal_()`` / ``torch.randn(...).cuda()`` would consume it."""
+        reference's ``normal_()`` / ``torch.randn(...).cuda()`` would consume it.  ``rng=(seed, offset_dev)`` pins both draws to
+        a device-resident Philox offset instead (CUDA-graph replay: the caller advances it by ``2 * philox_policy(B*z)[1]`` per
+        step, see bench.py)."""
         if self.training:
             mus, log_variances = self.encoder(x)
-            z = self.reparameterize(mus, log_variances, eps)
+            if rng is not None and eps is None:
+                inc = VF.philox_policy(len(x) * self.z_size, VF._num_sms(x.device))[1]
+                z, _ = VF.reparam_kl(mus, log_variances, rng=(rng[0], 0, rng[1]))
+                if z_p is None:
+                    z_p = VF.philox_normal((len(x), self.z_size), x.device, rng=(rng[0], inc, rng[1]))
+            else:
+                z = self.reparameterize(mus, log_variances, eps)
             x_tilde = self.decoder(z)
             params = self.param_encoder(z)
             if z_p is None:

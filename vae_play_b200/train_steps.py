@@ -67,3 +67,48 @@ def vaegan_step(net: VaeGan, optimizers, x, targets, fused=True, eps=None, z_p=N
     for o in optimizers:
         o.step()
     return losses
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# config 5: train_Style_GAN.py::train_random_gan (:162-281)
+# ------------------------------------------------------------------------------------------------------------------------
+def style_reparameterization(mu, logvar, eps):
+    """train_Style_GAN.py:156-160: std = exp(logvar / 2); z = eps * std + mu with HOST-drawn eps (np.random.normal) -- the caller
+    supplies it (``eps`` [B, z_dim] on the device)."""
+    z, _ = VF.reparam_kl(mu.contiguous(), logvar.contiguous(), eps=eps)
+    return z
+
+
+def style_gan_step(G, E, D, g_opt, e_opt, d_opt, x_target, x_content, y_org, eps, sample_z):
+    """One train_random_gan iteration, statement for statement (including its order: E steps before the latent loss is formed, G
+    after it; the discriminator heads return probabilities that F.cross_entropy soft-maxes again).  Returns the seven logged losses."""
+    b = x_target.size(0)
+    e_opt.zero_grad()
+    g_opt.zero_grad()
+    mu, logvar = E(x_target)
+    encode_z = style_reparameterization(mu, logvar, eps)
+    x_rec = G(x_content, encode_z, y_org)
+    d_rec_valid, d_rec_type = D(x_rec, x_content, y_org)
+    g_rec_kl_loss = VB.weighted_sums([VB.kl_per_sample(mu, logvar)], [1.0])                     # 0.5 * sum(exp(lv) + mu^2 - lv - 1)
+    g_rec_d_loss = VB.weighted_sums([VB.binary_cross_entropy_const(d_rec_valid, True), VB.cross_entropy(d_rec_type, y_org)], [1.0, 1.0])
+    g_rec_pixel_loss = VF.l1_loss(x_target, x_rec)
+    x_gen = G(x_content, sample_z, y_org)
+    d_gen_valid, d_gen_type = D(x_gen, x_content, y_org)
+    g_gen_d_loss = VB.weighted_sums([VB.binary_cross_entropy_const(d_gen_valid, True), VB.cross_entropy(d_gen_type, y_org)], [1.0, 1.0])
+    g_loss = VB.weighted_sums([g_rec_pixel_loss, g_rec_d_loss, g_rec_kl_loss, g_gen_d_loss], [1.0, 1.0, 1.0, 1.0])
+    g_loss.backward(retain_graph=True)
+    e_opt.step()
+    _mu, _ = E(x_gen)
+    loss_latent = VB.weighted_sums([VF.l1_loss(sample_z, _mu)], [0.5])
+    loss_latent.backward()
+    g_opt.step()
+    d_opt.zero_grad()
+    d_real_valid, d_real_type = D(x_target, x_content, y_org)
+    d_fake_valid, d_fake_type = D(x_rec.detach(), x_content, y_org)
+    d_real_loss = VB.weighted_sums([VB.binary_cross_entropy_const(d_real_valid, True), VB.cross_entropy(d_real_type, y_org)], [1.0, 1.0])
+    d_fake_loss = VB.weighted_sums([VB.binary_cross_entropy_const(d_fake_valid, False), VB.cross_entropy(d_fake_type, y_org)], [1.0, 1.0])
+    d_adv_loss = VB.weighted_sums([d_real_loss, d_fake_loss], [0.5, 0.5])
+    d_adv_loss.backward()
+    d_opt.step()
+    return {"g_rec_kl_loss": g_rec_kl_loss, "g_rec_d_loss": g_rec_d_loss, "g_rec_pixel_loss": g_rec_pixel_loss, "g_gen_d_loss": g_gen_d_loss,
+            "loss_latent": loss_latent, "d_real_loss": d_real_loss, "d_fake_loss": d_fake_loss}
