@@ -214,6 +214,16 @@ int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, c
                            float* mean, float* invstd, float* scale, float* shift, int64_t rows, int c,
                            int64_t* num_batches_tracked, void* stream);
 int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int prezeroed, void* stream);
+/* vp_conv_dgrad_cl of the layer that FOLLOWS a conv -> BatchNorm -> ReLU block (models/networks.py:27-30,42-46), fused with the
+ * first pass of that block's BatchNorm backward: dx (= dL/da of the block, bf16) is stored as usual, and the epilogue -- which
+ * TMA-loads the matching tile of the block's pre-norm output y_prev [n,hi,wi,ci] -- accumulates d = dx * (y*scale + shift > 0):
+ * parts[*nparts][2][ci] fp32 = per-CTA (sum d, sum d*(y - mean)).  vp_norm_bwd_finish_parts turns them into the `sums` that
+ * vp_norm_bwd_apply consumes; the separate vp_norm_bwd_reduce pass over (y, da) disappears.  VP_EUNSUPPORTED (nothing launched)
+ * when no kernel with this epilogue serves the shape. */
+int vp_conv_dgrad_cl_bnred(const VpConvGeom* g, const void* dy, const void* w_cl, void* dx, const void* y_prev,
+                           const float* scale, const float* shift, const float* mean, float* parts, int capacity,
+                           int* nparts, void* stream);
+int vp_norm_bwd_finish_parts(const float* parts, int nparts, const float* invstd, double* sums, int c, void* stream);
 /* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
 int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
 

@@ -877,3 +877,37 @@ def test_bf16_wire_pack_and_optimizer(vp):
                 close(npy(p), npy(q), 1e-6, f"RMSprop on wire gradients, step {step}")
     finally:
         gb.remove()
+
+
+def test_fused_bn_backward_matches_unfused(vp):
+    """BatchNorm backward, first pass: done by the epilogue of the consumer's data-gradient kernel (vp_conv_dgrad_cl_bnred, taken
+    at the bench size by the stride-2 sub-lattice kernel for decoder.conv.1 <- decoder.conv.2) == the separate reduce pass.
+    Same operands, same dx; only the summation (per-CTA fp32 partials, then double) differs."""
+    import copy
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    from vae_play_b200.models.networks import VaeGan
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    VF.set_grad_sinks({})
+    torch.manual_seed(0)
+    ref = VaeGan(64, 128).cuda().train()
+    x = torch.rand(256, 1, 64, 64, device="cuda")
+    eps = torch.randn(256, 128, device="cuda")
+    res, launches = [], []
+    try:
+        for fused in (False, True):
+            VF.set_fuse_bn_backward(fused)
+            m = copy.deepcopy(ref)
+            xt, mulv, kl = m.vae_forward(x, eps=eps)
+            n0 = _lib.launch_count()
+            VF.vae_loss(x, xt, kl).backward()
+            torch.cuda.synchronize()
+            launches.append(_lib.launch_count() - n0)
+            res.append({k: npy(p.grad) for k, p in m.named_parameters() if p.grad is not None})
+    finally:
+        VF.set_fuse_bn_backward(True)
+    assert launches[1] < launches[0], launches          # at least one reduce pass (+ its memset-free launch) disappeared
+    for k in res[0]:
+        r = rel_l2(res[1][k], res[0][k])
+        assert r < 2e-3, f"{k}: rel-L2 {r:.3e} fused vs unfused BatchNorm backward"

@@ -105,13 +105,18 @@ int run_tapgemm(const TapGemm& p, int dtype, int engine, cudaStream_t s) {
 // wlay: 0 = packed panels Wp[tap][N][K]; 1 = the module's weight in channels-last order [d0][kh][kw][d1] read in place, with
 // (N, K) = (d0, d1) -> K-major operand; 2 = same with (N, K) = (d1, d0) -> MN-major operand
 struct StatOut { float* parts; int capacity; int* nparts; };
+struct BnRed { const void* y; const float *scale, *shift, *mean; };
 
 int conv_like(const VpConvGeom& g, bool gather, const void* A, int ha, int wa, int K, void* D, int hd, int wd, int N,
               const void* wp, const float* bias, int act, float slope, int dtype, int out_dtype, int engine, cudaStream_t s, int wlay = 0,
-              const StatOut* st = nullptr) {
+              const StatOut* st = nullptr, const BnRed* bn = nullptr) {
     TapGemm p;
     memset(&p, 0, sizeof(p));
     if (st) { p.stat_parts = st->parts; p.stat_capacity = st->capacity; p.stat_nparts = st->nparts; }
+    if (bn) {
+        if (!gather) { set_error("fused BatchNorm-backward reduction: only gather-form data gradients"); return VP_EUNSUPPORTED; }
+        p.bn_y = bn->y; p.bn_scale = bn->scale; p.bn_shift = bn->shift; p.bn_mean = bn->mean;
+    }
     p.out_dtype = out_dtype;
     const int64_t T = (int64_t)g.kh * g.kw;
     if (wlay == 0) { p.w_st = (int64_t)N * K; p.w_sn = K; p.w_sk = 1; }
@@ -250,6 +255,21 @@ extern "C" int vp_conv_dgrad_cl(const VpConvGeom* g, const void* dy, const void*
     VP_CHECK_ARG(dy && w_cl && dx, "vp_conv_dgrad_cl: null pointer");
     return conv_like(*g, g->transposed != 0, dy, g->ho, g->wo, g->co, dx, g->hi, g->wi, g->ci, w_cl, nullptr, VP_ACT_NONE, 0.f, VP_BF16,
                      out_dtype, VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 1 : 2);
+}
+
+/* vp_conv_dgrad_cl of the layer that FOLLOWS a conv -> BatchNorm -> ReLU block, fused with the first pass of that block's
+ * BatchNorm backward: dx = dL/da of the block is stored as usual, and per-CTA partial sums of d = dx * (y*scale + shift > 0) and of
+ * d * (y - mean) are returned in parts[*nparts][2][ci] (vp_norm_bwd_finish_parts -> the `sums` vp_norm_bwd_apply consumes).
+ * VP_EUNSUPPORTED when the shape is not served by a kernel with this epilogue (the caller runs the plain vp_conv_dgrad_cl and
+ * vp_norm_bwd_reduce instead); nothing has been launched in that case. */
+extern "C" int vp_conv_dgrad_cl_bnred(const VpConvGeom* g, const void* dy, const void* w_cl, void* dx, const void* y_prev, const float* scale,
+                                      const float* shift, const float* mean, float* parts, int capacity, int* nparts, void* stream) {
+    if (!check_geom(g, "vp_conv_dgrad_cl_bnred")) return VP_EINVAL;
+    VP_CHECK_ARG(dy && w_cl && dx && y_prev && scale && shift && mean && parts && nparts && capacity > 0, "vp_conv_dgrad_cl_bnred: null pointer");
+    StatOut st{parts, capacity, nparts};
+    BnRed bn{y_prev, scale, shift, mean};
+    return conv_like(*g, g->transposed != 0, dy, g->ho, g->wo, g->co, dx, g->hi, g->wi, g->ci, w_cl, nullptr, VP_ACT_NONE, 0.f, VP_BF16,
+                     VP_BF16, VP_ENGINE_TC, (cudaStream_t)stream, g->transposed ? 1 : 2, &st, &bn);
 }
 
 extern "C" int vp_conv_wgrad_cl(const VpConvGeom* g, const void* x, const void* dy, float* dw_cl, int accumulate, void* stream) {

@@ -164,6 +164,12 @@ struct TapGemm {
     float* stat_parts;
     int stat_capacity;
     int* stat_nparts;
+    // optional fused BatchNorm-backward reduction (tcgen05 engine, the data gradient that FOLLOWS a conv -> BatchNorm -> ReLU block):
+    // D is dL/da of that block, bn_y its pre-norm conv output [n, hd, wd, N] bf16.  The epilogue forms d = D * (y*scale + shift > 0)
+    // and accumulates sum d and sum d*(y - mean) per channel into stat_parts[cta][2][N] (vp_norm_bwd_finish_parts adds them up):
+    // the separate reduce pass over (y, da) disappears.  D itself is stored unmasked.
+    const void* bn_y;
+    const float *bn_scale, *bn_shift, *bn_mean;
     TapList taps;
 };
 

@@ -429,6 +429,31 @@ __global__ void __launch_bounds__(1024) finalize_parts_kernel(const float* __res
 }  // namespace
 }  // namespace vp
 
+namespace vp {
+namespace {
+// parts[nparts][2][C] fp32 (sum d, sum d*(x - mean)) -> sums[2][C] double = (sum d, invstd * sum d*(x - mean)), fixed order
+__global__ void __launch_bounds__(256) bwd_finish_parts_kernel(const float* __restrict__ parts, int nparts, const float* __restrict__ invstd,
+                                                               double* __restrict__ sums, int C) {
+    pdl_sync();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    double a = 0, b = 0;
+    for (int i = 0; i < nparts; ++i) { a += (double)parts[(size_t)i * 2 * C + c]; b += (double)parts[(size_t)i * 2 * C + C + c]; }
+    sums[c] = a;
+    sums[C + c] = b * (double)invstd[c];
+}
+}  // namespace
+}  // namespace vp
+
+/* The `sums` of vp_norm_bwd_reduce (double [2][c]: sum d, sum d*xhat) from the per-CTA partial sums a fused data-gradient
+ * epilogue delivered (vp_conv_dgrad_cl_bnred): added in double in a fixed order, the common factor invstd applied here. */
+extern "C" int vp_norm_bwd_finish_parts(const float* parts, int nparts, const float* invstd, double* sums, int c, void* stream) {
+    VP_CHECK_ARG(parts && nparts > 0 && invstd && sums && c > 0, "vp_norm_bwd_finish_parts: bad arguments");
+    launch_k(bwd_finish_parts_kernel, dim3((c + 255) / 256), dim3(256), 0, (cudaStream_t)stream, parts, nparts, invstd, sums, c);
+    VP_CHECK_LAUNCH("vp_norm_bwd_finish_parts");
+    return VP_OK;
+}
+
 /* vp_norm_finalize for BatchNorm statistics delivered as per-CTA partial sums by a GEMM epilogue (vp_conv_fwd_cl_stats,
  * vp_thin_conv_fwd_stats): parts[nparts][2][c] fp32, added in double in a fixed order (deterministic). */
 extern "C" int vp_norm_finalize_parts(const float* parts, int nparts, const float* gamma, const float* beta, float* running_mean,

@@ -41,6 +41,7 @@ struct GwinParams {
     int halo_bytes;            // per brick, largest class, rounded up to 1024
     int tiles_w, tiles_h, ntiles_n, total_tiles;
     float* stat_parts;
+    const float *bn_scale, *bn_shift, *bn_mean;      // non-null: fused BatchNorm-backward reduction (mapY = the block's pre-norm output)
     int ncls;
     GClass cls[kMaxCls];
     int8_t sy[kMaxTaps], sx[kMaxTaps], widx[kMaxTaps];      // window offset inside the class halo, weight tap index
@@ -60,7 +61,8 @@ __device__ __forceinline__ GTile gdecode(const GwinParams& p, int q, int BN) {
 
 template <int BN, int BSTAGES>
 __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid_constant__ InMaps mapsA, const __grid_constant__ CUtensorMap mapB,
-                                                                    const __grid_constant__ CUtensorMap mapD, const __grid_constant__ GwinParams p) {
+                                                                    const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapY,
+                                                                    const __grid_constant__ GwinParams p) {
     constexpr int kBBytes = BN * 128;
     constexpr int kTmemCols = 4 * BN;                    // 2 buffers x 2 bricks
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -75,7 +77,9 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
     uint64_t* b_empty = b_full + BSTAGES;
     uint64_t* acc_full = b_empty + BSTAGES;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    uint64_t* y_full = acc_empty + 2;                            // [4 warps][2]: y tiles of the fused BatchNorm-backward reduction
+    uint32_t* tmem_slot = (uint32_t*)(y_full + 8);
+    uint8_t* smem_y = (uint8_t*)(((uintptr_t)(tmem_slot + 4) + 1023) & ~(uintptr_t)1023);   // 4 warps x 2 x [32 rows][64 B]
     if (p.stat_parts)
         for (int i = threadIdx.x; i < 2 * kStatMaxN; i += kGThreads) s_stat[i] = 0.f;
 
@@ -90,6 +94,7 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
             for (int s = 0; s < BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
             mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
             mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+            for (int i = 0; i < 8; ++i) mbar_init(&y_full[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -182,18 +187,30 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
         const int r = lane_base + lane;
         const int by = r >> 3, bx = r & 7;
         uint8_t* my_stage = smem_out + (warp & 3) * 4096;
-        uint32_t i = 0, sg = 0;
+        uint8_t* my_y = smem_y + (warp & 3) * 4096;
+        uint64_t* my_ybar = y_full + (warp & 3) * 2;
+        const bool bn = p.bn_scale != nullptr;
+        constexpr int kChunksN = BN / 32, kChunks = 2 * kChunksN;       // chunks of a tile: (brick, 32-column group)
+        uint32_t i = 0, sg = 0, yk = 0;                                  // yk: y tiles consumed so far (buffer = yk & 1, parity = (yk >> 1) & 1)
         for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
             const GTile t = gdecode(p, q, BN);
             const uint32_t buf = i & 1, use = i >> 1;
+            // y tile of chunk k of this tile -> buffer (yk + k) & 1; two chunks are kept in flight
+            auto issue_y = [&](int k, uint32_t slot) {
+                const int br = k / kChunksN, c = (k % kChunksN) * 32;
+                mbar_expect_tx(&my_ybar[slot], 2048);
+                tma_load_4d(my_y + slot * 2048, &mapY, &my_ybar[slot], t.col0 + c, t.gx0 + br * kBrickW, t.gy0 + (warp & 3) * 4, t.n);
+            };
+            if (bn && lane == 0) { issue_y(0, yk & 1); if (kChunks > 1) issue_y(1, (yk + 1) & 1); }      // (N is a multiple of BN here)
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
+            int k = 0;
 #pragma unroll 1
             for (int br = 0; br < 2; ++br) {
                 const int gy = t.gy0 + by, gx = t.gx0 + br * kBrickW + bx;
                 const uint32_t row_mask = __ballot_sync(0xffffffffu, gy < p.gh && gx < p.gw);
 #pragma unroll 1
-                for (int c = 0; c < BN; c += 32, ++sg) {
+                for (int c = 0; c < BN; c += 32, ++sg, ++k) {
                     if (t.col0 + c >= p.N) break;
                     uint8_t* st = my_stage + (sg & 1) * 2048;
                     uint32_t v[32];
@@ -204,7 +221,17 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
                     stage_chunk32_sw64(st, lane, t.col0 + c, v, p.bias, p.act, p.slope);
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (p.stat_parts) stats_chunk32_sw64(st, lane, s_stat + t.col0 + c, s_stat + kStatMaxN + t.col0 + c, row_mask);
+                    if (bn) {
+                        const uint32_t slot = yk & 1;
+                        mbar_wait(&my_ybar[slot], (yk >> 1) & 1);
+                        bnred_chunk32_sw64(st, my_y + slot * 2048, lane, s_stat + t.col0 + c, s_stat + kStatMaxN + t.col0 + c, row_mask,
+                                           p.bn_scale + t.col0 + c, p.bn_shift + t.col0 + c, p.bn_mean + t.col0 + c);
+                        __syncwarp();                                  // every lane is done with this y buffer before it is refilled
+                        if (lane == 0 && k + 2 < kChunks) issue_y(k + 2, slot);
+                        ++yk;
+                    } else if (p.stat_parts) {
+                        stats_chunk32_sw64(st, lane, s_stat + t.col0 + c, s_stat + kStatMaxN + t.col0 + c, row_mask);
+                    }
                     if (lane == 0) {
                         tma_store_4d(&mapD, st, t.col0 + c, t.gx0 + br * kBrickW, t.gy0 + (warp & 3) * 4, t.n);
                         tma_store_commit();
@@ -230,8 +257,10 @@ __global__ void __launch_bounds__(kGThreads, 1) tapgemm_gwin_kernel(const __grid
 }
 
 template <int BN, int BSTAGES>
-int launch_gwin(const InMaps& mA, const CUtensorMap& mB, const CUtensorMap& mD, const GwinParams& gp, cudaStream_t s) {
-    const int smem_bytes = smem_for_occupancy(kAStages * 2 * gp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 + (2 * kAStages + 2 * BSTAGES + 4) * 8 + 16 + 1024, 1);
+int launch_gwin(const InMaps& mA, const CUtensorMap& mB, const CUtensorMap& mD, const CUtensorMap& mY, const GwinParams& gp, cudaStream_t s) {
+    // + 8 y barriers, the TMEM slot, and (1 KB-aligned) 4 x 2 x 2 KB of y staging tiles for the fused BatchNorm-backward reduction
+    const int smem_bytes = smem_for_occupancy(kAStages * 2 * gp.halo_bytes + BSTAGES * BN * 128 + 4 * 2 * 2048 + 2 * kStatMaxN * 4 +
+                                              (2 * kAStages + 2 * BSTAGES + 4 + 8) * 8 + 16 + 1024 + 1024 + 4 * 2 * 2048, 1);
     if (smem_bytes > 227 * 1024) return VP_EUNSUPPORTED;
     static int attr_set = 0;
     if (attr_set < smem_bytes) {
@@ -240,7 +269,7 @@ int launch_gwin(const InMaps& mA, const CUtensorMap& mB, const CUtensorMap& mD, 
         attr_set = smem_bytes;
     }
     const int grid = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
-    launch_k(tapgemm_gwin_kernel<BN, BSTAGES>, dim3(grid), dim3(kGThreads), smem_bytes, s, mA, mB, mD, gp);
+    launch_k(tapgemm_gwin_kernel<BN, BSTAGES>, dim3(grid), dim3(kGThreads), smem_bytes, s, mA, mB, mD, mY, gp);
     VP_CHECK_LAUNCH("tapgemm_gwin");
     return VP_OK;
 }
@@ -316,6 +345,14 @@ int launch_tapgemm_gwin(const TapGemm& p, cudaStream_t s) {
     if (encode_weight_map(&mB, p, false, BN)) return VP_EUNSUPPORTED;
     if (encode_out_map(&mD, p.D, p.N, p.hd, p.wd, p.n, 1, 0, 0, kBrickW, 4, 1)) return VP_EUNSUPPORTED;
     gp.stat_parts = nullptr;
+    gp.bn_scale = gp.bn_shift = gp.bn_mean = nullptr;
+    CUtensorMap mY = mD;
+    if (p.bn_y) {
+        // fused BatchNorm-backward reduction: the same {32 ch, 8, 4, 1} SWIZZLE_64B boxes are LOADED from the block's pre-norm output
+        if (!p.stat_parts || !p.bn_scale || !p.bn_shift || !p.bn_mean || p.N % BN != 0) return VP_EUNSUPPORTED;
+        if (encode_out_map(&mY, const_cast<void*>(p.bn_y), p.N, p.hd, p.wd, p.n, 1, 0, 0, kBrickW, 4, 1)) return VP_EUNSUPPORTED;
+        gp.bn_scale = p.bn_scale; gp.bn_shift = p.bn_shift; gp.bn_mean = p.bn_mean;
+    }
     if (p.stat_parts) {
         if (p.bias || p.act != VP_ACT_NONE || p.N > kStatMaxN) return VP_EUNSUPPORTED;
         const int g = gp.total_tiles < num_sms() ? gp.total_tiles : num_sms();
@@ -323,7 +360,7 @@ int launch_tapgemm_gwin(const TapGemm& p, cudaStream_t s) {
         if (p.stat_nparts) *p.stat_nparts = g;
         gp.stat_parts = p.stat_parts;
     }
-    return BN == 128 ? launch_gwin<128, 4>(mA, mB, mD, gp, s) : launch_gwin<64, 6>(mA, mB, mD, gp, s);
+    return BN == 128 ? launch_gwin<128, 4>(mA, mB, mD, mY, gp, s) : launch_gwin<64, 6>(mA, mB, mD, mY, gp, s);
 }
 
 }  // namespace vp

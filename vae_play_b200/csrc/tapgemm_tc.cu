@@ -450,6 +450,11 @@ bool tc_available() {
 // All phases share A, Wp, D, K, N, as, ds, bias, act; they differ in (gh, gw, doy, dox, taps).
 int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) {
     const TapGemm& p = phases[0];
+    if (p.bn_y) {
+        // fused BatchNorm-backward reduction: only the kernels that carry that epilogue may take the problem
+        if (nphases == 1 && tc_variant() != 2) return launch_tapgemm_gwin(phases[0], s);
+        return VP_EUNSUPPORTED;
+    }
     // stride-1 tap sets go to the windowed (halo re-use) kernel first; VP_TC_VARIANT=2 disables it (A/B measurements)
     if (tc_variant() != 2 && nphases == 1) {
         const int rcg = launch_tapgemm_gwin(phases[0], s);

@@ -275,6 +275,36 @@ __device__ __forceinline__ void stats_chunk32_sw64(const uint8_t* stile, int lan
     }
 }
 
+// Fused BatchNorm-backward reduction of a dgrad epilogue: `stile` holds the 32 x 32 chunk of dL/da about to be stored, `ytile` the
+// matching chunk of the block's pre-norm conv output (TMA-loaded with the same box / swizzle, hence the same addresses).  Per
+// channel: d = da * (y*scale + shift > 0);  sum d  and  sum d*(y - mean)  go to the CTA's shared accumulators.  sc / sh / mu
+// point at this chunk's first channel.  Same lane mapping as stats_chunk32_sw64 (lane = row parity, 32-bit word).
+__device__ __forceinline__ void bnred_chunk32_sw64(const uint8_t* stile, const uint8_t* ytile, int lane, float* s_sum, float* s_q, uint32_t row_mask,
+                                                   const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ mu) {
+    const int h = lane >> 4, w = lane & 15;
+    const float sc0 = sc[2 * w], sc1 = sc[2 * w + 1], sh0 = sh[2 * w], sh1 = sh[2 * w + 1], mu0 = mu[2 * w], mu1 = mu[2 * w + 1];
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int r = 2 * i + h;
+        const int off = r * 64 + (((w >> 2) ^ (i & 3)) << 4) + (w & 3) * 4;
+        uint32_t dw = *reinterpret_cast<const uint32_t*>(stile + off);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(ytile + off);
+        dw = ((row_mask >> r) & 1u) ? dw : 0u;
+        const float ylo = __uint_as_float(yw << 16), yhi = __uint_as_float(yw & 0xffff0000u);
+        const float dlo = fmaf(ylo, sc0, sh0) > 0.f ? __uint_as_float(dw << 16) : 0.f;
+        const float dhi = fmaf(yhi, sc1, sh1) > 0.f ? __uint_as_float(dw & 0xffff0000u) : 0.f;
+        s0 += dlo; q0 = fmaf(dlo, ylo - mu0, q0);
+        s1 += dhi; q1 = fmaf(dhi, yhi - mu1, q1);
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 16); s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    q0 += __shfl_xor_sync(0xffffffffu, q0, 16); q1 += __shfl_xor_sync(0xffffffffu, q1, 16);
+    if (h == 0) {
+        atomicAdd(s_sum + 2 * w, s0); atomicAdd(s_sum + 2 * w + 1, s1);
+        atomicAdd(s_q + 2 * w, q0); atomicAdd(s_q + 2 * w + 1, q1);
+    }
+}
+
 // same for a 64-column [32 rows][128 B] SWIZZLE_128B staging tile: lane = 32-bit word (two channels), all 32 rows
 __device__ __forceinline__ void stats_group64_sw128(const uint8_t* stile, int lane, float* s_sum, float* s_sq) {
     float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;

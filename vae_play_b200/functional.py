@@ -105,6 +105,11 @@ def set_epilogue_stats(on: bool):
     _STATE["epilogue_stats"] = bool(on)
 
 
+def set_fuse_bn_backward(on: bool):
+    """BatchNorm backward: first pass in the epilogue of the consumer's data-gradient kernel (default) or as its own pass (tests)."""
+    _STATE["fuse_bn_bwd"] = bool(on)
+
+
 def set_pad_route(on: bool):
     """bf16 layers whose channel counts are not multiples of 64: zero-pad onto the tcgen05 kernels (default) or fall back to the
     packed route (CUDA-core kernel unless the shape happens to be tensor-core eligible) -- tests / A-B measurements."""
@@ -403,6 +408,28 @@ class TapLayer:
                       _STATE["engine"], _stream())
         return dx
 
+    def dgrad_bnred(self, dy, weight, x_shape, prev):
+        """Data gradient fused with the first pass of the PRODUCER block's BatchNorm backward (``prev``: that block's holder, see
+        ``fused_layer``).  Returns (dx, parts, nparts) or None when no kernel with that epilogue serves the shape."""
+        weight = weight.detach()
+        if dy.dtype != torch.bfloat16 or not self._cl(dy.dtype, weight) or _STATE.get("fuse_bn_bwd", True) is False:
+            return None
+        y = prev["y"]
+        if tuple(y.shape) != tuple(x_shape) or y.dtype != torch.bfloat16 or not y.is_contiguous():
+            return None
+        n, h, w, _ = x_shape
+        dx = torch.empty(x_shape, dtype=torch.bfloat16, device=dy.device)
+        g = self._layer_geom(n, h, w, dy.shape[1], dy.shape[2])
+        cap = 2 * _num_sms(dy.device)
+        parts = torch.empty(cap * 2 * self.cin, dtype=torch.float32, device=dy.device)
+        nparts = C.c_int(0)
+        rc = _lib.load().vp_conv_dgrad_cl_bnred(C.byref(g), _ptr(dy), _ptr(self._shadow(weight)), _ptr(dx), _ptr(y), _ptr(prev["scale"]),
+                                                _ptr(prev["shift"]), _ptr(prev["mean"]), _ptr(parts), cap, C.byref(nparts), _stream())
+        if rc == -3:          # VP_EUNSUPPORTED: nothing was launched
+            return None
+        _lib.check(rc, "vp_conv_dgrad_cl_bnred")
+        return dx, parts, nparts.value
+
     def wgrad(self, x, dy, weight):
         n, h, w, _ = x.shape
         dt = x.dtype
@@ -457,9 +484,10 @@ class _FusedLayerFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, gamma, beta, layer: TapLayer, norm: NormCfg, act, slope, training, bn_module,
-                out_dtype):
+                out_dtype, holder=None, prev_bn=None):
         _require_cuda(x, "fused layer input")
         ctx.set_materialize_grads(False)
+        ctx.holder, ctx.prev_bn = holder, prev_bn
         dt = x.dtype
         out_dtype = out_dtype or dt
         ctx.layer, ctx.norm, ctx.act, ctx.slope = layer, norm, act, slope
@@ -529,6 +557,9 @@ class _FusedLayerFn(torch.autograd.Function):
         ctx.dims = (groups, rpg, cc, c)
         ctx.train_stats = bool(training or norm.kind == "instance")
         ctx.has_affine = gamma is not None
+        if holder is not None and norm.kind == "batch" and training and act == "relu" and dt == torch.bfloat16:
+            # what the NEXT layer's data-gradient epilogue needs to do the first pass of this block's BatchNorm backward
+            holder.update(ok=True, y=y, scale=scale, shift=shift, mean=mean)
         return a, y
 
     @staticmethod
@@ -539,7 +570,7 @@ class _FusedLayerFn(torch.autograd.Function):
         if norm.kind is None:
             x, weight, a = ctx.saved_tensors
             if da is None:
-                return (None,) * 12
+                return (None,) * 14
             da = da.contiguous()
             dt = x.dtype
             n, h, w, c = a.shape
@@ -577,13 +608,13 @@ class _FusedLayerFn(torch.autograd.Function):
             groups, rpg, cc, c = ctx.dims
             dt = y.dtype
             if da is None and dy_extra is None:
-                return (None,) * 12
+                return (None,) * 14
             if da is None:
                 # only the pre-norm output was used (Discriminator 'REC' mode, networks.py:180-185)
                 dy = dy_extra.contiguous()
                 dw = layer.wgrad(x, dy, weight)
                 dx = layer.dgrad(dy, weight, ctx.x_shape) if ctx.needs_input_grad[0] else None
-                return dx, dw, None, None, None, None, None, None, None, None, None, None
+                return dx, dw, None, None, None, None, None, None, None, None, None, None, None, None
             da = da.contiguous()
             dy = torch.empty_like(y)
             if ctx.few_rows:
@@ -594,8 +625,13 @@ class _FusedLayerFn(torch.autograd.Function):
                           _ptr(dbeta), _code(dt), rpg, cc, ACT[act], float(slope), _stream())
             elif ctx.train_stats:
                 sums = torch.empty(2 * groups * cc, dtype=torch.float64, device=dev)
-                _lib.call("vp_norm_bwd_reduce", _ptr(y), _ptr(da), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
-                          _ptr(sums), None, _code(dt), groups, rpg, cc, ACT[act], float(slope), _stream())
+                pre = ctx.holder.pop("pre", None) if ctx.holder else None
+                if pre is not None and pre[0] == da.data_ptr() and pre[1] == da._version and tuple(da.shape) == tuple(y.shape):
+                    # the consumer's data-gradient epilogue already reduced d = da * relu'(.) over this very tensor
+                    _lib.call("vp_norm_bwd_finish_parts", _ptr(pre[2]), pre[3], _ptr(invstd), _ptr(sums), cc, _stream())
+                else:
+                    _lib.call("vp_norm_bwd_reduce", _ptr(y), _ptr(da), _ptr(mean), _ptr(invstd), _ptr(scale), _ptr(shift),
+                              _ptr(sums), None, _code(dt), groups, rpg, cc, ACT[act], float(slope), _stream())
                 if ctx.has_affine:
                     dgamma = torch.empty(cc, dtype=torch.float32, device=dev)
                     dbeta = torch.empty(cc, dtype=torch.float32, device=dev)
@@ -613,12 +649,26 @@ class _FusedLayerFn(torch.autograd.Function):
                 # removed by the mean subtraction: its gradient is identically zero (the reference computes round-off noise)
                 dbias = torch.zeros(cc if norm.kind == "batch" else c, dtype=torch.float32, device=dev)
         dw = layer.wgrad(x, dy, weight)
-        dx = layer.dgrad(dy, weight, ctx.x_shape) if ctx.needs_input_grad[0] else None
-        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            prev = ctx.prev_bn
+            fused = layer.dgrad_bnred(dy, weight, ctx.x_shape, prev) if prev is not None and prev.get("ok") else None
+            if fused is not None:
+                dx, parts, nparts = fused
+                prev["pre"] = (dx.data_ptr(), dx._version, parts, nparts)
+            else:
+                dx = layer.dgrad(dy, weight, ctx.x_shape)
+        return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 
 def fused_layer(x, weight, bias, gamma, beta, layer, norm, act, slope, training, bn_module=None, out_dtype=None):
-    out = _FusedLayerFn.apply(x, weight, bias, gamma, beta, layer, norm, act, slope, training, bn_module, out_dtype)
+    # producer -> consumer link for the fused BatchNorm backward: the activated output of a conv-BatchNorm-ReLU block carries a
+    # holder; the layer that consumes it hands it to its own backward, whose data-gradient epilogue does the reduction pass
+    holder = {} if norm.kind == "batch" else None
+    out = _FusedLayerFn.apply(x, weight, bias, gamma, beta, layer, norm, act, slope, training, bn_module, out_dtype, holder,
+                              getattr(x, "_vp_bn", None))
+    if holder:
+        out[0]._vp_bn = holder
     if _TRACE is not None:
         _TRACE.append(out[0].detach())
     return out

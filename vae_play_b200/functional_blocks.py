@@ -515,7 +515,8 @@ def smooth_l1_sum(a, b, scale=1.0):
 class _KlPerSample(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mu, logvar):
-        _require_cuda(mu, "kl_per_sample")
+        if not mu.is_cuda:
+            raise _lib.VaePlayError(f"kl_per_sample: tensor is on {mu.device}; vae_play_b200 has no CPU path")
         if mu.stride(-1) != 1 or logvar.stride(-1) != 1 or mu.stride(0) != logvar.stride(0):
             mu, logvar = mu.contiguous(), logvar.contiguous()
         rows, z = mu.shape
