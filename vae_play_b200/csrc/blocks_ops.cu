@@ -503,7 +503,7 @@ extern "C" int vp_scse_bwd(const void* x, const void* cse, const void* sse, cons
     VP_CHECK_ARG(x && cse && sse && dy && dx && dcse_f32 && dsse && n > 0 && hw > 0 && c > 0, "vp_scse_bwd: bad arguments");
     VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_scse_bwd: bad dtype %d", dtype);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaMemsetAsync(dcse_f32, 0, sizeof(float) * (size_t)(n * c), s);
+    zero_async(dcse_f32, sizeof(float) * (size_t)(n * c), s);
     const unsigned g = grid_for(n * hw * 32);
     VP_DISPATCH_T(dtype, launch_k(scse_bwd_kernel<float>, dim3(g), dim3(256), 0, s, (const float*)x, (const float*)cse, (const float*)sse, (const float*)dy, (float*)dx, dcse_f32, (float*)dsse, n, hw, c),
                   launch_k(scse_bwd_kernel<bf16>, dim3(g), dim3(256), 0, s, (const bf16*)x, (const bf16*)cse, (const bf16*)sse, (const bf16*)dy, (bf16*)dx, dcse_f32, (bf16*)dsse, n, hw, c));
@@ -581,7 +581,7 @@ extern "C" int vp_dot(const void* a, const void* b, double* acc, int dtype, int6
     VP_CHECK_ARG(a && b && acc && n > 0, "vp_dot: bad arguments");
     VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_dot: bad dtype %d", dtype);
     cudaStream_t s = (cudaStream_t)stream;
-    cudaMemsetAsync(acc, 0, sizeof(double), s);
+    zero_async(acc, sizeof(double), s);
     VP_DISPATCH_T(dtype, launch_k(dot_kernel<float>, dim3(grid_for(n, 4)), dim3(256), 0, s, (const float*)a, (const float*)b, acc, n),
                   launch_k(dot_kernel<bf16>, dim3(grid_for(n, 4)), dim3(256), 0, s, (const bf16*)a, (const bf16*)b, acc, n));
     VP_CHECK_LAUNCH("vp_dot");
@@ -592,7 +592,7 @@ extern "C" int vp_dice_fwd(const float* p, const float* t, int64_t rows, int64_t
                            void* stream) {
     VP_CHECK_ARG(p && t && acc && counter && loss && rows > 0 && per > 0 && rows <= 65535, "vp_dice_fwd: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    cudaMemsetAsync(acc, 0, sizeof(double) * 3 * (size_t)rows, s);
+    zero_async(acc, sizeof(double) * 3 * (size_t)rows, s);
     int64_t bx = (per + 1023) / 1024;
     if (bx > 64) bx = 64;
     launch_k(dice_fwd_kernel, dim3((unsigned)bx, (unsigned)rows), dim3(256), 0, s, p, t, rows, per, smooth, acc, counter, loss);

@@ -56,9 +56,18 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
     at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &at;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    // Only while the stream is being CAPTURED into a CUDA graph: there a programmatic edge can only come from a kernel node, so a
+    // memset / copy node in front of this kernel stays a full dependency.  On a live stream the attribute also relaxes the order
+    // against a preceding cudaMemsetAsync (measured: a padded-bias torch.zeros + cast pair lost the race) -- and eager launches
+    // are bound by the host anyway.
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cfg.numAttrs = (pdl_enabled() && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusActive) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
+
+// Stream-ordered zero fill by one of OUR kernels (PDL-aware, a kernel node in captured graphs) instead of cudaMemsetAsync:
+// keeps the programmatic chain of the step graph unbroken and every producer / consumer of the buffer inside one ordering domain.
+int zero_async(void* ptr, size_t bytes, cudaStream_t s);
 
 #define VP_CHECK_ARG(cond, ...)                  \
     do {                                         \

@@ -273,6 +273,14 @@ __global__ void __launch_bounds__(256) cast_kernel(const TS* __restrict__ s, TD*
         Cvt<TD>::st(d + i, Cvt<TS>::ld(s + i));
 }
 
+// ---- zero fill (replaces cudaMemsetAsync inside the library) -------------------------------------------------------------------
+__global__ void __launch_bounds__(256) zero_fill_kernel(uint32_t* __restrict__ p, int64_t n4, int64_t nwords) {
+    pdl_sync();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) reinterpret_cast<uint4*>(p)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) p[i] = 0u;
+}
+
 // ---- channel padding: layers whose channel counts are not multiples of 64 run on the 64-multiple tcgen05 kernels -------------
 // dst[r, j] = j < c ? src[r, j] : 0   (activations, channels-last rows)
 template <typename T>
@@ -402,6 +410,27 @@ __global__ void __launch_bounds__(256) fill_from_kernel(const float* __restrict_
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = v;
 }
 
+}  // namespace
+
+int zero_async(void* ptr, size_t bytes, cudaStream_t s) {
+    if (bytes == 0) return VP_OK;
+    if (((uintptr_t)ptr & 3) || (bytes & 3)) {      // never the case for the library's fp32 / double scratch; keep the exact semantics anyway
+        return cudaMemsetAsync(ptr, 0, bytes, s) == cudaSuccess ? VP_OK : VP_ECUDA;
+    }
+    const int64_t nwords = (int64_t)(bytes / 4);
+    const int64_t n4 = ((uintptr_t)ptr & 15) == 0 ? nwords / 4 : 0;
+    int64_t blocks = (nwords / 4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    launch_k(zero_fill_kernel, dim3((unsigned)blocks), dim3(256), 0, s, (uint32_t*)ptr, n4, nwords);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("zero_async: %s", cudaGetErrorString(e)); return VP_ECUDA; }
+    count_launch();
+    return VP_OK;
+}
+
+namespace {
+
 inline unsigned grid_for(int64_t n, int per_thread = 1) {
     int64_t b = (n + 256LL * per_thread - 1) / (256LL * per_thread);
     const int64_t cap = 148 * 16;
@@ -485,7 +514,7 @@ extern "C" int vp_bce_dice_fwd(const float* logits, const float* target, int64_t
                                double* acc, unsigned int* counter, float* loss, void* stream) {
     VP_CHECK_ARG(logits && target && acc && counter && loss && rows > 0 && rows <= 65535 && per > 0, "vp_bce_dice_fwd: bad arguments");
     dim3 grid((unsigned)((per + 1023) / 1024 < 64 ? (per + 1023) / 1024 : 64), (unsigned)rows);
-    cudaMemsetAsync(acc, 0, sizeof(double) * 4 * rows, (cudaStream_t)stream);
+    zero_async(acc, sizeof(double) * 4 * rows, (cudaStream_t)stream);
     launch_k(bce_dice_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, logits, target, rows, per, bce_weight, acc, counter, loss);
     VP_CHECK_LAUNCH("vp_bce_dice_fwd");
     return VP_OK;

@@ -357,7 +357,7 @@ extern "C" int vp_norm_stats(const void* x, double* sums, int dtype, int64_t gro
                              void* stream) {
     VP_CHECK_ARG(x && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_stats: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_stats: too many groups");
-    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
+    zero_async(sums, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
     if (groups == 1) {
         const int rc = norm_stream(0, dtype, x, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, sums, nullptr, nullptr, rpg, c, 0,
                                    0.f, (cudaStream_t)stream);
@@ -548,7 +548,7 @@ extern "C" int vp_norm_bwd_reduce(const void* x, const void* da, const float* me
                                   int64_t groups, int64_t rpg, int c, int act, float slope, void* stream) {
     VP_CHECK_ARG(x && da && sums && groups > 0 && rpg > 0 && c > 0, "vp_norm_bwd_reduce: bad arguments");
     VP_CHECK_ARG(groups <= 65535, "vp_norm_bwd_reduce: too many groups");
-    cudaMemsetAsync(sums, 0, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
+    zero_async(sums, sizeof(double) * 2 * groups * c, (cudaStream_t)stream);
     if (groups == 1 && !mean && !scale && dxo && c <= 4 && (rpg * c) % 8 == 0 && (((uintptr_t)x | (uintptr_t)da | (uintptr_t)dxo) & 15) == 0) {
         const int64_t n8 = rpg * c / 8;
         int64_t blocks = (n8 + 255) / 256;

@@ -536,7 +536,7 @@ int launch_tapgemm_simt(const TapGemm& p, int dtype, cudaStream_t s) {
 
 int launch_tapwgrad_simt(const TapWgrad& p, int dtype, cudaStream_t s) {
     const int64_t M = (int64_t)p.n * p.gh * p.gw;
-    if (!p.accumulate) cudaMemsetAsync(p.dWp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    if (!p.accumulate) zero_async(p.dWp, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     if (M == 0 || p.GC == 0 || p.AC == 0) return VP_OK;
     if (dtype == VP_BF16) count_simt_bf16();
     if (dtype == VP_BF16) {   // (the fp32 check mode keeps the double-accumulating generic kernel)

@@ -526,7 +526,7 @@ int launch_tapgemm_tc_multi(const TapGemm* phases, int nphases, cudaStream_t s) 
                 tp.iters_per_split = (iters + ks - 1) / ks;
                 tp.ksplit = (iters + tp.iters_per_split - 1) / tp.iters_per_split;
                 tp.total_tiles = tp.base_tiles * tp.ksplit;
-                cudaMemsetAsync(ws, 0, (size_t)out_elems * sizeof(float), s);
+                zero_async(ws, (size_t)out_elems * sizeof(float), s);
             }
         }
     }
@@ -840,7 +840,7 @@ int launch_tapwgrad_tc(const TapWgrad& p, cudaStream_t s) {
     if (r) { set_error("tcgen05 wgrad: cuTensorMapEncodeTiled(A) failed (%d)", r); return VP_EUNSUPPORTED; }
     // a single pixel split writes every element exactly once: no clearing pass, plain stores (the fc layers: K = batch only)
     tp.store_only = (nsplit == 1 && p.AC % 32 == 0) ? 1 : 0;
-    if (!p.accumulate && !tp.store_only) cudaMemsetAsync(p.dWp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    if (!p.accumulate && !tp.store_only) zero_async(p.dWp, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     dim3 grid((unsigned)out_tiles, (unsigned)nsplit);
     // short reductions (the fc layers: K = batch = a few bricks): a 2-stage ring is enough and lets 3 CTAs share an SM, which
     // hides the per-CTA prologue (barrier init, TMEM allocation) and epilogue behind the neighbours' main loops

@@ -333,7 +333,7 @@ int launch_tapwgrad_win(const TapWgrad& p, int kh, int kw, int pad, cudaStream_t
         if (e != cudaSuccess) { set_error("tapwgrad_row: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
         attr_set = smem_bytes;
     }
-    if (!p.accumulate) cudaMemsetAsync(p.dWp, 0, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
+    if (!p.accumulate) zero_async(p.dWp, sizeof(float) * (size_t)p.taps.ntaps * p.GC * p.AC, s);
     dim3 grid((unsigned)sets, (unsigned)nsplit);
     launch_k(tapwgrad_row_kernel, grid, dim3(kRThreads), smem_bytes, s, mG, maps[0], maps[1], maps[2], maps[3], rp);
     VP_CHECK_LAUNCH("tapwgrad_row");

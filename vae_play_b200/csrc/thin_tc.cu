@@ -847,6 +847,6 @@ extern "C" int vp_thin_conv_wgrad(const VpConvGeom* g, const void* x, const void
     p.total_tiles = (int)total;
     CUtensorMap mw;
     if (encode_box(&mw, wide, wc, p.gw, p.gh, p.n, 8, 16)) { set_error("vp_thin_conv_wgrad: cuTensorMapEncodeTiled failed"); return VP_EUNSUPPORTED; }
-    if (!accumulate) cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)g->co * g->ci * T, s);
+    if (!accumulate) zero_async(dw, sizeof(float) * (size_t)g->co * g->ci * T, s);
     return launch_thin_w(mw, p, wc / 64, s);
 }

@@ -344,8 +344,8 @@ class TapLayer:
             gp = self._padded_geom(n, h, w, shp[1], shp[2])
             bp = None
             if bias is not None:
-                bp = torch.zeros(cop, dtype=torch.float32, device=x.device)
-                _lib.call("vp_cast", _ptr(bias.detach()), F32, _ptr(bp), F32, self.cout, _stream())
+                bp = torch.empty(cop, dtype=torch.float32, device=x.device)
+                _lib.call("vp_pad_channels", _ptr(bias.detach()), self.cout, _ptr(bp), cop, 1, F32, _stream())     # zero-padded bias, one kernel
             yp = y if cop == self.cout else torch.empty(shp[:3] + (cop,), dtype=out_dtype, device=x.device)
             _lib.call("vp_conv_fwd_cl", C.byref(gp), _ptr(self._pad_act(x, cip)), _ptr(self._padded_weight(weight)), _ptr(bp), _ptr(yp),
                       _code(out_dtype), ACT[act], float(slope), _stream())
