@@ -347,8 +347,10 @@ class TapLayer:
                 bp = torch.empty(cop, dtype=torch.float32, device=x.device)
                 _lib.call("vp_pad_channels", _ptr(bias.detach()), self.cout, _ptr(bp), cop, 1, F32, _stream())     # zero-padded bias, one kernel
             yp = y if cop == self.cout else torch.empty(shp[:3] + (cop,), dtype=out_dtype, device=x.device)
-            _lib.call("vp_conv_fwd_cl", C.byref(gp), _ptr(self._pad_act(x, cip)), _ptr(self._padded_weight(weight)), _ptr(bp), _ptr(yp),
-                      _code(out_dtype), ACT[act], float(slope), _stream())
+            # the padded temporaries stay referenced until the call has been issued: a tensor dropped right after its pointer was
+            # taken would hand its block to the NEXT allocation (the padded weight on a cache miss) before the kernel is queued
+            xp, wp = self._pad_act(x, cip), self._padded_weight(weight)
+            _lib.call("vp_conv_fwd_cl", C.byref(gp), _ptr(xp), _ptr(wp), _ptr(bp), _ptr(yp), _code(out_dtype), ACT[act], float(slope), _stream())
             if yp is not y:
                 _lib.call("vp_copy_channels", _ptr(yp), cop, 0, _ptr(y), self.cout, 0, self.cout, y.numel() // self.cout, _code(out_dtype), 0, _stream())
         else:
@@ -398,8 +400,8 @@ class TapLayer:
             cip, cop = self._up64(self.cin), self._up64(self.cout)
             gp = self._padded_geom(n, h, w, dy.shape[1], dy.shape[2])
             dxp = dx if cip == self.cin else torch.empty(tuple(x_shape[:3]) + (cip,), dtype=out_dtype, device=dy.device)
-            _lib.call("vp_conv_dgrad_cl", C.byref(gp), _ptr(self._pad_act(dy, cop)), _ptr(self._padded_weight(weight)), _ptr(dxp), _code(out_dtype),
-                      _stream())
+            dyp, wp = self._pad_act(dy, cop), self._padded_weight(weight)
+            _lib.call("vp_conv_dgrad_cl", C.byref(gp), _ptr(dyp), _ptr(wp), _ptr(dxp), _code(out_dtype), _stream())
             if dxp is not dx:
                 _lib.call("vp_copy_channels", _ptr(dxp), cip, 0, _ptr(dx), self.cin, 0, self.cin, dx.numel() // self.cin, _code(out_dtype), 0, _stream())
         else:
@@ -446,7 +448,8 @@ class TapLayer:
             cop = self._up64(self.cout)
             gp = self._geom(n, h, w, 1, dy.shape[1], dy.shape[2], cop, self.k, self.stride, self.pad, 0)
             dwp = torch.empty((cop,) + tuple(weight.shape[1:]), dtype=torch.float32, device=x.device)
-            _lib.call("vp_thin_conv_wgrad", C.byref(gp), _ptr(x), _ptr(self._pad_act(dy, cop)), _ptr(dwp), 0, _stream())
+            dyp = self._pad_act(dy, cop)
+            _lib.call("vp_thin_conv_wgrad", C.byref(gp), _ptr(x), _ptr(dyp), _ptr(dwp), 0, _stream())
             dw, _ = _grad_target(weight)
             _lib.call("vp_cast", _ptr(dwp), F32, _ptr(dw), F32, weight.numel(), _stream())
             return dw
@@ -455,7 +458,8 @@ class TapLayer:
             gp = self._padded_geom(n, h, w, dy.shape[1], dy.shape[2])
             d0, d1, taps, s0, s1, st, d0p, d1p = self._pad_dims(weight)
             dwp = torch.empty(d0p * taps * d1p, dtype=torch.float32, device=x.device)
-            _lib.call("vp_conv_wgrad_cl", C.byref(gp), _ptr(self._pad_act(x, cip)), _ptr(self._pad_act(dy, cop)), _ptr(dwp), 0, _stream())
+            xp, dyp = self._pad_act(x, cip), self._pad_act(dy, cop)
+            _lib.call("vp_conv_wgrad_cl", C.byref(gp), _ptr(xp), _ptr(dyp), _ptr(dwp), 0, _stream())
             dw, _ = _grad_target(weight)
             _lib.call("vp_unpad_wgrad_cl", _ptr(dwp), _ptr(dw), d0, d1, taps, s0, s1, st, d1p, _stream())
             return dw
@@ -643,7 +647,8 @@ class _FusedLayerFn(torch.autograd.Function):
             if dy_extra is not None:
                 if dt != torch.float32:
                     raise _lib.VaePlayError("gradient into the pre-norm output is supported in fp32 mode only")
-                _lib.call("vp_axpy", 1.0, _ptr(dy_extra.contiguous()), _ptr(dy), dy.numel(), _stream())
+                extra = dy_extra.contiguous()
+                _lib.call("vp_axpy", 1.0, _ptr(extra), _ptr(dy), dy.numel(), _stream())
             if ctx.has_bias:
                 # a bias directly in front of Batch/InstanceNorm (StyleUp's ConvTranspose2d, network_Style_GAN.py:49-50) is
                 # removed by the mean subtraction: its gradient is identically zero (the reference computes round-off noise)

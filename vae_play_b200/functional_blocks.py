@@ -596,7 +596,8 @@ class _NllPick(torch.autograd.Function):
         s, label = ctx.saved_tensors
         rows, cols = s.shape
         ds = torch.empty_like(s)
-        _lib.call("vp_nll_pick_bwd", _ptr(s), _ptr(label), _ptr(g.contiguous().float()), _ptr(ds), rows, cols, _stream())
+        g = g.contiguous().float()
+        _lib.call("vp_nll_pick_bwd", _ptr(s), _ptr(label), _ptr(g), _ptr(ds), rows, cols, _stream())
         return ds, None
 
 
