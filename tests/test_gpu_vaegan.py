@@ -282,7 +282,8 @@ def test_fused_single_backward_equals_five_backward(vp):
     its five backward(retain_graph=True) calls (train.py:68-73).  fp32 check mode, batch 16 fixture: encoder / decoder /
     param_encoder gradients agree with the five-call mode to fp32 round-off; the discriminator's pure-lambda gradients
     (BatchNorm of the last block, fc.*: lambda = 1e-6 times the GAN-loss gradient, which the reference forms as the
-    difference of two nearly equal fp32 numbers and gets wrong by 10-50 %) match the FLOAT64 truth to 1e-3 in the fused mode."""
+    difference of two nearly equal fp32 numbers and gets wrong by 10-50 %) match the FLOAT64 truth to a ReLU flip (2e-3 measured:
+    the same conv.3 flip test_vaegan_step_golden_fp32[16] sees) in the fused mode."""
     from vae_play_b200 import train_steps as TS
     g, dev = fixture(16)
     try:
@@ -304,6 +305,6 @@ def test_fused_single_backward_equals_five_backward(vp):
         assert len(pure_lambda) >= 6
         for k in pure_lambda:
             r, _ = grad_dev(grads[True][k], g, k)
-            assert r < 2e-3, f"{k}: fused-mode deviation from the float64 truth {r:.3e} (reference fp32: {dev[k]:.2e})"
+            assert r < FLIP_BOUND, f"{k}: fused-mode deviation from the float64 truth {r:.3e} (reference fp32: {dev[k]:.2e})"
     finally:
         vp.set_precision("bf16")
