@@ -224,6 +224,11 @@ int vp_conv_dgrad_cl_bnred(const VpConvGeom* g, const void* dy, const void* w_cl
                            const float* scale, const float* shift, const float* mean, float* parts, int capacity,
                            int* nparts, void* stream);
 int vp_norm_bwd_finish_parts(const float* parts, int nparts, const float* invstd, double* sums, int c, void* stream);
+/* the same fusion for the decoder's output layer (models/networks.py:101: 64 -> 1 channels): its thin data-gradient kernel
+ * produces dL/da of the last DecoderBlock -- the largest activation of the step -- and reduces it against that block's y_prev */
+int vp_thin_conv_dgrad_bnred(const VpConvGeom* g, const void* dy, const float* w, void* dx, const void* y_prev,
+                             const float* scale, const float* shift, const float* mean, float* parts, int capacity,
+                             int* nparts, void* stream);
 /* dst[b][c][r] = src[b][r][c] (same dtype): channels-last 8x8 map <-> the NCHW-flatten order of the fc layers */
 int vp_transpose_bt(const void* src, void* dst, int dtype, int batch, int rows, int cols, void* stream);
 

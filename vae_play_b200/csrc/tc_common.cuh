@@ -319,6 +319,28 @@ __device__ __forceinline__ void stats_group64_sw128(const uint8_t* stile, int la
     atomicAdd(s_sq + 2 * lane, q0); atomicAdd(s_sq + 2 * lane + 1, q1);
 }
 
+// the fused BatchNorm-backward reduction for a 64-column [32 rows][128 B] SWIZZLE_128B staging tile (thin-layer kernels):
+// lane = 32-bit word (two channels), all 32 rows; see bnred_chunk32_sw64
+__device__ __forceinline__ void bnred_group64_sw128(const uint8_t* stile, const uint8_t* ytile, int lane, float* s_sum, float* s_q, uint32_t row_mask,
+                                                    const float* __restrict__ sc, const float* __restrict__ sh, const float* __restrict__ mu) {
+    const float sc0 = sc[2 * lane], sc1 = sc[2 * lane + 1], sh0 = sh[2 * lane], sh1 = sh[2 * lane + 1], mu0 = mu[2 * lane], mu1 = mu[2 * lane + 1];
+    float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {
+        const int off = r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4;
+        uint32_t dw = *reinterpret_cast<const uint32_t*>(stile + off);
+        const uint32_t yw = *reinterpret_cast<const uint32_t*>(ytile + off);
+        dw = ((row_mask >> r) & 1u) ? dw : 0u;
+        const float ylo = __uint_as_float(yw << 16), yhi = __uint_as_float(yw & 0xffff0000u);
+        const float dlo = fmaf(ylo, sc0, sh0) > 0.f ? __uint_as_float(dw << 16) : 0.f;
+        const float dhi = fmaf(yhi, sc1, sh1) > 0.f ? __uint_as_float(dw & 0xffff0000u) : 0.f;
+        s0 += dlo; q0 = fmaf(dlo, ylo - mu0, q0);
+        s1 += dhi; q1 = fmaf(dhi, yhi - mu1, q1);
+    }
+    atomicAdd(s_sum + 2 * lane, s0); atomicAdd(s_sum + 2 * lane + 1, s1);
+    atomicAdd(s_q + 2 * lane, q0); atomicAdd(s_q + 2 * lane + 1, q1);
+}
+
 struct OutMaps { CUtensorMap m[4]; };      // one output tensor map per output-parity phase (TMA-store epilogue)
 constexpr int kStatMaxN = 512;             // widest layer whose BatchNorm statistics are taken in the GEMM epilogue
 

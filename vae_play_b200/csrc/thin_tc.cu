@@ -209,12 +209,16 @@ struct ThinKParams {
     int tiles_w, tiles_h, total_tiles;
     int tma_store;                    // bf16 output with N % 64 == 0: epilogue through shared memory + TMA store
     float* stat_parts;                // [gridDim.x][2][N] per-CTA BatchNorm partial sums of the stored output, or null
+    // fused BatchNorm-backward reduction (N == 64 data gradient of the output layer): D is dL/da of the producer block, mapY its
+    // pre-norm output; stat_parts then receives (sum d, sum d*(y - mean)) with d = D * (y*scale + shift > 0)
+    const float *bn_scale, *bn_shift, *bn_mean;
 };
 
 constexpr int kKStages = 3;
 constexpr int kKThreads = 288;        // warps 0-3 builders, warp 4 MMA, warps 5-8 epilogue
 
-__global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ ThinKParams p) {
+__global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_constant__ CUtensorMap mapD, const __grid_constant__ CUtensorMap mapY,
+                                                              const __grid_constant__ ThinKParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_b = smem + kKStages * 16384;                  // weight tile: N rows x 128 B (<= 16 KB)
@@ -225,7 +229,8 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
     uint64_t* empty = full + kKStages;
     uint64_t* acc_full = empty + kKStages;
     uint64_t* acc_empty = acc_full + 2;
-    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
+    uint64_t* y_full = acc_empty + 2;                           // [4]: one y tile in flight per epilogue warp (fused BatchNorm backward)
+    uint32_t* tmem_slot = (uint32_t*)(y_full + 4);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     constexpr int kTmemCols = 256;                              // 2 accumulators x 128 columns
     if (threadIdx.x < 256) s_stat[threadIdx.x] = 0.f;
@@ -235,6 +240,7 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
             for (int s = 0; s < kKStages; ++s) { mbar_init(&full[s], 4); mbar_init(&empty[s], 1); }   // one arrive per builder warp
             mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
             mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+            for (int i = 0; i < 4; ++i) mbar_init(&y_full[i], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -283,6 +289,17 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
         const int r = lane_base + lane;
         const int by = r >> 3, bx = r & 7;
         uint32_t g = 0, sg = 0;
+        const bool bn = p.bn_scale != nullptr;          // N == 64: one 64-column group per tile; staging slot 1 holds the y tile
+        uint8_t* ybuf = stage_out + (warp & 3) * 8192 + 4096;
+        uint64_t* ybar = &y_full[warp & 3];
+        auto issue_y = [&](int q2) {                    // lane 0: the y tile of this warp's 32 rows of tile q2
+            int m2 = q2;
+            const int tw2 = m2 % p.tiles_w; m2 /= p.tiles_w;
+            const int th2 = m2 % p.tiles_h; m2 /= p.tiles_h;
+            mbar_expect_tx(ybar, 4096);
+            tma_load_4d(ybuf, &mapY, ybar, 0, tw2 * 8, th2 * 16 + (warp & 3) * 4, m2);
+        };
+        if (bn && lane == 0 && (int)blockIdx.x < p.total_tiles) issue_y(blockIdx.x);
         for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++g) {
             int m = q;
             const int tw = m % p.tiles_w; m /= p.tiles_w;
@@ -295,10 +312,11 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
             tc_fence_after();
             if (p.tma_store) {
                 uint8_t* my_stage = stage_out + (warp & 3) * 8192;
+                const uint32_t row_mask = __ballot_sync(0xffffffffu, row_ok);
 #pragma unroll 1
                 for (int c = 0; c < p.N; c += 64, ++sg) {
-                    uint8_t* st = my_stage + (sg & 1) * 4096;
-                    if (lane == 0) tma_store_wait_read<1>();          // the store that last read this buffer has drained it
+                    uint8_t* st = my_stage + (bn ? 0 : (sg & 1) * 4096);
+                    if (lane == 0) { if (bn) tma_store_wait_read<0>(); else tma_store_wait_read<1>(); }   // the store that last read this buffer has drained it
                     __syncwarp();
 #pragma unroll
                     for (int cc = 0; cc < 64; cc += 32) {
@@ -309,7 +327,14 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
-                    if (p.stat_parts) stats_group64_sw128(st, lane, s_stat + c, s_stat + 128 + c);
+                    if (bn) {
+                        mbar_wait(ybar, g & 1);
+                        bnred_group64_sw128(st, ybuf, lane, s_stat + c, s_stat + 128 + c, row_mask, p.bn_scale + c, p.bn_shift + c, p.bn_mean + c);
+                        __syncwarp();                                  // every lane is done with the y tile: fetch the next tile's
+                        if (lane == 0 && q + (int)gridDim.x < p.total_tiles) issue_y(q + gridDim.x);
+                    } else if (p.stat_parts) {
+                        stats_group64_sw128(st, lane, s_stat + c, s_stat + 128 + c);
+                    }
                     if (lane == 0) {
                         tma_store_4d(&mapD, st, c, tw * 8, th * 16 + (warp & 3) * 4, m);
                         tma_store_commit();
@@ -342,14 +367,15 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
     }
 }
 
-constexpr int kKSmem = kKStages * 16384 + 16384 + 4 * 2 * 4096 + 2 * kHaloBuf + 256 * 4 + (2 * kKStages + 4) * 8 + 16 + 1024;
+constexpr int kKSmem = kKStages * 16384 + 16384 + 4 * 2 * 4096 + 2 * kHaloBuf + 256 * 4 + (2 * kKStages + 4 + 4) * 8 + 16 + 1024;
 
 int encode_box(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh);
 
-int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* stat_nparts = nullptr) {
-    CUtensorMap mD;
+int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* stat_nparts = nullptr, const void* bn_y = nullptr) {
+    CUtensorMap mD, mY;
     memset(&mD, 0, sizeof(mD));
     p.tma_store = (!p.out_f32 && p.N % 64 == 0) ? 1 : 0;
+    if (bn_y && (p.N != 64 || !p.tma_store || !p.stat_parts)) return VP_EUNSUPPORTED;
     if (p.stat_parts) {
         const int g = p.total_tiles < 2 * num_sms() ? p.total_tiles : 2 * num_sms();
         if (!p.tma_store || p.bias || p.act != VP_ACT_NONE) { set_error("thin_k: epilogue statistics need a bf16 output, N %% 64 == 0, no bias/activation"); return VP_EUNSUPPORTED; }
@@ -357,6 +383,8 @@ int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* st
         if (stat_nparts) *stat_nparts = g;
     }
     if (p.tma_store && encode_box(&mD, p.D, p.N, p.gw, p.gh, p.n, 8, 4)) { set_error("thin_k: cuTensorMapEncodeTiled(D) failed"); return VP_EUNSUPPORTED; }
+    mY = mD;
+    if (bn_y && encode_box(&mY, bn_y, p.N, p.gw, p.gh, p.n, 8, 4)) { set_error("thin_k: cuTensorMapEncodeTiled(y) failed"); return VP_EUNSUPPORTED; }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(thin_k_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKSmem);
@@ -365,7 +393,7 @@ int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* st
     }
     const int slots = 2 * num_sms();
     const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-    launch_k(thin_k_kernel, dim3(grid), dim3(kKThreads), kKSmem, s, mD, p);
+    launch_k(thin_k_kernel, dim3(grid), dim3(kKThreads), kKSmem, s, mD, mY, p);
     VP_CHECK_LAUNCH("thin_k");
     return VP_OK;
 }
@@ -806,6 +834,32 @@ extern "C" int vp_thin_conv_dgrad(const VpConvGeom* g, const void* dy, const flo
     if (total > 0x7fffffff) { set_error("vp_thin_conv_dgrad: too many tiles"); return VP_EUNSUPPORTED; }
     p.total_tiles = (int)total;
     return launch_thin_k(p, (cudaStream_t)stream);
+}
+
+/* vp_thin_conv_dgrad (bf16 dx, ci == 64) fused with the first pass of the PRODUCER block's BatchNorm backward, as
+ * vp_conv_dgrad_cl_bnred: parts[*nparts][2][ci] = per-CTA (sum d, sum d*(y - mean)), d = dx * (y_prev*scale + shift > 0). */
+extern "C" int vp_thin_conv_dgrad_bnred(const VpConvGeom* g, const void* dy, const float* w, void* dx, const void* y_prev, const float* scale,
+                                        const float* shift, const float* mean, float* parts, int capacity, int* nparts, void* stream) {
+    if (!thin_geom_ok(g, "vp_thin_conv_dgrad_bnred")) return VP_EINVAL;
+    VP_CHECK_ARG(dy && w && dx && y_prev && scale && shift && mean && parts && nparts && capacity > 0, "vp_thin_conv_dgrad_bnred: null pointer");
+    const int T = g->kh * g->kw;
+    if (!tc_available() || g->transposed || g->stride != 1 || g->co != 1 || g->kh > 8 || g->kw > 8 || g->ci != 64 || ((uintptr_t)dx & 15) != 0 ||
+        ((uintptr_t)y_prev & 15) != 0)
+        return VP_EUNSUPPORTED;
+    ThinKParams p;
+    memset(&p, 0, sizeof(p));
+    p.g.S = (const bf16*)dy; p.g.hs = g->ho; p.g.ws = g->wo; p.g.stride = 1;
+    fill_gather(p.g, g, true);
+    if (!finish_gather(p.g, g->kw)) return VP_EUNSUPPORTED;
+    p.W = w; p.w_sn = T; p.w_st = 1;
+    p.D = dx; p.bias = nullptr; p.n = g->n; p.gh = g->hi; p.gw = g->wi; p.N = g->ci;
+    p.act = VP_ACT_NONE; p.slope = 0.f; p.out_f32 = 0;
+    p.tiles_w = (p.gw + 7) / 8; p.tiles_h = (p.gh + 15) / 16;
+    const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.n;
+    if (total > 0x7fffffff) return VP_EUNSUPPORTED;
+    p.total_tiles = (int)total;
+    p.stat_parts = parts; p.bn_scale = scale; p.bn_shift = shift; p.bn_mean = mean;
+    return launch_thin_k(p, (cudaStream_t)stream, capacity, nparts, y_prev);
 }
 
 // dw (fp32, torch layout [co][ci][kh][kw], zeroed by the call) = dL/dw of an nn.Conv2d with ONE input channel, or with ONE

@@ -414,7 +414,8 @@ class TapLayer:
         """Data gradient fused with the first pass of the PRODUCER block's BatchNorm backward (``prev``: that block's holder, see
         ``fused_layer``).  Returns (dx, parts, nparts) or None when no kernel with that epilogue serves the shape."""
         weight = weight.detach()
-        if dy.dtype != torch.bfloat16 or not self._cl(dy.dtype, weight) or _STATE.get("fuse_bn_bwd", True) is False:
+        thin = self._thin("dgrad", dy.dtype, weight) and self.cin == 64
+        if dy.dtype != torch.bfloat16 or not (thin or self._cl(dy.dtype, weight)) or _STATE.get("fuse_bn_bwd", True) is False:
             return None
         y = prev["y"]
         if tuple(y.shape) != tuple(x_shape) or y.dtype != torch.bfloat16 or not y.is_contiguous():
@@ -425,11 +426,13 @@ class TapLayer:
         cap = 2 * _num_sms(dy.device)
         parts = torch.empty(cap * 2 * self.cin, dtype=torch.float32, device=dy.device)
         nparts = C.c_int(0)
-        rc = _lib.load().vp_conv_dgrad_cl_bnred(C.byref(g), _ptr(dy), _ptr(self._shadow(weight)), _ptr(dx), _ptr(y), _ptr(prev["scale"]),
-                                                _ptr(prev["shift"]), _ptr(prev["mean"]), _ptr(parts), cap, C.byref(nparts), _stream())
+        name = "vp_thin_conv_dgrad_bnred" if thin else "vp_conv_dgrad_cl_bnred"
+        rc = getattr(_lib.load(), name)(C.byref(g), _ptr(dy), _ptr(weight if thin else self._shadow(weight)), _ptr(dx), _ptr(y),
+                                        _ptr(prev["scale"]), _ptr(prev["shift"]), _ptr(prev["mean"]), _ptr(parts), cap, C.byref(nparts),
+                                        _stream())
         if rc == -3:          # VP_EUNSUPPORTED: nothing was launched
             return None
-        _lib.check(rc, "vp_conv_dgrad_cl_bnred")
+        _lib.check(rc, name)
         return dx, parts, nparts.value
 
     def wgrad(self, x, dy, weight):
