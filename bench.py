@@ -275,15 +275,14 @@ class StepRunner:
             xt, mulv, kl = model.vae_forward(x, rng=(rank, 0, off_dev), taps=taps)
             VF.philox_advance(off_dev, eps_inc)
             loss = VF.vae_loss(x, xt, kl, mse_scale=1.0 / world)
-            a3 = taps[0]
-            a3.retain_grad()
+            a3 = taps[0]          # behind VF.grad_cut: naming it in `inputs` executes only that identity node
+            a3.register_hook(lambda g: cut.__setitem__("g", g))
             loss.backward(inputs=stage1_params + [a3], retain_graph=True)
             cut["a"] = a3
             return loss
 
         def bwd_stage2():
-            a3 = cut["a"]
-            a3.backward(a3.grad, inputs=enc_conv_params)
+            cut["a"].backward(cut["g"], inputs=enc_conv_params)
 
         def eager_step(x):
             opt.zero_grad(set_to_none=True)
@@ -432,6 +431,19 @@ class StepRunner:
         return self._max_over_ranks(e0.elapsed_time(e1))
 
 
+def init_nccl(args, dev):
+    """NCCL's kernels get a bounded number of CTAs (the SMs our persistent grids leave free while the exchange overlaps backward)
+    and a high-priority stream (their CTAs are placed first when SMs free up)."""
+    import torch.distributed as dist
+    try:
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        opts.config.max_ctas = args.sm_reserve
+        opts.config.min_ctas = min(args.sm_reserve, 4)
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+    except Exception:
+        dist.init_process_group("nccl", device_id=dev)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -446,15 +458,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: the driver reads ONE JSON line
-        try:
-            # NCCL's kernels get a bounded number of CTAs (the SMs our persistent grids leave free while the exchange overlaps
-            # backward) and a high-priority stream (their CTAs are placed first when SMs free up)
-            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-            opts.config.max_ctas = args.sm_reserve
-            opts.config.min_ctas = min(args.sm_reserve, 4)
-            dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-        except Exception:
-            dist.init_process_group("nccl", device_id=dev)
+        init_nccl(args, dev)
     vp.set_precision(args.precision)
     B, img, cin = args.batch, args.img, args.cin
     if cin != 1:
@@ -916,8 +920,7 @@ def kernel_probe(model, B, dev, peaks, iters=20):
 DOMINANT_TRAFFIC_BYTES = {64: 222103552}     # profiles/r01_ncu_prof_ct3_fwd_r1e.summary.txt: 132.05 MB read + 90.05 MB written
 
 
-def main():
-    ap = argparse.ArgumentParser()
+def add_arguments(ap):
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
@@ -939,6 +942,11 @@ def main():
                     help="data parallel: gradient buckets cross NVLink in bf16 (half the bytes; the optimiser reads the reduced bf16 values) or fp32")
     ap.add_argument("--sm-reserve", type=int, default=32, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    add_arguments(ap)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

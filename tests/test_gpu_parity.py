@@ -774,14 +774,17 @@ def test_persistent_grads_and_zeroing_optimizer(vp):
 
 
 def test_two_stage_backward_matches_single(vp):
-    """bench.py's optional data-parallel step cuts the backward at the output of the encoder's conv stack (so that the
-    gradient all-reduce of everything downstream can overlap the conv-stack backward): same gradients as one backward
-    call through the SAME forward graph."""
+    """bench.py's data-parallel step cuts the backward at the output of the encoder's conv stack (so that the gradient
+    all-reduce of everything downstream can overlap the conv-stack backward): same gradients as one backward call through
+    the SAME forward graph, with the weight gradients written in place into persistent slots as in bench.py, and no kernel
+    launched twice (the cut sits behind VF.grad_cut: naming a block's own output in ``inputs`` would run its backward in
+    both stages)."""
     import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
     from vae_play_b200.models.networks import VaeGan
     vp.set_precision("bf16")
     vp.set_engine("auto")
-    VF.set_grad_sinks({})
+    VF.set_fuse_bn_backward(False)        # fp32 shared-memory atomics in the fused reduction: not bit-comparable run to run
     torch.manual_seed(1)
     m = VaeGan(64, 128).cuda().train()
     x = torch.rand(16, 1, 64, 64, device="cuda")
@@ -789,20 +792,35 @@ def test_two_stage_backward_matches_single(vp):
     params = list(m.encoder.parameters()) + list(m.decoder.parameters())
     conv_params = [p for blk in m.encoder.conv for p in blk.parameters()]
     ids = {id(p) for p in conv_params}
-    taps = []
-    xt, mulv, kl = m.vae_forward(x, eps=eps, taps=taps)
-    loss = VF.vae_loss(x, xt, kl)
-    a3 = taps[0]
-    a3.retain_grad()
-    loss.backward(inputs=[p for p in params if id(p) not in ids] + [a3], retain_graph=True)
-    assert all(p.grad is None for p in conv_params) and all(p.grad is not None for p in params if id(p) not in ids)
-    a3.backward(a3.grad, inputs=conv_params, retain_graph=True)
-    staged = [npy(p.grad) for p in params]
-    for p in params:
-        p.grad = None
-    loss.backward()
-    for a, p in zip(staged, params):
-        assert rel_l2(a, npy(p.grad)) < 1e-4      # same kernels on the same saved activations; only the order of fp32 atomics differs
+    try:
+        flat = VF.persistent_grads(params)
+        taps, cut = [], {}
+        xt, mulv, kl = m.vae_forward(x, eps=eps, taps=taps)
+        loss = VF.vae_loss(x, xt, kl)
+        a3 = taps[0]
+        a3.register_hook(lambda g: cut.__setitem__("g", g))
+        n0 = _lib.launch_count()
+        loss.backward(inputs=[p for p in params if id(p) not in ids] + [a3], retain_graph=True)
+        assert all(p.grad is None for p in conv_params) and all(p.grad is not None for p in params if id(p) not in ids)
+        a3.backward(cut["g"], inputs=conv_params, retain_graph=True)
+        n_staged = _lib.launch_count() - n0
+        slot = lambda p: flat.data_ptr() <= p.grad.data_ptr() < flat.data_ptr() + 4 * flat.numel()
+        names = {id(p): k for k, p in m.named_parameters()}
+        outside = [names[id(p)] for p in params if p.dim() > 1 and not slot(p)]
+        assert not [k for k in outside if "l_mu" not in k and "l_var" not in k], f"weight gradients that left their persistent slots: {outside}"
+        staged = [npy(p.grad) for p in params]
+        VF.set_grad_sinks({})
+        for p in params:
+            p.grad = None
+        n0 = _lib.launch_count()
+        loss.backward()
+        n_single = _lib.launch_count() - n0
+        for a, p in zip(staged, params):
+            assert rel_l2(a, npy(p.grad)) < 1e-4      # same kernels on the same saved activations; only the order of fp32 atomics differs
+        assert n_staged <= n_single, (n_staged, n_single)     # the single pass zero-fills fresh gradient buffers the slots do not need
+    finally:
+        VF.set_fuse_bn_backward(True)
+        VF.set_grad_sinks({})
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
@@ -879,10 +897,12 @@ def test_bf16_wire_pack_and_optimizer(vp):
         gb.remove()
 
 
-def test_fused_bn_backward_matches_unfused(vp):
+@pytest.mark.parametrize("thin", [False, True])
+def test_fused_bn_backward_matches_unfused(vp, thin):
     """BatchNorm backward, first pass: done by the epilogue of the consumer's data-gradient kernel (vp_conv_dgrad_cl_bnred, taken
-    at the bench size by the stride-2 sub-lattice kernel for decoder.conv.1 <- decoder.conv.2) == the separate reduce pass.
-    Same operands, same dx; only the summation (per-CTA fp32 partials, then double) differs."""
+    at the bench size by the stride-2 sub-lattice kernel for decoder.conv.1 <- decoder.conv.2; with ``thin`` also
+    vp_thin_conv_dgrad_bnred for decoder.conv.2 <- the output layer) == the separate reduce pass.  Same operands, same dx; only
+    the summation (per-CTA fp32 partials, then double) differs."""
     import copy
     import vae_play_b200.functional as VF
     from vae_play_b200 import _lib
@@ -891,29 +911,32 @@ def test_fused_bn_backward_matches_unfused(vp):
     vp.set_engine("auto")
     VF.set_grad_sinks({})
     torch.manual_seed(0)
-    ref = VaeGan(64, 128).cuda().train()
+    m = VaeGan(64, 128).cuda().train()
     x = torch.rand(256, 1, 64, 64, device="cuda")
     eps = torch.randn(256, 128, device="cuda")
     res, launches = [], []
+    # ONE forward, two backward passes over the same saved activations (the forward's own BatchNorm statistics come from fp32
+    # shared-memory atomics: two forwards already differ by bf16 rounding flips that grow to ~1e-2 in the gradients)
+    xt, mulv, kl = m.vae_forward(x, eps=eps)
+    loss = VF.vae_loss(x, xt, kl)
     try:
         for fused in (False, True):
-            VF.set_fuse_bn_backward(fused)
-            m = copy.deepcopy(ref)
-            xt, mulv, kl = m.vae_forward(x, eps=eps)
+            VF.set_fuse_bn_backward(fused, thin=thin)
+            for p in m.parameters():
+                p.grad = None
             n0 = _lib.launch_count()
-            VF.vae_loss(x, xt, kl).backward()
+            loss.backward(retain_graph=True)
             torch.cuda.synchronize()
             launches.append(_lib.launch_count() - n0)
             res.append({k: npy(p.grad) for k, p in m.named_parameters() if p.grad is not None})
     finally:
         VF.set_fuse_bn_backward(True)
-    assert launches[1] < launches[0], launches          # at least one reduce pass (+ its memset-free launch) disappeared
+    assert launches[1] <= launches[0] - (2 if thin else 1), launches     # one reduce pass per fused block disappeared
     for k in res[0]:
         r = rel_l2(res[1][k], res[0][k])
-        # the block whose reduction moved (decoder.conv.1) and everything downstream of it in backward order: same dx, only the
-        # summation differs.  Further upstream (decoder.conv.0, fc, encoder) the 1e-4-level difference passes through bf16 storage
-        # and ReLU patterns like any other rounding noise (measured 3.6e-3 on encoder.conv.0).
-        tight = k.startswith("decoder.conv.1.") or k.startswith("decoder.conv.2.") or k.startswith("decoder.conv.3.")
-        # (bf16 training is only reproducible to ~1e-2 run to run -- fp32 atomics order -> roundings -> ReLU patterns; see
-        #  test_persistent_grads_and_zeroing_optimizer -- so the far-upstream bound only guards against gross errors)
-        assert r < (2e-3 if tight else 0.1), f"{k}: rel-L2 {r:.3e} fused vs unfused BatchNorm backward"
+        # the block whose reduction moved and everything downstream of it in backward order: same dx, only the summation
+        # differs (measured 7e-5 on the block's own weight gradient).  Further upstream the difference passes through bf16
+        # storage of each dx like any other rounding noise.
+        first = 2 if thin else 1         # decoder.conv.<first>: the last block (in forward order) whose reduce pass is fused
+        tight = any(k.startswith(f"decoder.conv.{i}.") for i in range(first, 4))
+        assert r < (5e-4 if tight else 2e-2), f"{k}: rel-L2 {r:.3e} fused vs unfused BatchNorm backward"

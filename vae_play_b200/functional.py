@@ -105,9 +105,13 @@ def set_epilogue_stats(on: bool):
     _STATE["epilogue_stats"] = bool(on)
 
 
-def set_fuse_bn_backward(on: bool):
-    """BatchNorm backward: first pass in the epilogue of the consumer's data-gradient kernel (default) or as its own pass (tests)."""
+def set_fuse_bn_backward(on: bool, thin: bool = False):
+    """BatchNorm backward: first pass in the epilogue of the consumer's data-gradient kernel (default) or as its own pass (tests).
+    ``thin``: also in the output layer's thin data-gradient kernel (vp_thin_conv_dgrad_bnred).  Off by default: that kernel runs at
+    ~50 % of HBM bandwidth and the extra 134 MB read of y costs it more (+55 us at batch 256, 64x64) than the separate reduce pass
+    over the last decoder block (-15 us net loss measured: 1.913 vs 1.874 ms per step)."""
     _STATE["fuse_bn_bwd"] = bool(on)
+    _STATE["fuse_bn_bwd_thin"] = bool(on) and bool(thin)
 
 
 def set_pad_route(on: bool):
@@ -415,6 +419,8 @@ class TapLayer:
         ``fused_layer``).  Returns (dx, parts, nparts) or None when no kernel with that epilogue serves the shape."""
         weight = weight.detach()
         thin = self._thin("dgrad", dy.dtype, weight) and self.cin == 64
+        if thin and not _STATE.get("fuse_bn_bwd_thin", False):
+            return None
         if dy.dtype != torch.bfloat16 or not (thin or self._cl(dy.dtype, weight)) or _STATE.get("fuse_bn_bwd", True) is False:
             return None
         y = prev["y"]
@@ -692,6 +698,23 @@ def trace_activations(enable: bool):
 # ------------------------------------------------------------------------------------------------
 # graph edges
 # ------------------------------------------------------------------------------------------------
+class _GradCut(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def grad_cut(x):
+    """Identity whose autograd node does nothing: the place to cut a backward pass in two.  ``loss.backward(inputs=[..., t])``
+    with a non-leaf ``t`` EXECUTES t's grad_fn (torch marks the nodes of all ``inputs`` as needed); cutting at the output of a
+    conv block itself would therefore run that block's whole backward in the first stage and again in the second."""
+    return _GradCut.apply(x)
+
+
 class _ToCL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, dtype):

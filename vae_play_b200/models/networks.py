@@ -95,6 +95,7 @@ class Encoder(nn.Module):
         for blk in self.conv:
             a = blk.forward_cl(a)
         if taps is not None:
+            a = VF.grad_cut(a)
             taps.append(a)
         if a.shape[1] != 8 or a.shape[2] != 8:
             raise ValueError(f"Encoder expects an 8x8 map before fc, got {tuple(a.shape)} (img_size must be 8 * 2**iter_level)")
