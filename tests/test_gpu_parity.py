@@ -940,3 +940,38 @@ def test_fused_bn_backward_matches_unfused(vp, thin):
         first = 2 if thin else 1         # decoder.conv.<first>: the last block (in forward order) whose reduce pass is fused
         tight = any(k.startswith(f"decoder.conv.{i}.") for i in range(first, 4))
         assert r < (5e-4 if tight else 2e-2), f"{k}: rel-L2 {r:.3e} fused vs unfused BatchNorm backward"
+
+
+def test_host_io_pipeline(vp):
+    """HostBatchPipeline / ScalarReadback (vae_play_b200/host_io.py): every fed batch arrives intact and in order while the
+    consumer keeps the device busy, staging buffers are not overwritten before their reader is done, and scalar read-backs
+    return each step's value in order."""
+    from vae_play_b200.host_io import HostBatchPipeline, ScalarReadback
+    torch.manual_seed(0)
+    batches = [torch.rand(64, 1, 64, 64).pin_memory() for _ in range(7)]
+    pipe, reader = HostBatchPipeline((64, 1, 64, 64)), ScalarReadback(2)
+    sink = torch.zeros(64, 1, 64, 64, device="cuda")
+    busy = torch.rand(4096, 4096, device="cuda")
+    got = []
+    pipe.feed(batches[0])
+    for i in range(len(batches)):
+        xd = pipe.take()
+        if i + 1 < len(batches):
+            pipe.feed(batches[i + 1])
+        for _ in range(3):
+            busy = busy * 1.0001          # keep the consumer's stream behind the copy stream
+        sink.copy_(xd, non_blocking=True)
+        vals = torch.stack([sink.sum(), sink.flatten()[i]])
+        pipe.release()
+        if reader.pending() == 2:
+            got.append(reader.pop())
+        reader.push(vals)
+    while reader.pending():
+        got.append(reader.pop())
+    assert len(got) == len(batches)
+    for i, (b, g) in enumerate(zip(batches, got)):
+        assert abs(g[0] - float(b.sum())) < 1e-3 * float(b.sum()) and g[1] == float(b.flatten()[i]), i
+    with pytest.raises(ValueError):
+        pipe.feed(torch.rand(64, 1, 64, 64))          # not pinned
+    with pytest.raises(RuntimeError):
+        pipe.feed(batches[0]); pipe.feed(batches[0]); pipe.feed(batches[0])
