@@ -34,12 +34,12 @@ def main(path, last_n=None):
         print(f"{k[:100]:100s} {v[0]:5d} {v[1]:10.1f} {100 * v[1] / tot:6.1f}%")
     fam = collections.defaultdict(float)
     for k, v in agg.items():
-        key = ("tcgen05 contraction (fwd/dgrad)" if ("tapgemm_tc" in k or "tapgemm_win" in k or "splitk" in k)
+        key = ("tcgen05 contraction (fwd/dgrad)" if any(s_ in k for s_ in ("tapgemm_tc", "tapgemm_win", "tapgemm_pair", "tapgemm_gwin", "splitk"))
                else "tcgen05 contraction (wgrad)" if "tapwgrad" in k
                else "tcgen05 thin layers" if "thin_" in k
                else "cuda-core contraction" if "simt" in k
-               else "norm/act" if any(s_ in k for s_ in ("norm_stream", "stats_kernel", "apply_kernel", "bwd_reduce", "finalize", "colsum", "bn_rows"))
-               else "optimiser" if "rmsprop" in k
+               else "norm/act" if any(s_ in k for s_ in ("norm_stream", "stats_kernel", "apply_kernel", "bwd_reduce", "finalize", "colsum", "bn_rows", "bwd_finish"))
+               else "optimiser" if ("rmsprop" in k or "adam" in k)
                else "pack/cast/layout" if any(s_ in k for s_ in ("pack", "nchw", "nhwc", "cast", "transpose"))
                else "torch" if k.startswith("at::") else "other (loss, reparam, ...)")
         fam[key] += v[1]

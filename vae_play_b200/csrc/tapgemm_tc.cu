@@ -735,32 +735,35 @@ __global__ void __launch_bounds__(kFwdThreads) tapwgrad_tc_kernel(const __grid_c
         }
     } else if (warp >= 2 && warp <= 5) {
         const int lane_base = (warp & 3) * 32;
-        const int gc = m0 + lane_base + lane;
         mbar_wait(acc_ready, 0);
         tc_fence_after();
-        float* out = p.dWp + (int64_t)p.taps.widx[tap] * p.o_st + (int64_t)gc * p.o_sg + c0;
+        // acc_ready also says that every pipeline stage has been consumed (this CTA computes ONE output tile): the ring's
+        // shared memory now serves as a per-warp transposition buffer, so that each store / reduction instruction of a warp
+        // covers four full 128-byte row segments instead of 32 sixteen-byte pieces of 32 different rows
+        constexpr int kTStride = 36;                                // floats per staged row: conflict-free 16-byte accesses
+        float* stg = reinterpret_cast<float*>(smem) + (warp & 3) * (32 * kTStride);
+        const int cr = lane >> 3, cc = (lane & 7) * 4;
+        float* out = p.dWp + (int64_t)p.taps.widx[tap] * p.o_st + (int64_t)(m0 + lane_base + cr) * p.o_sg + c0 + cc;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
             tmem_ld_wait();
-            if (gc < p.GC) {
-                if (p.store_only && c0 + c + 32 <= p.AC) {
+            __syncwarp();                                           // the previous chunk has been read out of the buffer
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4*>(out + c + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                                                              __uint_as_float(v[j + 3]));
-                } else if (c0 + c + 32 <= p.AC) {
-                    // whole chunk inside the tensor: 8 vector reductions (red.global.add.v4.f32), no per-element predicates
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(stg + lane * kTStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            if (c0 + c + 32 <= p.AC) {                              // always (AC % 64 == 0, BN | AC): kept as a guard
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(out + c + j), "f"(__uint_as_float(v[j])),
-                                     "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + cr;
+                    if (m0 + lane_base + row >= p.GC) continue;
+                    const float4 val = *reinterpret_cast<const float4*>(stg + row * kTStride + cc);
+                    float* o = out + (int64_t)(4 * i) * p.o_sg + c;
+                    if (p.store_only) *reinterpret_cast<float4*>(o) = val;
+                    else
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(val.x), "f"(val.y), "f"(val.z), "f"(val.w)
                                      : "memory");
-                } else {
-#pragma unroll 4
-                    for (int j = 0; j < 32; ++j)
-                        if (c0 + c + j < p.AC) atomicAdd(out + c + j, __uint_as_float(v[j]));
                 }
             }
         }

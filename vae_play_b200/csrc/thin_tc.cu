@@ -641,19 +641,24 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
         const int h = half * 128 + lane_base + lane;
         const int pr = et >> 1, part = et & 1;                    // brick pixel, tap parity
         const int by = pr >> 3, bx = pr & 7;
-        int poff[16];
+        // shared-space byte addresses of this thread's 16 partial sums (taps part, part+2, ...); a tap index past the filter
+        // points at the padding words of row 0 (columns 32..35 are never written by the tiles: cleared once, below)
+        const uint32_t ps_u32 = smem_u32(psum);
+        uint32_t poff[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-            const int t = min(2 * u + part, p.ntaps - 1);
-            poff[u] = ((by + p.ty[t] - p.tymin) * p.Wh + bx + p.tx[t] - p.txmin) * kPStride + t * p.CT;
+            const int t = 2 * u + part;
+            poff[u] = t < p.ntaps ? ps_u32 + 4u * (uint32_t)(((by + p.ty[t] - p.tymin) * p.Wh + bx + p.tx[t] - p.txmin) * kPStride + t * p.CT)
+                                  : ps_u32 + 4u * 32u;
         }
+        if (et < 4) psum[32 + et] = 0.f;
+        const uint32_t my_row = ps_u32 + 4u * (uint32_t)(h * kPStride);
+        const float bias0 = p.bias ? p.bias[0] : 0.f, bias1 = (p.bias && p.CT > 1) ? p.bias[1] : 0.f;
+        TileWalk tl;
+        tl.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
         uint32_t i = 0;
-        for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i) {
-            int m = q;
-            const int tw = m % p.tiles_w; m /= p.tiles_w;
-            const int th = m % p.tiles_h; m /= p.tiles_h;
+        for (int q = blockIdx.x; q < p.total_tiles; q += gridDim.x, ++i, tl.next(p.tiles_w, p.tiles_h)) {
             const uint32_t buf = i & 1, use = i >> 1;
-            float* ps = psum;
             mbar_wait(&acc_full[buf], use & 1);
             tc_fence_after();
             uint32_t v[32];
@@ -665,22 +670,24 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
             named_bar_sync(2, 256);                               // everyone has finished reading the previous tile's sums
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<uint4*>(ps + h * kPStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + 4u * j), "r"(v[j]), "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                             : "memory");
             named_bar_sync(1, 256);
-            const int gy = th * 16 + by, gx = tw * 8 + bx;
+            const int gy = tl.th * 16 + by, gx = tl.tw * 8 + bx;
+            const bool ok = part == 0 && gy < p.gh && gx < p.gw;
+            const int64_t off0 = (((int64_t)tl.m * p.gh + gy) * p.gw + gx) * p.CT;
             for (int c = 0; c < p.CT; ++c) {
                 float part_sum[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) part_sum[u] = ps[poff[u] + c];
-                float acc = 0.f;
-#pragma unroll
-                for (int u = 0; u < 16; ++u) acc += (2 * u + part < p.ntaps) ? part_sum[u] : 0.f;
+                for (int u = 0; u < 16; ++u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(part_sum[u]) : "r"(poff[u] + 4u * c) : "memory");
+                float a0 = part_sum[0] + part_sum[1], a1 = part_sum[2] + part_sum[3], a2 = part_sum[4] + part_sum[5], a3 = part_sum[6] + part_sum[7];
+                a0 += part_sum[8] + part_sum[9]; a1 += part_sum[10] + part_sum[11]; a2 += part_sum[12] + part_sum[13]; a3 += part_sum[14] + part_sum[15];
+                float acc = (a0 + a1) + (a2 + a3);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                if (part == 0 && gy < p.gh && gx < p.gw) {
-                    acc = act_fwd(acc + (p.bias ? p.bias[c] : 0.f), p.act, p.slope);
-                    const int64_t off = (((int64_t)m * p.gh + gy) * p.gw + gx) * p.CT + c;
-                    if (p.out_f32) ((float*)p.D)[off] = acc;
-                    else ((bf16*)p.D)[off] = __float2bfloat16_rn(acc);
+                if (ok) {
+                    acc = act_fwd(acc + (c ? bias1 : bias0), p.act, p.slope);
+                    if (p.out_f32) ((float*)p.D)[off0 + c] = acc;
+                    else ((bf16*)p.D)[off0 + c] = __float2bfloat16_rn(acc);
                 }
             }
         }
