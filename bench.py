@@ -927,7 +927,7 @@ def kernel_probe(model, B, dev, peaks, iters=20):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant kernel, from the ncu --set full capture
 # summarised in profiles/ (per image size); None until captured
-DOMINANT_TRAFFIC_BYTES = {64: 222103552}     # profiles/r01_ncu_prof_ct3_fwd_r1e.summary.txt: 132.05 MB read + 90.05 MB written
+DOMINANT_TRAFFIC_BYTES = {64: 222577920}     # profiles/r02_ncu_ct3_fwd.summary.txt: 132.07 MB read + 90.51 MB written
 
 
 def add_arguments(ap):

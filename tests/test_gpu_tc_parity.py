@@ -356,3 +356,26 @@ def test_bf16_discriminator_step_runs_on_tensor_cores(vp):
     torch.cuda.synchronize()
     assert _lib.simt_bf16_count() == simt0
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in d.parameters())
+
+
+@pytest.mark.parametrize("cin,cout,k,hw,b,act", [(64, 4, 1, 1, 3, "relu"), (64, 4, 1, 9, 2, "none"), (64, 2, 3, 12, 2, "sigmoid"),
+                                                 (128, 3, 3, 17, 2, "tanh"), (64, 32, 1, 8, 2, "none"), (64, 1, 5, 20, 2, "sigmoid"),
+                                                 (256, 5, 1, 6, 3, "relu")])
+def test_thin_output_layers_multi_channel(vp, cin, cout, k, hw, b, act):
+    """The thin-output forward kernel (a few output channels: the decoder's 64 -> 1 layer, SCSE's 64 -> 4 squeeze, BE heads) with
+    MORE than one output channel, a bias per channel, every activation, ragged bricks: float64 reference on the bf16-quantised
+    operands.  (A two-channel shortcut for the bias once slipped through the one-channel bench-shape test.)"""
+    import vae_play_b200.functional as VF
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    layer = VF.TapLayer("conv", cin, cout, k=k, stride=1, pad=k // 2)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.1
+    bias = torch.randn(cout, device="cuda", generator=g)
+    x = torch.randn(b, hw, hw, cin, device="cuda", generator=g).to(torch.bfloat16)
+    assert layer._thin("fwd", torch.bfloat16, w)
+    y = layer.fwd(x, w, bias, act=act, out_dtype=torch.float32)
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w.to(torch.bfloat16).double(), bias.double(), padding=k // 2)
+    ref = {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](ref).permute(0, 2, 3, 1)
+    r = rel(npy(y), npy(ref))
+    assert r < TOL_FP32_OUT, f"thin forward {cin}->{cout} k{k} {act}: rel {r:.3e}"

@@ -667,7 +667,7 @@ struct OptTable {
     int64_t n[kOptMax];
 };
 __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd, int zero_g) {
-    pdl_sync();
+    pdl_wait();     // no early trigger: kernels that follow may read the fp32 master weights before their own wait (thin_tc.cu)
     const int ti = blockIdx.y;
     float* __restrict__ p = t.p[ti];
     bf16* __restrict__ sh = t.sh[ti];
@@ -711,6 +711,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
         if (zero_g) const_cast<float*>(g)[i] = 0.f;
         if (sh) sh[i] = __float2bfloat16_rn(pn);
     }
+    __threadfence();      // the updated weights are in L2 before this CTA exits (see pdl_wait() above)
 }
 }  // namespace
 }  // namespace vp
@@ -768,7 +769,7 @@ struct AdamTable {
 };
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable t, float lr, float b1, float b2, float eps, float wd, int64_t step,
                                                    const unsigned long long* __restrict__ step_dev, int zero_g) {
-    pdl_sync();
+    pdl_wait();     // no early trigger (see rmsprop_kernel)
     const int ti = blockIdx.y;
     float* __restrict__ p = t.p[ti];
     float* __restrict__ g = const_cast<float*>(t.g[ti]);
@@ -790,6 +791,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
         if (zero_g) g[i] = 0.f;
         if (sh) sh[i] = __float2bfloat16_rn(pn);
     }
+    __threadfence();
 }
 }  // namespace
 }  // namespace vp

@@ -247,14 +247,15 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    pdl_sync();     // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory only from here on
-    // weight tile B[n][k] = W[n, kmap[k]] (zero for padding K), K-major SWIZZLE_128B
+    // weight tile B[n][k] = W[n, kmap[k]] (zero for padding K), K-major SWIZZLE_128B.  Read BEFORE pdl_sync(): the fp32 master
+    // weights are written by the optimiser kernels only, and those never let a dependent grid start early (common.cuh)
     for (int i = threadIdx.x; i < p.N * 64; i += kKThreads) {
         const int n = i >> 6, k = i & 63;
         const int t = p.g.kmap[k];
         const float v = t >= 0 ? p.W[n * p.w_sn + t * p.w_st] : 0.f;
         *reinterpret_cast<bf16*>(smem_b + n * 128 + (((k >> 3) ^ (n & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
     }
+    pdl_sync();     // everything above overlaps the previous kernel's tail; activations / gradients only from here on
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -577,14 +578,15 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    pdl_sync();     // barrier init / TMEM allocation above overlap the previous kernel's tail; global memory only from here on
-    // weight tiles: per 64-channel k-block, 32 rows j = t*CT + c of 64 input channels (K-major SW128)
+    // weight tiles: per 64-channel k-block, 32 rows j = t*CT + c of 64 input channels (K-major SW128); read before pdl_sync()
+    // like thin_k_kernel's (only the optimiser kernels write the fp32 master weights, and they hold their dependents back)
     for (int i = threadIdx.x; i < p.kblocks * 32 * 64; i += kNThreads) {
         const int k = i & 63, j = (i >> 6) & 31, kb = i >> 11;
         float v = 0.f;
         if (j < nvals) v = p.W[(j % p.CT) * p.w_sc + (int64_t)(kb * 64 + k) * p.w_sk + p.widx[j / p.CT] * p.w_st];
         *reinterpret_cast<bf16*>(smem_b + kb * 4096 + j * 128 + (((k >> 3) ^ (j & 7)) << 4) + (k & 7) * 2) = __float2bfloat16_rn(v);
     }
+    pdl_sync();     // everything above overlaps the previous kernel's tail; activations only from here on
     fence_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -653,7 +655,9 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
         }
         if (et < 4) psum[32 + et] = 0.f;
         const uint32_t my_row = ps_u32 + 4u * (uint32_t)(h * kPStride);
-        const float bias0 = p.bias ? p.bias[0] : 0.f, bias1 = (p.bias && p.CT > 1) ? p.bias[1] : 0.f;
+        uint32_t vmask = 0;                                       // bit u: tap 2u+part exists (its address moves with the channel c)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) vmask |= (2 * u + part < p.ntaps ? 1u : 0u) << u;
         TileWalk tl;
         tl.init(blockIdx.x, gridDim.x, p.tiles_w, p.tiles_h);
         uint32_t i = 0;
@@ -679,13 +683,14 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
             for (int c = 0; c < p.CT; ++c) {
                 float part_sum[16];
 #pragma unroll
-                for (int u = 0; u < 16; ++u) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(part_sum[u]) : "r"(poff[u] + 4u * c) : "memory");
+                for (int u = 0; u < 16; ++u)
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(part_sum[u]) : "r"(poff[u] + ((vmask >> u) & 1u ? 4u * c : 0u)) : "memory");
                 float a0 = part_sum[0] + part_sum[1], a1 = part_sum[2] + part_sum[3], a2 = part_sum[4] + part_sum[5], a3 = part_sum[6] + part_sum[7];
                 a0 += part_sum[8] + part_sum[9]; a1 += part_sum[10] + part_sum[11]; a2 += part_sum[12] + part_sum[13]; a3 += part_sum[14] + part_sum[15];
                 float acc = (a0 + a1) + (a2 + a3);
                 acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                 if (ok) {
-                    acc = act_fwd(acc + (c ? bias1 : bias0), p.act, p.slope);
+                    acc = act_fwd(acc + (p.bias ? p.bias[c] : 0.f), p.act, p.slope);
                     if (p.out_f32) ((float*)p.D)[off0 + c] = acc;
                     else ((bf16*)p.D)[off0 + c] = __float2bfloat16_rn(acc);
                 }
