@@ -253,6 +253,10 @@ class StepRunner:
         off_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         _, eps_inc = VF.philox_policy(B * 128, torch.cuda.get_device_properties(dev).multi_processor_count)
 
+        # weight gradients on a side stream: the tensor-bound wgrad kernel of block L runs next to the bandwidth-bound
+        # BatchNorm-backward passes of block L-1 (functional.set_async_wgrad); joined at the end of every backward (stage)
+        VF.set_async_wgrad(not args.no_async_wgrad and not args.torch_optim)
+
         def fwd_bwd(x):
             # disjoint, reproducible Philox streams per rank: seed = rank; the offset lives on the device and
             # advances by what Tensor.normal_() on B*z elements would consume, so CUDA-graph replays draw fresh eps
@@ -260,6 +264,7 @@ class StepRunner:
             VF.philox_advance(off_dev, eps_inc)
             loss = VF.vae_loss(x, xt, kl, mse_scale=1.0 / world)
             loss.backward()
+            VF.join_async()
             return loss
 
         # Data parallel, graph mode: the backward is cut at the output of the encoder's conv stack.  Stage 1 (decoder, heads,
@@ -278,11 +283,13 @@ class StepRunner:
             a3 = taps[0]          # behind VF.grad_cut: naming it in `inputs` executes only that identity node
             a3.register_hook(lambda g: cut.__setitem__("g", g))
             loss.backward(inputs=stage1_params + [a3], retain_graph=True)
+            VF.join_async()
             cut["a"] = a3
             return loss
 
         def bwd_stage2():
             cut["a"].backward(cut["g"], inputs=enc_conv_params)
+            VF.join_async()
 
         def eager_step(x):
             opt.zero_grad(set_to_none=True)
@@ -620,6 +627,7 @@ def vaegan_bench(args, dev, peaks, img=128, B=64):
     from vae_play_b200.models.networks import VaeGan
     from vae_play_b200.optim import FusedRMSprop
     torch.manual_seed(0)
+    VF.set_async_wgrad(False)       # the decoder / discriminator weights are used two and three times per backward: autograd adds on the main stream
     net = VaeGan(img, 128).to(dev).train()
     groups = [net.encoder, net.decoder, net.discriminator, net.param_encoder]             # train.py:136-140
     opts = [FusedRMSprop(list(m.parameters()), lr=1e-4, zero_grads=True) for m in groups]
@@ -952,6 +960,7 @@ def add_arguments(ap):
                     help="data parallel: gradient buckets cross NVLink in bf16 (half the bytes; the optimiser reads the reduced bf16 values) or fp32")
     ap.add_argument("--sm-reserve", type=int, default=32, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-async-wgrad", action="store_true", help="weight gradients on the main stream (default: a side stream, overlapping the BatchNorm-backward passes)")
 
 
 def main():

@@ -975,3 +975,74 @@ def test_host_io_pipeline(vp):
         pipe.feed(torch.rand(64, 1, 64, 64))          # not pinned
     with pytest.raises(RuntimeError):
         pipe.feed(batches[0]); pipe.feed(batches[0]); pipe.feed(batches[0])
+
+
+def test_async_wgrad_matches_sync(vp):
+    """Weight gradients on the side stream (functional.set_async_wgrad) == on the main stream: ONE forward, two backward passes
+    over the same graph into persistent slots, eagerly and inside a captured CUDA graph (fork / join inside the capture)."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200.models.networks import VaeGan
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    VF.set_fuse_bn_backward(False)        # bit-comparable backward passes (see test_two_stage_backward_matches_single)
+    torch.manual_seed(3)
+    m = VaeGan(64, 128).cuda().train()
+    x = torch.rand(64, 1, 64, 64, device="cuda")
+    eps = torch.randn(64, 128, device="cuda")
+    params = list(m.encoder.parameters()) + list(m.decoder.parameters())
+    # everything on ONE non-default stream: autograd pins each AccumulateGrad node to the stream of the first forward that used
+    # the parameter, and the legacy default stream cannot take part in a capture
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    try:
+      with torch.cuda.stream(side):
+          flat = VF.persistent_grads(params)
+          xt, mulv, kl = m.vae_forward(x, eps=eps)
+          loss = VF.vae_loss(x, xt, kl)
+          res = []
+          for on in (False, True, True):
+              VF.set_async_wgrad(on)
+              for p in params:
+                  p.grad = None
+              flat.zero_()
+              for e in VF._GRAD_SINKS.values():
+                  e[3], e[4] = True, False
+              loss.backward(retain_graph=True)
+              VF.join_async()
+              torch.cuda.synchronize()
+              res.append([npy(p.grad) for p in params])
+          for a, b, c in zip(*res):
+              assert rel_l2(b, a) < 1e-5 and rel_l2(c, a) < 1e-5
+          # captured: the side stream forks from and joins the capture stream inside the graph
+          for p in params:
+              p.grad = None
+          flat.zero_()
+          for e in VF._GRAD_SINKS.values():
+              e[3], e[4] = True, False
+          g = torch.cuda.CUDAGraph()
+
+          def fb():
+              xt, mulv, kl = m.vae_forward(x, eps=eps)
+              VF.vae_loss(x, xt, kl).backward()
+              VF.join_async()
+          for p in params:
+              p.grad = None
+          fb()                                      # warm-up outside the capture
+          torch.cuda.synchronize()
+          for p in params:
+              p.grad = None
+          flat.zero_()
+          for e in VF._GRAD_SINKS.values():
+              e[3], e[4] = True, False
+          with torch.cuda.graph(g, stream=side):
+              fb()
+          flat.zero_()
+          g.replay()
+          torch.cuda.synchronize()
+          for a, p in zip(res[0], params):
+              assert rel_l2(npy(p.grad), a) < 3e-2      # a second forward: its BatchNorm statistics differ by atomics order (bf16 flips)
+              assert np.isfinite(npy(p.grad)).all()
+    finally:
+        VF.set_async_wgrad(False)
+        VF.set_fuse_bn_backward(True)
+        VF.set_grad_sinks({})

@@ -24,11 +24,14 @@ VF.persistent_grads(params)
 x = torch.rand(B, 1, img, img, device=dev)
 off = torch.zeros(1, dtype=torch.int64, device=dev)
 
+VF.set_async_wgrad("--no-async-wgrad" not in sys.argv)
+
 def fwd_bwd():
     xt, mulv, kl = model.vae_forward(x, rng=(0, 0, off))
     VF.philox_advance(off, 4)
     loss = VF.vae_loss(x, xt, kl)
     loss.backward()
+    VF.join_async()
     return loss
 
 def eager_step():

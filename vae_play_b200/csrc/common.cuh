@@ -25,9 +25,9 @@ void count_simt_bf16();      // a bf16 contraction that fell back to the CUDA-co
 // captured CUDA graph the launches become programmatic dependency edges.  RULE: a kernel launched through launch_k() must
 // execute pdl_wait() in every thread before its first global-memory access (reads of what the predecessor wrote AND writes
 // to what it may still read); pdl_trigger() right after it lets the successor pre-launch in turn (at most one kernel ahead).
-// EXCEPTION: the fp32 master weights.  They are written by the optimiser kernels only, which never trigger early and fence
-// their stores before exiting, so a grid can only be scheduled once every optimiser CTA has retired with its updates in L2;
-// the thin-layer kernels use this to build their weight tile (a strided fp32 gather, ~5 us) ahead of pdl_wait().
+// EXCEPTION: the fp32 master weights.  They are written by the optimiser kernels only, which never trigger early: without
+// griddepcontrol.launch_dependents the dependent grid is scheduled when the optimiser grid has completed, as in plain stream
+// order.  The thin-layer kernels use this to build their weight tile (a strided fp32 gather, ~5 us) ahead of pdl_wait().
 // VP_PDL=0 in the environment launches everything fully serialised (A/B measurements, debugging).
 bool pdl_enabled();
 // Dynamic shared memory to request so that AT MOST `ctas_per_sm` CTAs of a kernel fit on an SM.  A persistent kernel sized as

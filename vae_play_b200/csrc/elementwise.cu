@@ -667,7 +667,8 @@ struct OptTable {
     int64_t n[kOptMax];
 };
 __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd, int zero_g) {
-    pdl_wait();     // no early trigger: kernels that follow may read the fp32 master weights before their own wait (thin_tc.cu)
+    pdl_wait();     // no early trigger: a dependent grid starts only once this grid has COMPLETED -- kernels that follow may read
+                    // the fp32 master weights ahead of their own wait (thin_tc.cu)
     const int ti = blockIdx.y;
     float* __restrict__ p = t.p[ti];
     bf16* __restrict__ sh = t.sh[ti];
@@ -711,7 +712,6 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
         if (zero_g) const_cast<float*>(g)[i] = 0.f;
         if (sh) sh[i] = __float2bfloat16_rn(pn);
     }
-    __threadfence();      // the updated weights are in L2 before this CTA exits (see pdl_wait() above)
 }
 }  // namespace
 }  // namespace vp
@@ -791,7 +791,6 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
         if (zero_g) g[i] = 0.f;
         if (sh) sh[i] = __float2bfloat16_rn(pn);
     }
-    __threadfence();
 }
 }  // namespace
 }  // namespace vp

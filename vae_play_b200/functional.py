@@ -114,6 +114,47 @@ def set_fuse_bn_backward(on: bool, thin: bool = False):
     _STATE["fuse_bn_bwd_thin"] = bool(on) and bool(thin)
 
 
+_ASYNC = {"on": False, "stream": None, "pending": [], "forked": False}
+
+
+def set_async_wgrad(on: bool):
+    """Weight gradients of the fused layers on a side stream, concurrent with the rest of the backward pass (the tensor-bound
+    weight-gradient kernel of block L overlaps the bandwidth-bound BatchNorm-backward passes of block L-1).  Only gradients that
+    go straight into a persistent slot (``persistent_grads`` / data-parallel buckets) take the side stream: nothing on the main
+    stream touches them until the optimiser -- PROVIDED every weight is used once per backward (the VAE step; not the VAE-GAN
+    step, whose decoder / discriminator weights receive several gradients that autograd sums on the main stream).  The caller
+    MUST call ``join_async()`` after ``backward()`` -- inside the same
+    CUDA-graph capture when capturing; the fused optimisers and ``GradBuckets`` also join before they read gradients."""
+    _ASYNC["on"] = bool(on)
+    if not on:
+        join_async()
+
+
+def _async_fork(weight):
+    """An event on the current stream if this weight's gradient may be computed on the side stream, else None."""
+    if not _ASYNC["on"]:
+        return None
+    hit = _GRAD_SINKS.get(weight.data_ptr())
+    if hit is None or hit[2].grad is not None or hit[4] or hit[2].shape != weight.shape or hit[2].stride() != weight.stride():
+        return None            # no slot, or the slot is taken: autograd will add on the main stream
+    if _ASYNC["stream"] is None or _ASYNC["stream"].device != weight.device:
+        _ASYNC["stream"] = torch.cuda.Stream(weight.device)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(weight.device))
+    _ASYNC["forked"] = True
+    return ev
+
+
+def join_async():
+    """The current stream waits for every weight gradient launched on the side stream; their operands may be freed."""
+    if _ASYNC["forked"]:
+        ev = torch.cuda.Event()
+        ev.record(_ASYNC["stream"])
+        torch.cuda.current_stream(_ASYNC["stream"].device).wait_event(ev)
+        _ASYNC["forked"] = False
+    _ASYNC["pending"].clear()
+
+
 def set_pad_route(on: bool):
     """bf16 layers whose channel counts are not multiples of 64: zero-pad onto the tcgen05 kernels (default) or fall back to the
     packed route (CUDA-core kernel unless the shape happens to be tensor-core eligible) -- tests / A-B measurements."""
@@ -662,7 +703,7 @@ class _FusedLayerFn(torch.autograd.Function):
                 # a bias directly in front of Batch/InstanceNorm (StyleUp's ConvTranspose2d, network_Style_GAN.py:49-50) is
                 # removed by the mean subtraction: its gradient is identically zero (the reference computes round-off noise)
                 dbias = torch.zeros(cc if norm.kind == "batch" else c, dtype=torch.float32, device=dev)
-        dw = layer.wgrad(x, dy, weight)
+        fork = _async_fork(weight)          # dy is complete at this point of the stream: a concurrent weight gradient may start here
         dx = None
         if ctx.needs_input_grad[0]:
             prev = ctx.prev_bn
@@ -672,6 +713,15 @@ class _FusedLayerFn(torch.autograd.Function):
                 prev["pre"] = (dx.data_ptr(), dx._version, parts, nparts)
             else:
                 dx = layer.dgrad(dy, weight, ctx.x_shape)
+        if fork is None:
+            dw = layer.wgrad(x, dy, weight)
+        else:
+            # launched AFTER the data gradient (the critical path keeps the SMs first), on the side stream: it runs next to the
+            # bandwidth-bound BatchNorm-backward passes of the block below
+            with torch.cuda.stream(_ASYNC["stream"]):
+                _ASYNC["stream"].wait_event(fork)
+                dw = layer.wgrad(x, dy, weight)
+            _ASYNC["pending"].append((x, dy))        # keep the operands allocated until join_async()
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 

@@ -65,6 +65,8 @@ class FusedRMSprop(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from . import functional as VF
+        VF.join_async()          # weight gradients still running on the side stream (functional.set_async_wgrad)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for gi, group in enumerate(self.param_groups):
             pa, ga, sa, na, n, plist, sha, shadows, wire = self._table(gi, group)
@@ -128,6 +130,8 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from . import functional as VF
+        VF.join_async()          # weight gradients still running on the side stream (functional.set_async_wgrad)
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         for gi, group in enumerate(self.param_groups):
             pa, ga, ma, va, na, n, plist, sha, shadows = self._table(gi, group)

@@ -101,6 +101,7 @@ class GradBuckets:
         the current stream.  No-op with an fp32 wire.  Called by the hooks (eager) or by the caller inside its captured graph."""
         if self.wire_dtype is None:
             return
+        self._join_side_stream()
         import ctypes as C
         from . import _lib
         from . import functional as VF
@@ -118,7 +119,14 @@ class GradBuckets:
         b = self.buckets[bucket_id]
         return {id(p): torch.as_strided(b["wire"], p.shape, p.stride(), storage_offset=self.slot[id(p)][2]) for p in b["params"]}
 
+    @staticmethod
+    def _join_side_stream():
+        if torch.cuda.is_available():
+            from . import functional as VF           # weight gradients still running on functional's side stream
+            VF.join_async()
+
     def _reduce(self, b):
+        self._join_side_stream()
         if self.wire_dtype is not None and not b["packed"]:
             self.pack([next(i for i, x in enumerate(self.buckets) if x is b)])
         buf = b["wire"] if self.wire_dtype is not None else b["buf"]
