@@ -284,7 +284,8 @@ class StepRunner:
             a3.register_hook(lambda g: cut.__setitem__("g", g))
             loss.backward(inputs=stage1_params + [a3], retain_graph=True)
             VF.join_async()
-            cut["a"] = a3
+            a3.grad = None        # `inputs` also accumulated it into .grad
+            cut["a"] = taps[1]    # stage 2 starts one identity node further in: no retained .grad to clone or add into
             return loss
 
         def bwd_stage2():
@@ -302,6 +303,29 @@ class StepRunner:
             else:
                 opt.step()
             return loss
+
+        # One GPU: the optimiser is split in two and its larger part (everything but the encoder convs: 97 % of the bytes) is
+        # launched on its own stream as soon as those gradients are final -- a bandwidth-bound kernel next to the tensor-bound
+        # encoder-conv backward.  The whole step is then ONE CUDA graph.
+        overlap_opt = use_graph and buckets is None and not args.torch_optim and not args.no_overlap_opt
+        if overlap_opt:
+            from vae_play_b200.optim import FusedRMSprop
+            opt1 = FusedRMSprop(stage1_params, lr=1e-4, zero_grads=True)
+            opt2 = FusedRMSprop(enc_conv_params, lr=1e-4, zero_grads=True)
+            opt_stream = torch.cuda.Stream()
+
+            def eager_step(x):            # noqa: F811 -- same step, the optimiser in two parts
+                main = torch.cuda.current_stream()
+                opt1.zero_grad(set_to_none=True)                          # host-side only: the slots are handed out afresh
+                opt2.zero_grad(set_to_none=True)
+                loss = fwd_bwd_stage1(x)                                  # ends with join_async(): every stage-1 gradient is final
+                opt_stream.wait_stream(main)
+                with torch.cuda.stream(opt_stream):
+                    opt1.step()
+                bwd_stage2()
+                opt2.step()
+                main.wait_stream(opt_stream)
+                return loss
 
         graph_a = graph_b = graph_a2 = None
         graph_bs = []
@@ -327,7 +351,11 @@ class StepRunner:
             opt.zero_grad(set_to_none=True)
             graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             l0 = _lib.launch_count()
-            if split_backward:
+            if overlap_opt:
+                with torch.cuda.graph(graph_a):
+                    static_loss = eager_step(static_x)
+                graph_b = None
+            elif split_backward:
                 early = buckets.buckets_within(stage1_params)
                 graph_a2 = torch.cuda.CUDAGraph()
                 late = [i for i in range(len(buckets.buckets)) if i not in early]
@@ -352,7 +380,9 @@ class StepRunner:
                 buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)
                 buckets.allreduce(check_missing=False)
             l0 = _lib.launch_count()
-            if bucket_opts is not None:
+            if overlap_opt:
+                pass
+            elif bucket_opts is not None:
                 graph_bs = []
                 for o in bucket_opts:
                     gb_ = torch.cuda.CUDAGraph()
@@ -364,6 +394,8 @@ class StepRunner:
                     opt.step()
             launches_opt = _lib.launch_count() - l0
         self.graph = graph_a is not None
+        self.overlap_opt = bool(overlap_opt)
+        self.async_wgrad = not args.no_async_wgrad and not args.torch_optim
         self.split = graph_a2 is not None
         self.launches_per_step = (launches_per_replay + launches_opt) if self.graph else None
 
@@ -373,6 +405,8 @@ class StepRunner:
             if x.data_ptr() != static_x.data_ptr():
                 static_x.copy_(x, non_blocking=True)
             graph_a.replay()
+            if graph_b is None:
+                return static_loss
             if graph_a2 is not None:
                 buckets.allreduce_subset(early, pre_packed=True)      # overlaps the encoder-conv backward below
                 graph_a2.replay()
@@ -519,6 +553,8 @@ def run_ours(args):
                            input="one synthetic batch, re-used every step (resident: already in HBM; e2e: copied from pinned host memory every step on a copy stream, double-buffered, and every step's loss read back one or two steps late -- vae_play_b200/host_io.py)",
                            timing=f"median of {args.repeats} timed regions of {args.steps} steps each (CUDA events, barrier + synchronize on both sides, max over ranks)",
                            cuda_graph=run.graph, pdl=os.environ.get("VP_PDL", "1") != "0",
+                           streams=("weight gradients on a side stream next to the BatchNorm-backward passes" if run.async_wgrad else "single stream")
+                                   + ("; optimiser of everything but the encoder convs on a third stream next to the encoder-conv backward (one graph per step)" if run.overlap_opt else ""),
                            allreduce=(None if world == 1 else
                                       f"bucketed NCCL all-reduce, {run.wire} on the wire (<= {args.sm_reserve} CTAs, high-priority stream); the decoder / fc / heads buckets "
                                       f"(94 % of the bytes) run next to the encoder-conv backward graph, whose persistent grids are capped at "
@@ -960,6 +996,7 @@ def add_arguments(ap):
                     help="data parallel: gradient buckets cross NVLink in bf16 (half the bytes; the optimiser reads the reduced bf16 values) or fp32")
     ap.add_argument("--sm-reserve", type=int, default=32, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-overlap-opt", action="store_true", help="one GPU: optimiser as its own graph after the backward (default: its larger part runs next to the encoder-conv backward)")
     ap.add_argument("--no-async-wgrad", action="store_true", help="weight gradients on the main stream (default: a side stream, overlapping the BatchNorm-backward passes)")
 
 

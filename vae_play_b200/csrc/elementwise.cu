@@ -665,11 +665,15 @@ struct OptTable {
     bf16* sh[kOptMax];          // optional bf16 copy of the updated parameter (same element order), or null
     const bf16* wire[kOptMax];  // optional: the gradient is read from this bf16 buffer (data-parallel wire format) instead of g
     int64_t n[kOptMax];
+    int blk0[kOptMax + 1];      // rmsprop: tensor i is served by the CTAs [blk0[i], blk0[i+1]) of a flat grid (no idle CTAs)
 };
-__global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, float lr, float alpha, float eps, float wd, int zero_g) {
+__global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ OptTable t, int ntensors, float lr, float alpha, float eps, float wd,
+                                                      int zero_g) {
     pdl_wait();     // no early trigger: a dependent grid starts only once this grid has COMPLETED -- kernels that follow may read
                     // the fp32 master weights ahead of their own wait (thin_tc.cu)
-    const int ti = blockIdx.y;
+    int ti = 0;
+    while (ti + 1 < ntensors && (int)blockIdx.x >= t.blk0[ti + 1]) ++ti;
+    const int bid = blockIdx.x - t.blk0[ti], nblk = t.blk0[ti + 1] - t.blk0[ti];
     float* __restrict__ p = t.p[ti];
     bf16* __restrict__ sh = t.sh[ti];
     const float* __restrict__ g = t.g[ti];
@@ -677,8 +681,8 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
     const int64_t n = t.n[ti];
     const bf16* __restrict__ wire = t.wire[ti];
     const int64_t n4 = (((uintptr_t)p | (uintptr_t)g | (uintptr_t)sq) & 15) == 0 && (((uintptr_t)sh | (uintptr_t)wire) & 7) == 0 ? n / 4 : 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    const int64_t stride = (int64_t)nblk * blockDim.x;
+    for (int64_t i = (int64_t)bid * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pv = reinterpret_cast<float4*>(p)[i];
         float4 gv0;
         if (wire) {
@@ -703,7 +707,7 @@ __global__ void __launch_bounds__(256) rmsprop_kernel(const __grid_constant__ Op
             reinterpret_cast<uint2*>(sh)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
         }
     }
-    for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (int64_t i = n4 * 4 + (int64_t)bid * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float gg = (wire ? __bfloat162float(wire[i]) : g[i]) + wd * p[i];
         const float s2 = alpha * sq[i] + (1.f - alpha) * gg * gg;
         sq[i] = s2;
@@ -739,18 +743,30 @@ extern "C" int vp_rmsprop_step_wire(void* const* params, void* const* grads, voi
     for (int base = 0; base < count; base += kOptMax) {
         OptTable t;
         const int m = count - base < kOptMax ? count - base : kOptMax;
-        int64_t nmax = 0;
+        // CTAs in proportion to each tensor's size: ~4 float4 iterations per thread at least, at most 2 CTAs per SM per tensor
+        const int cap = 2 * num_sms();
+        int total = 0;
         for (int i = 0; i < m; ++i) {
             t.p[i] = (float*)params[base + i]; t.g[i] = (const float*)grads[base + i]; t.sq[i] = (float*)sq[base + i];
             t.n[i] = numel[base + i];
             t.sh[i] = shadows ? (bf16*)shadows[base + i] : nullptr;
             t.wire[i] = wire_grads ? (const bf16*)wire_grads[base + i] : nullptr;
-            nmax = numel[base + i] > nmax ? numel[base + i] : nmax;
+            int64_t nb = (numel[base + i] / 4 + 1023) / 1024;
+            nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
+            t.blk0[i] = total;
+            total += (int)nb;
         }
-        int64_t bx = (nmax / 4 + 255) / 256;
-        if (bx > 148 * 2) bx = 148 * 2;
-        if (bx < 1) bx = 1;
-        launch_k(rmsprop_kernel, dim3((unsigned)bx, (unsigned)m), dim3(256), 0, (cudaStream_t)stream, t, lr, alpha, eps, weight_decay, zero_grads);
+        t.blk0[m] = total;
+        // Ask for the maximum shared-memory carve-out although the kernel uses none: an SM whose L1 / shared split was set for a
+        // kernel without shared memory cannot take CTAs of the TMA kernels (75-220 KB each) until it has drained, i.e. the
+        // optimiser could never run NEXT TO the backward pass it is meant to overlap (measured: the first BatchNorm pass of the
+        // encoder backward started only when this kernel had finished).
+        static bool carve_set = false;
+        if (!carve_set) {
+            cudaFuncSetAttribute(rmsprop_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            carve_set = true;
+        }
+        launch_k(rmsprop_kernel, dim3((unsigned)total), dim3(256), 0, (cudaStream_t)stream, t, m, lr, alpha, eps, weight_decay, zero_grads);
         VP_CHECK_LAUNCH("vp_rmsprop_step");
     }
     return VP_OK;

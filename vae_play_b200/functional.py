@@ -114,7 +114,7 @@ def set_fuse_bn_backward(on: bool, thin: bool = False):
     _STATE["fuse_bn_bwd_thin"] = bool(on) and bool(thin)
 
 
-_ASYNC = {"on": False, "stream": None, "pending": [], "forked": False}
+_ASYNC = {"on": False, "stream": None, "pending": [], "forked": False, "home": None}
 
 
 def set_async_wgrad(on: bool):
@@ -140,19 +140,25 @@ def _async_fork(weight):
     if _ASYNC["stream"] is None or _ASYNC["stream"].device != weight.device:
         _ASYNC["stream"] = torch.cuda.Stream(weight.device)
     ev = torch.cuda.Event()
-    ev.record(torch.cuda.current_stream(weight.device))
+    _ASYNC["home"] = torch.cuda.current_stream(weight.device)
+    ev.record(_ASYNC["home"])
     _ASYNC["forked"] = True
     return ev
 
 
 def join_async():
-    """The current stream waits for every weight gradient launched on the side stream; their operands may be freed."""
+    """The current stream waits for every weight gradient launched on the side stream.  When the current stream is the one the
+    backward ran on, their operands may be freed too (a third stream -- an optimiser overlapping the rest of the backward --
+    only waits: the allocator hands freed blocks straight back to the stream that allocated them)."""
+    cur = None
     if _ASYNC["forked"]:
         ev = torch.cuda.Event()
         ev.record(_ASYNC["stream"])
-        torch.cuda.current_stream(_ASYNC["stream"].device).wait_event(ev)
+        cur = torch.cuda.current_stream(_ASYNC["stream"].device)
+        cur.wait_event(ev)
+    if cur is None or _ASYNC.get("home") is None or cur == _ASYNC["home"]:
         _ASYNC["forked"] = False
-    _ASYNC["pending"].clear()
+        _ASYNC["pending"].clear()
 
 
 def set_pad_route(on: bool):

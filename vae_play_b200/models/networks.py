@@ -89,14 +89,18 @@ class Encoder(nn.Module):
 
     def forward_packed(self, ten, taps=None):
         """NCHW fp32 image -> fused head output [B, 2Z] = (mu | logvar), fp32.  ``taps`` (a list) receives the output of
-        the conv stack: the point where a two-stage backward can be cut (bench.py overlaps the gradient all-reduce of
+        the conv stack twice (see below): the point where a two-stage backward can be cut (bench.py overlaps the gradient all-reduce of
         everything downstream of it with the backward of the conv stack)."""
         a = VF.to_channels_last(ten)
         for blk in self.conv:
             a = blk.forward_cl(a)
         if taps is not None:
-            a = VF.grad_cut(a)
+            # two identity nodes: a two-stage backward names taps[0] in ``inputs`` of stage 1 (autograd then also retains its
+            # .grad, and would clone / add into it again on every later pass through its node) and starts stage 2 from taps[1]
+            inner = VF.grad_cut(a)
+            a = VF.grad_cut(inner)
             taps.append(a)
+            taps.append(inner)
         if a.shape[1] != 8 or a.shape[2] != 8:
             raise ValueError(f"Encoder expects an 8x8 map before fc, got {tuple(a.shape)} (img_size must be 8 * 2**iter_level)")
         h, _ = VF.fused_layer(VF.hwc_to_chw_flat(a), self.fc[0].weight, None, self.fc[1].weight, self.fc[1].bias, self._fc_layer,
