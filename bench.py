@@ -330,6 +330,8 @@ class StepRunner:
         graph_a = graph_b = graph_a2 = None
         graph_bs = []
         early = []
+        extra_launches = 0
+        xstream = torch.cuda.Stream() if buckets is not None else None
         # data parallel: on by default -- the backward graph is cut after encoder.fc's weight gradient (94 % of the gradient
         # bytes are complete there) and the encoder-conv backward that follows is captured with its persistent grids capped at
         # (#SMs - sm_reserve), so that NCCL's CTAs find free SMs and the all-reduce really runs next to it
@@ -356,12 +358,14 @@ class StepRunner:
                     static_loss = eager_step(static_x)
                 graph_b = None
             elif split_backward:
-                early = buckets.buckets_within(stage1_params)
+                early = sorted(buckets.buckets_within(stage1_params), key=lambda i: -buckets.buckets[i]["buf"].numel())
                 graph_a2 = torch.cuda.CUDAGraph()
                 late = [i for i in range(len(buckets.buckets)) if i not in early]
                 with torch.cuda.graph(graph_a):
                     static_loss = fwd_bwd_stage1(static_x)
-                    buckets.pack(early)
+                l1 = _lib.launch_count()
+                buckets.pack(early)              # per step this runs on the exchange stream, next to stage 2 (see step())
+                extra_launches = _lib.launch_count() - l1
                 nsm = torch.cuda.get_device_properties(dev).multi_processor_count
                 _lib.call("vp_set_sm_limit", max(nsm - args.sm_reserve, nsm // 2))
                 try:
@@ -397,7 +401,7 @@ class StepRunner:
         self.overlap_opt = bool(overlap_opt)
         self.async_wgrad = not args.no_async_wgrad and not args.torch_optim
         self.split = graph_a2 is not None
-        self.launches_per_step = (launches_per_replay + launches_opt) if self.graph else None
+        self.launches_per_step = (launches_per_replay + launches_opt + extra_launches) if self.graph else None
 
         def step(x):
             if graph_a is None:
@@ -407,14 +411,26 @@ class StepRunner:
             graph_a.replay()
             if graph_b is None:
                 return static_loss
+            main = torch.cuda.current_stream()
             if graph_a2 is not None:
-                buckets.allreduce_subset(early, pre_packed=True)      # overlaps the encoder-conv backward below
+                # exchange stream: bf16 packing of the stage-1 buckets, then their all-reduce -- all of it next to stage 2
+                xstream.wait_stream(main)
+                with torch.cuda.stream(xstream):
+                    for bi in early:                       # largest first (encoder.fc's weight: 73 % of the bytes)
+                        buckets.pack([bi])
+                        buckets.allreduce_subset([bi], pre_packed=True)
                 graph_a2.replay()
             if bucket_opts is not None:
-                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)      # all buckets queued on NCCL's stream, in order
+                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)      # the rest, queued on NCCL's stream in order
+                with torch.cuda.stream(xstream):
+                    for bi in early:                                        # their updates too run next to stage 2 / the late exchange:
+                        buckets.wait_bucket(bi)                             # nothing left in the step reads those weights
+                        graph_bs[bi].replay()
                 for bi, gb_ in enumerate(graph_bs):
-                    buckets.wait_bucket(bi)                                 # update of bucket bi overlaps the all-reduce of bi+1
-                    gb_.replay()
+                    if bi not in early:
+                        buckets.wait_bucket(bi)
+                        gb_.replay()
+                main.wait_stream(xstream)
                 return static_loss
             if buckets is not None:
                 buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)

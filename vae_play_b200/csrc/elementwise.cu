@@ -592,6 +592,11 @@ extern "C" int vp_pack_grads_bf16(float* src, void* dst_bf16, int64_t n, int zer
     VP_CHECK_ARG(src && dst_bf16 && n >= 0 && (n & 3) == 0 && (((uintptr_t)src | (uintptr_t)dst_bf16) & 15) == 0,
                  "vp_pack_grads_bf16: n must be a multiple of 4 and the buffers 16-byte aligned");
     if (n == 0) return VP_OK;
+    static bool carve_set = false;       // meant to run NEXT TO the TMA kernels of the backward pass: see vp_rmsprop_step_wire
+    if (!carve_set) {
+        cudaFuncSetAttribute(pack_grads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carve_set = true;
+    }
     launch_k(pack_grads_kernel, dim3(grid_for(n / 4)), dim3(256), 0, (cudaStream_t)stream, src, (bf16*)dst_bf16, n / 4, zero_src);
     VP_CHECK_LAUNCH("vp_pack_grads_bf16");
     return VP_OK;
