@@ -732,6 +732,17 @@ def vaegan_bench(args, dev, peaks, img=128, B=64):
     for _ in range(10):
         step()
     torch.cuda.synchronize()
+    if os.environ.get("VP_PROFILE_VAEGAN"):       # diagnostic: per-kernel device time of this step (VP_PDL=0 for clean durations) -> stderr
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        rows = sorted(((e.device_time_total / 3, e.count / 3, e.key) for e in prof.key_averages() if e.device_time_total), reverse=True)
+        tot = sum(r[0] for r in rows)
+        print(f"[vaegan{img} profile] {tot:.0f} us of kernels per step in {sum(r[1] for r in rows):.0f} launches", file=sys.stderr)
+        for t, c, k in rows[:40]:
+            print(f"[vaegan{img} profile] {t:9.1f} us {100 * t / tot:5.1f}%  n={c:5.1f}  {k.replace('void ', '').replace('vp::', '').replace('(anonymous namespace)::', '')[:120]}", file=sys.stderr)
     regs = []
     for _ in range(args.repeats):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

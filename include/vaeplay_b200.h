@@ -226,6 +226,10 @@ int vp_conv_dgrad_cl_bnred(const VpConvGeom* g, const void* dy, const void* w_cl
 int vp_norm_bwd_finish_parts(const float* parts, int nparts, const float* invstd, double* sums, int c, void* stream);
 /* the same fusion for the decoder's output layer (models/networks.py:101: 64 -> 1 channels): its thin data-gradient kernel
  * produces dL/da of the last DecoderBlock -- the largest activation of the step -- and reduces it against that block's y_prev */
+/* dx [n][hi][wi][1] = data gradient of a stride-1 Conv2d with ONE INPUT channel (the discriminator's first layer,
+ * models/networks.py:159, whose input x_tilde carries a gradient): the thin-output forward kernel on dy with flipped taps.
+ * co % 64 == 0 (pad 32 -> 64 first), k <= 5.  dx in out_dtype. */
+int vp_thin_conv_dgrad_in1(const VpConvGeom* g, const void* dy, const float* w, void* dx, int out_dtype, void* stream);
 int vp_thin_conv_dgrad_bnred(const VpConvGeom* g, const void* dy, const float* w, void* dx, const void* y_prev,
                              const float* scale, const float* shift, const float* mean, float* parts, int capacity,
                              int* nparts, void* stream);

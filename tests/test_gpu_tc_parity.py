@@ -379,3 +379,23 @@ def test_thin_output_layers_multi_channel(vp, cin, cout, k, hw, b, act):
     ref = {"none": lambda t: t, "relu": torch.relu, "sigmoid": torch.sigmoid, "tanh": torch.tanh}[act](ref).permute(0, 2, 3, 1)
     r = rel(npy(y), npy(ref))
     assert r < TOL_FP32_OUT, f"thin forward {cin}->{cout} k{k} {act}: rel {r:.3e}"
+
+
+@pytest.mark.parametrize("cout,k,hw,b", [(32, 5, 20, 3), (64, 5, 33, 2), (32, 3, 16, 2), (128, 5, 12, 2)])
+def test_single_channel_input_dgrad(vp, cout, k, hw, b):
+    """Data gradient w.r.t. a ONE-channel input (the VAE-GAN discriminator's first layer sits on x_tilde, which needs a gradient:
+    models/networks.py:159): served by the thin-output kernel with flipped taps, 32-channel dy zero-padded to 64.  float64
+    reference on the bf16-quantised operands; no CUDA-core contraction, no 64x-padded tensor-core launch."""
+    import vae_play_b200.functional as VF
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    layer = VF.TapLayer("conv", 1, cout, k=k, stride=1, pad=k // 2)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    w = torch.randn(cout, 1, k, k, device="cuda", generator=g) * 0.1
+    dy = torch.randn(b, hw, hw, cout, device="cuda", generator=g).to(torch.bfloat16)
+    simt0 = vp._lib.simt_bf16_count()
+    dx = layer.dgrad(dy, w, (b, hw, hw, 1), out_dtype=torch.float32)
+    assert vp._lib.simt_bf16_count() == simt0
+    ref = torch.nn.grad.conv2d_input((b, 1, hw, hw), w.to(torch.bfloat16).double(), dy.double().permute(0, 3, 1, 2), stride=1, padding=k // 2)
+    r = rel(npy(dx), npy(ref.permute(0, 2, 3, 1)))
+    assert r < TOL_FP32_OUT, f"dgrad to a single-channel input, {cout} channels k{k}: rel {r:.3e}"

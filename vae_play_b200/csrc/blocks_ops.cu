@@ -30,6 +30,19 @@ __global__ void __launch_bounds__(256) copy_channels_kernel(const T* __restrict_
     }
 }
 
+// 2-byte elements, everything a multiple of 8 channels, no accumulation (the slice after a padded data gradient, concatenations
+// of 32 / 64-channel maps): one 16-byte chunk per thread
+__global__ void __launch_bounds__(256) copy_channels16_kernel(const uint4* __restrict__ src, int src_c8, int src_off8, uint4* __restrict__ dst, int dst_c8,
+                                                              int dst_off8, int nc8, int64_t rows) {
+    pdl_sync();
+    const int64_t total = rows * nc8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / nc8;
+        const int c = (int)(i - r * nc8);
+        dst[r * dst_c8 + dst_off8 + c] = src[r * src_c8 + src_off8 + c];
+    }
+}
+
 // ---- AddCoords (models/blocks.py:97-112): out[..., :c] = x, out[..., c] = column index, out[..., c+1] = row index ---------
 template <typename T>
 __global__ void __launch_bounds__(256) add_coords_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n, int h, int w, int c, int normalize) {
@@ -425,6 +438,12 @@ extern "C" int vp_copy_channels(const void* src, int src_c, int src_off, void* d
     VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_copy_channels: bad dtype %d", dtype);
     if (rows == 0) return VP_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (dtype == VP_BF16 && !accumulate && ((src_c | src_off | dst_c | dst_off | nc) & 7) == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        launch_k(copy_channels16_kernel, dim3(grid_for(rows * (nc / 8))), dim3(256), 0, s, (const uint4*)src, src_c / 8, src_off / 8, (uint4*)dst, dst_c / 8,
+                 dst_off / 8, nc / 8, rows);
+        VP_CHECK_LAUNCH("vp_copy_channels");
+        return VP_OK;
+    }
     VP_DISPATCH_T(dtype, launch_k(copy_channels_kernel<float>, dim3(grid_for(rows * nc)), dim3(256), 0, s, (const float*)src, src_c, src_off, (float*)dst, dst_c, dst_off, nc, rows, accumulate),
                   launch_k(copy_channels_kernel<bf16>, dim3(grid_for(rows * nc)), dim3(256), 0, s, (const bf16*)src, src_c, src_off, (bf16*)dst, dst_c, dst_off, nc, rows, accumulate));
     VP_CHECK_LAUNCH("vp_copy_channels");

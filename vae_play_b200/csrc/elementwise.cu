@@ -293,6 +293,17 @@ __global__ void __launch_bounds__(256) pad_channels_kernel(const T* __restrict__
         Cvt<T>::st(dst + i, j < c ? Cvt<T>::ld(src + r * c + j) : 0.f);
     }
 }
+// the same for 2-byte elements with c % 8 == 0 and cp % 8 == 0 (32 -> 64 channels): one 16-byte chunk per thread, no divisions by
+// non-powers of two in the common case
+__global__ void __launch_bounds__(256) pad_channels16_kernel(const uint4* __restrict__ src, int c8, uint4* __restrict__ dst, int cp8, int64_t rows) {
+    pdl_sync();
+    const int64_t total = rows * cp8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cp8;
+        const int j = (int)(i - r * cp8);
+        dst[i] = j < c8 ? src[r * c8 + j] : make_uint4(0u, 0u, 0u, 0u);
+    }
+}
 // weight [d0][d1][taps] with element strides (s0, s1, st)  ->  bf16 [d0p][taps][d1p] (channels-last element order), zero padded
 __global__ void __launch_bounds__(256) pad_weight_cl_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int d0, int d1, int taps, int64_t s0,
                                                             int64_t s1, int64_t st, int d0p, int d1p) {
@@ -566,6 +577,11 @@ extern "C" int vp_pad_channels(const void* src, int c, void* dst, int cp, int64_
     VP_CHECK_ARG(src && dst && c > 0 && cp >= c && rows >= 0, "vp_pad_channels: bad arguments");
     VP_CHECK_ARG(dtype == VP_F32 || dtype == VP_BF16, "vp_pad_channels: bad dtype %d", dtype);
     if (rows == 0) return VP_OK;
+    if (dtype == VP_BF16 && c % 8 == 0 && cp % 8 == 0 && (((uintptr_t)src | (uintptr_t)dst) & 15) == 0) {
+        launch_k(pad_channels16_kernel, dim3(grid_for(rows * (cp / 8))), dim3(256), 0, (cudaStream_t)stream, (const uint4*)src, c / 8, (uint4*)dst, cp / 8, rows);
+        VP_CHECK_LAUNCH("vp_pad_channels");
+        return VP_OK;
+    }
     if (dtype == VP_F32) launch_k(pad_channels_kernel<float>, dim3(grid_for(rows * cp)), dim3(256), 0, (cudaStream_t)stream, (const float*)src, c, (float*)dst, cp, rows);
     else launch_k(pad_channels_kernel<bf16>, dim3(grid_for(rows * cp)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)src, c, (bf16*)dst, cp, rows);
     VP_CHECK_LAUNCH("vp_pad_channels");

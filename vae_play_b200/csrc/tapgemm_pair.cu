@@ -250,12 +250,12 @@ __global__ void __launch_bounds__(kPThreads, 1) tapgemm_pair_kernel(const __grid
 // (channels-last, in-place) weights, K a multiple of 64, grids of at least 12 x 12.
 int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
     const TapGemm& p = phases[0];
-    if (!tc_available() || nphases != 4 || getenv("VP_NO_PAIR")) return VP_EUNSUPPORTED;
-    if (p.as != 1 || p.ds != 2 || p.N != 64 || p.K % 64 != 0 || p.n <= 0 || p.out_dtype != VP_BF16) return VP_EUNSUPPORTED;
-    if (!(p.w_sn == 1 && p.w_sk != 1)) return VP_EUNSUPPORTED;
-    if (((uintptr_t)p.A & 15) || ((uintptr_t)p.Wp & 15) || ((uintptr_t)p.D & 15)) return VP_EUNSUPPORTED;
+    if (!tc_available() || nphases != 4 || getenv("VP_NO_PAIR")) { set_error("pair tap GEMM: not eligible (check %d)", 1); return VP_EUNSUPPORTED; }
+    if (p.as != 1 || p.ds != 2 || p.N != 64 || p.K % 64 != 0 || p.n <= 0 || p.out_dtype != VP_BF16) { set_error("pair tap GEMM: not eligible (check %d)", 2); return VP_EUNSUPPORTED; }
+    if (!(p.w_sn == 1 && p.w_sk != 1)) { set_error("pair tap GEMM: not eligible (check %d)", 3); return VP_EUNSUPPORTED; }
+    if (((uintptr_t)p.A & 15) || ((uintptr_t)p.Wp & 15) || ((uintptr_t)p.D & 15)) { set_error("pair tap GEMM: not eligible (check %d)", 4); return VP_EUNSUPPORTED; }
     for (int i = 0; i < 4; ++i)
-        if (phases[i].doy != (i >> 1) || phases[i].dox != (i & 1) || phases[i].taps.ntaps < 1) return VP_EUNSUPPORTED;
+        if (phases[i].doy != (i >> 1) || phases[i].dox != (i & 1) || phases[i].taps.ntaps < 1) { set_error("pair tap GEMM: not eligible (check %d)", 5); return VP_EUNSUPPORTED; }
     int tymin = 1 << 20, tymax = -(1 << 20), txmin = 1 << 20, txmax = -(1 << 20), gh = 0, gw = 0;
     for (int i = 0; i < 4; ++i) {
         const TapList& t = phases[i].taps;
@@ -266,7 +266,7 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
         gh = phases[i].gh > gh ? phases[i].gh : gh;
         gw = phases[i].gw > gw ? phases[i].gw : gw;
     }
-    if (tymax - tymin > 4 || txmax - txmin > 4 || gh < 12 || gw < 12) return VP_EUNSUPPORTED;
+    if (tymax - tymin > 4 || txmax - txmin > 4 || gh < 12 || gw < 12) { set_error("pair tap GEMM: not eligible (check %d)", 6); return VP_EUNSUPPORTED; }
     PairParams pp;
     memset(&pp, 0, sizeof(pp));
     pp.tymin = tymin; pp.txmin = txmin;
@@ -276,7 +276,7 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
     for (int pr = 0; pr < 2; ++pr) {
         PairInfo& pi = pp.pr[pr];
         const TapGemm &a = phases[2 * pr], &b = phases[2 * pr + 1];
-        if (a.gh != b.gh) return VP_EUNSUPPORTED;
+        if (a.gh != b.gh) { set_error("pair tap GEMM: not eligible (check %d)", 7); return VP_EUNSUPPORTED; }
         pi.gh = a.gh; pi.gw[0] = a.gw; pi.gw[1] = b.gw; pi.doy = a.doy; pi.dox[0] = a.dox; pi.dox[1] = b.dox;
         const int gwm = a.gw > b.gw ? a.gw : b.gw;
         pi.tiles_w = (gwm + 2 * kBrickW - 1) / (2 * kBrickW);
@@ -291,7 +291,7 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
                 for (int k = 0; k < b.taps.ntaps; ++k)
                     if (b.taps.ty[k] == a.taps.ty[ja] && b.taps.tx[k] == a.taps.tx[ja]) jb = k;
                 if ((pass == 0) != (jb >= 0)) continue;
-                if (ne >= kMaxEnt) return VP_EUNSUPPORTED;
+                if (ne >= kMaxEnt) { set_error("pair tap GEMM: not eligible (check %d)", 8); return VP_EUNSUPPORTED; }
                 pi.ty[ne] = a.taps.ty[ja]; pi.tx[ne] = a.taps.tx[ja];
                 pi.mode[ne] = pass == 0 ? 0 : 1;
                 pi.widx0[ne] = a.taps.widx[ja]; pi.widx1[ne] = jb >= 0 ? b.taps.widx[jb] : 0;
@@ -302,14 +302,14 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
             for (int k = 0; k < a.taps.ntaps; ++k)
                 if (a.taps.ty[k] == b.taps.ty[kb_] && a.taps.tx[k] == b.taps.tx[kb_]) shared = true;
             if (shared) continue;
-            if (ne >= kMaxEnt) return VP_EUNSUPPORTED;
+            if (ne >= kMaxEnt) { set_error("pair tap GEMM: not eligible (check %d)", 9); return VP_EUNSUPPORTED; }
             pi.ty[ne] = b.taps.ty[kb_]; pi.tx[ne] = b.taps.tx[kb_]; pi.mode[ne] = 2; pi.widx0[ne] = 0; pi.widx1[ne] = b.taps.widx[kb_];
             ++ne;
         }
         pi.nent = ne;
-        if (ne == 0 || pi.mode[0] != 0) return VP_EUNSUPPORTED;      // the first entry must initialise both accumulators
+        if (ne == 0 || pi.mode[0] != 0) { set_error("pair tap GEMM: not eligible (check %d)", 10); return VP_EUNSUPPORTED; }      // the first entry must initialise both accumulators
     }
-    if (tiles > 0x7fffffff) return VP_EUNSUPPORTED;
+    if (tiles > 0x7fffffff) { set_error("pair tap GEMM: not eligible (check %d)", 11); return VP_EUNSUPPORTED; }
     pp.total_tiles = (int)tiles;
     pp.bias = p.bias; pp.n = p.n; pp.hd = p.hd; pp.wd = p.wd; pp.N = p.N; pp.ds = p.ds; pp.act = p.act; pp.slope = p.slope;
     pp.kblocks = p.K / 64;
@@ -323,23 +323,23 @@ int launch_tapgemm_pair(const TapGemm* phases, int nphases, cudaStream_t s) {
         cuuint32_t estr[4] = {1, 1, 1, 1};
         if (encode(&mA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(p.A), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-            return VP_EUNSUPPORTED;
+            { set_error("pair tap GEMM: not eligible (check %d)", 12); return VP_EUNSUPPORTED; }
     }
-    if (encode_weight_map(&mB, p, true, 64)) return VP_EUNSUPPORTED;
+    if (encode_weight_map(&mB, p, true, 64)) { set_error("pair tap GEMM: not eligible (check %d)", 13); return VP_EUNSUPPORTED; }
     OutMaps om;
     memset(&om, 0, sizeof(om));
     for (int i = 0; i < 4; ++i)
-        if (encode_out_map(&om.m[i], p.D, p.N, p.hd, p.wd, p.n, p.ds, phases[i].doy, phases[i].dox, kBrickW, 4, 1)) return VP_EUNSUPPORTED;
+        if (encode_out_map(&om.m[i], p.D, p.N, p.hd, p.wd, p.n, p.ds, phases[i].doy, phases[i].dox, kBrickW, 4, 1)) { set_error("pair tap GEMM: not eligible (check %d)", 14); return VP_EUNSUPPORTED; }
     const int grid = pp.total_tiles < num_sms() ? pp.total_tiles : num_sms();
     pp.stat_parts = nullptr;
     if (p.stat_parts) {
-        if (p.bias || p.act != VP_ACT_NONE) return VP_EUNSUPPORTED;
+        if (p.bias || p.act != VP_ACT_NONE) { set_error("pair tap GEMM: not eligible (check %d)", 15); return VP_EUNSUPPORTED; }
         if (grid > p.stat_capacity) { set_error("pair tap GEMM: statistics buffer holds %d parts, %d needed", p.stat_capacity, grid); return VP_EINVAL; }
         if (p.stat_nparts) *p.stat_nparts = grid;
         pp.stat_parts = p.stat_parts;
     }
     const int smem_bytes = smem_for_occupancy(kAStages * 2 * pp.halo_bytes + kBStages * kBStage + 4 * 2 * 2048 + 128 * 4 + (2 * kAStages + 2 * kBStages + 4) * 8 + 16 + 1024, 1);
-    if (smem_bytes > 227 * 1024) return VP_EUNSUPPORTED;
+    if (smem_bytes > 227 * 1024) { set_error("pair tap GEMM: not eligible (check %d)", 16); return VP_EUNSUPPORTED; }
     static int attr_set = 0;
     if (attr_set < smem_bytes) {
         cudaError_t e = cudaFuncSetAttribute(tapgemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

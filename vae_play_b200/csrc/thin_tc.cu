@@ -208,6 +208,7 @@ struct ThinKParams {
     int out_f32;
     int tiles_w, tiles_h, total_tiles;
     int tma_store;                    // bf16 output with N % 64 == 0: epilogue through shared memory + TMA store
+    int tma_store32;                  // bf16 output with N % 32 == 0 (and not % 64): the same with 32-column SWIZZLE_64B tiles
     float* stat_parts;                // [gridDim.x][2][N] per-CTA BatchNorm partial sums of the stored output, or null
     // fused BatchNorm-backward reduction (N == 64 data gradient of the output layer): D is dL/da of the producer block, mapY its
     // pre-norm output; stat_parts then receives (sum d, sum d*(y - mean)) with d = D * (y*scale + shift > 0)
@@ -341,6 +342,25 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
                         tma_store_commit();
                     }
                 }
+            } else if (p.tma_store32) {
+                // N % 32 == 0 (the VAE-GAN discriminator's 1 -> 32 first layer): 32-column [32 rows][64 B] SWIZZLE_64B staging tiles
+                uint8_t* my_stage = stage_out + (warp & 3) * 8192;
+#pragma unroll 1
+                for (int c = 0; c < p.N; c += 32, ++sg) {
+                    uint8_t* st = my_stage + (sg & 3) * 2048;
+                    if (lane == 0) tma_store_wait_read<3>();
+                    __syncwarp();
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + buf * 128 + ((uint32_t)lane_base << 16) + (uint32_t)c, v);
+                    tmem_ld_wait();
+                    stage_chunk32_sw64(st, lane, c, v, p.bias, p.act, p.slope);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&mapD, st, c, tw * 8, th * 16 + (warp & 3) * 4, m);
+                        tma_store_commit();
+                    }
+                }
             } else {
 #pragma unroll 1
                 for (int c = 0; c < p.N; c += 32) {
@@ -354,7 +374,7 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        if (p.tma_store && lane == 0) tma_store_wait_read<0>();
+        if ((p.tma_store || p.tma_store32) && lane == 0) tma_store_wait_read<0>();
     }
     tc_fence_before();
     __syncthreads();
@@ -370,12 +390,13 @@ __global__ void __launch_bounds__(kKThreads, 2) thin_k_kernel(const __grid_const
 
 constexpr int kKSmem = kKStages * 16384 + 16384 + 4 * 2 * 4096 + 2 * kHaloBuf + 256 * 4 + (2 * kKStages + 4 + 4) * 8 + 16 + 1024;
 
-int encode_box(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh);
+int encode_box(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bc = 64);
 
 int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* stat_nparts = nullptr, const void* bn_y = nullptr) {
     CUtensorMap mD, mY;
     memset(&mD, 0, sizeof(mD));
     p.tma_store = (!p.out_f32 && p.N % 64 == 0) ? 1 : 0;
+    p.tma_store32 = (!p.out_f32 && !p.tma_store && p.N % 32 == 0 && !p.stat_parts) ? 1 : 0;
     if (bn_y && (p.N != 64 || !p.tma_store || !p.stat_parts)) return VP_EUNSUPPORTED;
     if (p.stat_parts) {
         const int g = p.total_tiles < 2 * num_sms() ? p.total_tiles : 2 * num_sms();
@@ -384,6 +405,7 @@ int launch_thin_k(ThinKParams& p, cudaStream_t s, int stat_capacity = 0, int* st
         if (stat_nparts) *stat_nparts = g;
     }
     if (p.tma_store && encode_box(&mD, p.D, p.N, p.gw, p.gh, p.n, 8, 4)) { set_error("thin_k: cuTensorMapEncodeTiled(D) failed"); return VP_EUNSUPPORTED; }
+    if (p.tma_store32 && encode_box(&mD, p.D, p.N, p.gw, p.gh, p.n, 8, 4, 32)) { set_error("thin_k: cuTensorMapEncodeTiled(D, 32) failed"); return VP_EUNSUPPORTED; }
     mY = mD;
     if (bn_y && encode_box(&mY, bn_y, p.N, p.gw, p.gh, p.n, 8, 4)) { set_error("thin_k: cuTensorMapEncodeTiled(y) failed"); return VP_EUNSUPPORTED; }
     static bool attr_set = false;
@@ -707,14 +729,15 @@ __global__ void __launch_bounds__(kNThreads, 2) thin_n_kernel(const __grid_const
 
 constexpr int kNSmemBase = kNStages * kNStage + 256 * kPStride * 4 + (2 * kNStages + 4) * 8 + 16 + 1024;   // + kblocks * 4096
 
-int encode_box(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh) {
+int encode_box(CUtensorMap* m, const void* ptr, int C, int W, int H, int N, int bw, int bh, int bc) {
     EncodeTiledFn encode = get_encode();
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+    cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        bc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
@@ -763,6 +786,7 @@ extern "C" int vp_thin_conv_fwd_stats(const VpConvGeom* g, const void* x, const 
     return thin_conv_fwd_impl(g, x, w, nullptr, y, VP_BF16, VP_ACT_NONE, 0.f, stat_parts, stat_capacity, nparts, stream);
 }
 
+static int launch_thin_n(const ThinNParams& p, const void* A, int C, int W, int H, int N, cudaStream_t s);
 static int thin_conv_fwd_impl(const VpConvGeom* g, const void* x, const float* w, const float* bias, void* y, int out_dtype, int act, float slope,
                               float* stat_parts, int stat_capacity, int* stat_nparts, void* stream) {
     if (!thin_geom_ok(g, "vp_thin_conv_fwd")) return VP_EINVAL;
@@ -804,23 +828,58 @@ static int thin_conv_fwd_impl(const VpConvGeom* g, const void* x, const float* w
         const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.n;
         if (total > 0x7fffffff) { set_error("vp_thin_conv_fwd: too many tiles"); return VP_EUNSUPPORTED; }
         p.total_tiles = (int)total;
-        CUtensorMap mA;
-        if (encode_box(&mA, x, g->ci, g->wi, g->hi, g->n, p.Wh, p.Hh)) { set_error("vp_thin_conv_fwd: cuTensorMapEncodeTiled failed"); return VP_EUNSUPPORTED; }
-        const int smem_bytes = kNSmemBase + p.kblocks * 4096;
-        static int attr_set = 0;
-        if (attr_set < smem_bytes) {
-            cudaError_t e = cudaFuncSetAttribute(thin_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-            if (e != cudaSuccess) { set_error("thin_n: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
-            attr_set = smem_bytes;
-        }
-        const int slots = num_sms() * (2 * smem_bytes <= 227 * 1024 ? 2 : 1);
-        const int grid = p.total_tiles < slots ? p.total_tiles : slots;
-        launch_k(thin_n_kernel, dim3(grid), dim3(kNThreads), smem_bytes, s, mA, p);
-        VP_CHECK_LAUNCH("thin_n");
-        return VP_OK;
+        return launch_thin_n(p, x, g->ci, g->wi, g->hi, g->n, s);
     }
     set_error("vp_thin_conv_fwd: shape not of a thin form (ci=%d co=%d k=%dx%d s=%d)", g->ci, g->co, g->kh, g->kw, g->stride);
     return VP_EUNSUPPORTED;
+}
+
+// the wide tensor A [N][H][W][C] (C = 64 * kblocks) of a thin_n problem -> tensor map, shared-memory attribute, launch
+static int launch_thin_n(const ThinNParams& p, const void* A, int C, int W, int H, int N, cudaStream_t s) {
+    CUtensorMap mA;
+    if (encode_box(&mA, A, C, W, H, N, p.Wh, p.Hh)) { set_error("thin_n: cuTensorMapEncodeTiled failed"); return VP_EUNSUPPORTED; }
+    const int smem_bytes = kNSmemBase + p.kblocks * 4096;
+    static int attr_set = 0;
+    if (attr_set < smem_bytes) {
+        cudaError_t e = cudaFuncSetAttribute(thin_n_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) { set_error("thin_n: cannot set %d bytes of dynamic smem: %s", smem_bytes, cudaGetErrorString(e)); return VP_ECUDA; }
+        attr_set = smem_bytes;
+    }
+    const int slots = num_sms() * (2 * smem_bytes <= 227 * 1024 ? 2 : 1);
+    const int grid = p.total_tiles < slots ? p.total_tiles : slots;
+    launch_k(thin_n_kernel, dim3(grid), dim3(kNThreads), smem_bytes, s, mA, p);
+    VP_CHECK_LAUNCH("thin_n");
+    return VP_OK;
+}
+
+/* dx [n][hi][wi][1] = dL/dx of a stride-1 nn.Conv2d with ONE INPUT channel (the VAE-GAN discriminator's first layer, whose input
+ * x_tilde needs a gradient: models/networks.py:159):  dx[p] = sum_t sum_co dy[p + pad - t][co] . w[co][0][t]  -- the thin-output
+ * forward kernel on dy with flipped taps.  co % 64 == 0 (the caller pads 32 -> 64), k <= 5, dx bf16 or fp32. */
+extern "C" int vp_thin_conv_dgrad_in1(const VpConvGeom* g, const void* dy, const float* w, void* dx, int out_dtype, void* stream) {
+    if (!thin_geom_ok(g, "vp_thin_conv_dgrad_in1")) return VP_EINVAL;
+    VP_CHECK_ARG(dy && w && dx, "vp_thin_conv_dgrad_in1: null pointer");
+    const int T = g->kh * g->kw;
+    if (!tc_available() || g->transposed || g->stride != 1 || g->ci != 1 || g->co % 64 != 0 || g->co > 64 * kNMaxKb || g->kh > 5 || g->kw > 5 ||
+        T > kMaxThinTaps || ((uintptr_t)dy & 15) != 0) {
+        set_error("vp_thin_conv_dgrad_in1: shape not served (ci=%d co=%d k=%dx%d s=%d)", g->ci, g->co, g->kh, g->kw, g->stride);
+        return VP_EUNSUPPORTED;
+    }
+    ThinNParams p;
+    memset(&p, 0, sizeof(p));
+    p.W = w; p.w_sc = 0; p.w_sk = T; p.w_st = 1;
+    p.bias = nullptr; p.D = dx; p.n = g->n; p.gh = g->hi; p.gw = g->wi; p.CT = 1; p.ntaps = T;
+    for (int ky = 0; ky < g->kh; ++ky)
+        for (int kx = 0; kx < g->kw; ++kx) {
+            const int t = ky * g->kw + kx;
+            p.ty[t] = (int8_t)(g->pad - ky); p.tx[t] = (int8_t)(g->pad - kx); p.widx[t] = (int8_t)t;
+        }
+    p.tymin = g->pad - (g->kh - 1); p.txmin = g->pad - (g->kw - 1); p.Hh = 16 + g->kh - 1; p.Wh = 8 + g->kw - 1;
+    p.kblocks = g->co / 64; p.act = VP_ACT_NONE; p.slope = 0.f; p.out_f32 = out_dtype == VP_F32;
+    p.tiles_w = (p.gw + 7) / 8; p.tiles_h = (p.gh + 15) / 16;
+    const int64_t total = (int64_t)p.tiles_w * p.tiles_h * p.n;
+    if (total > 0x7fffffff) { set_error("vp_thin_conv_dgrad_in1: too many tiles"); return VP_EUNSUPPORTED; }
+    p.total_tiles = (int)total;
+    return launch_thin_n(p, dy, g->co, g->wo, g->ho, g->n, (cudaStream_t)stream);
 }
 
 // dx = dL/dx of a stride-1 nn.Conv2d with ONE output channel:  dx[p][ci] = sum_t dy[p + pad - t] . w[0][ci][t]

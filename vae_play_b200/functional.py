@@ -341,6 +341,37 @@ class TapLayer:
         self._cache["padw"] = (key, wp)
         return wp
 
+    # padded copies of layer inputs made by a training-mode forward, for the weight gradient of the same call.  The ORIGINAL
+    # tensor is held too (autograd saves it anyway): while it lives its address cannot be handed to another tensor, so
+    # (address, version, shape) identifies it.  At most 4 pending entries per layer (REC + GAN passes, z + z_p).
+    def _remember_padded(self, x, xp):
+        pend = self._cache.setdefault("padded_inputs", [])
+        pend.append((x.data_ptr(), x._version, tuple(x.shape), x, xp))
+        if len(pend) > 4:
+            pend.pop(0)
+
+    def _recall_padded(self, x, cp):
+        pend = self._cache.get("padded_inputs")
+        if pend:
+            for i in range(len(pend) - 1, -1, -1):
+                e = pend[i]
+                if e[0] == x.data_ptr() and e[1] == x._version and e[2] == tuple(x.shape) and e[4].shape[-1] == cp:
+                    pend.pop(i)
+                    return e[4]
+        return None
+
+    def _padded_rows(self, weight, cop):
+        """fp32 weight [co][...] with zero rows appended up to cop (cached per weight version)."""
+        key = ("rows", cop)
+        hit = self._cache.get(key)
+        if hit is not None and hit[0] == weight.data_ptr() and hit[1] == weight._version and hit[3] == _EPOCH[0]:
+            return hit[2]
+        per = weight.numel() // weight.shape[0]
+        wq = hit[2] if hit is not None and hit[2].numel() == cop * per else torch.empty(cop * per, dtype=torch.float32, device=weight.device)
+        _lib.call("vp_pad_channels", _ptr(weight), weight.numel(), _ptr(wq), cop * per, 1, F32, _stream())     # one "row" of co*per values, zero tail
+        self._cache[key] = (weight.data_ptr(), weight._version, wq, _EPOCH[0])
+        return wq
+
     @staticmethod
     def _pad_act(x, cp):
         c = x.shape[-1]
@@ -401,6 +432,8 @@ class TapLayer:
             # the padded temporaries stay referenced until the call has been issued: a tensor dropped right after its pointer was
             # taken would hand its block to the NEXT allocation (the padded weight on a cache miss) before the kernel is queued
             xp, wp = self._pad_act(x, cip), self._padded_weight(weight)
+            if xp is not x and torch.is_grad_enabled() and weight.requires_grad:
+                self._remember_padded(x, xp)          # the weight gradient needs the same padded copy: keep it instead of padding again
             _lib.call("vp_conv_fwd_cl", C.byref(gp), _ptr(xp), _ptr(wp), _ptr(bp), _ptr(yp), _code(out_dtype), ACT[act], float(slope), _stream())
             if yp is not y:
                 _lib.call("vp_copy_channels", _ptr(yp), cop, 0, _ptr(y), self.cout, 0, self.cout, y.numel() // self.cout, _code(out_dtype), 0, _stream())
@@ -447,6 +480,16 @@ class TapLayer:
             _lib.call("vp_thin_conv_dgrad", C.byref(g), _ptr(dy), _ptr(weight), _ptr(dx), _code(out_dtype), _stream())
         elif self._cl(dt, weight):
             _lib.call("vp_conv_dgrad_cl", C.byref(g), _ptr(dy), _ptr(self._shadow(weight)), _ptr(dx), _code(out_dtype), _stream())
+        elif (self.kind == "conv" and self.cin == 1 and self.stride == 1 and self.k <= 5 and dt == torch.bfloat16 and weight.is_contiguous()
+              and _STATE["engine"] != _lib.ENGINE_SIMT and self._up64(self.cout) <= 256):
+            # gradient w.r.t. a single-channel input (the discriminator's first layer on x_tilde): the thin-output forward kernel on dy
+            # with flipped taps; a 32-channel dy is zero-padded to 64 (its weight rows beyond cout are never read: K blocks of 64
+            # channels, the padding channels of dy are zero and meet whatever the weight tile holds -- so pad the weight view too)
+            cop = self._up64(self.cout)
+            gp = self._geom(n, h, w, 1, dy.shape[1], dy.shape[2], cop, self.k, self.stride, self.pad, 0)
+            dyp = self._pad_act(dy, cop)
+            wq = weight if cop == self.cout else self._padded_rows(weight, cop)
+            _lib.call("vp_thin_conv_dgrad_in1", C.byref(gp), _ptr(dyp), _ptr(wq), _ptr(dx), _code(out_dtype), _stream())
         elif self._padded(dt, weight):
             cip, cop = self._up64(self.cin), self._up64(self.cout)
             gp = self._padded_geom(n, h, w, dy.shape[1], dy.shape[2])
@@ -514,7 +557,8 @@ class TapLayer:
             gp = self._padded_geom(n, h, w, dy.shape[1], dy.shape[2])
             d0, d1, taps, s0, s1, st, d0p, d1p = self._pad_dims(weight)
             dwp = torch.empty(d0p * taps * d1p, dtype=torch.float32, device=x.device)
-            xp, dyp = self._pad_act(x, cip), self._pad_act(dy, cop)
+            xp = self._recall_padded(x, cip)
+            xp, dyp = (xp if xp is not None else self._pad_act(x, cip)), self._pad_act(dy, cop)
             _lib.call("vp_conv_wgrad_cl", C.byref(gp), _ptr(xp), _ptr(dyp), _ptr(dwp), 0, _stream())
             dw, _ = _grad_target(weight)
             _lib.call("vp_unpad_wgrad_cl", _ptr(dwp), _ptr(dw), d0, d1, taps, s0, s1, st, d1p, _stream())
