@@ -6,9 +6,45 @@
 namespace vp {
 namespace {
 
-// out[r] = 0.5 * sum_j (a[r,j] - b[r,j])^2   (one warp per row)          networks.py:273
+// out[r] += 0.5 * sum_j (a[r,j] - b[r,j])^2 over the column slice of this CTA (grid = splits x rows; out zeroed by the caller: a
+// batch of 64 rows x 65 536 features must not be left to 64 warps)                                                     networks.py:273
 __global__ void __launch_bounds__(256) feat_mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t rows,
                                                            int64_t cols) {
+    pdl_sync();
+    __shared__ float part[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t r = blockIdx.y;
+    const int64_t chunk = ((cols + gridDim.x - 1) / gridDim.x + 3) & ~(int64_t)3;
+    const int64_t c0 = (int64_t)blockIdx.x * chunk, c1 = c0 + chunk < cols ? c0 + chunk : cols;
+    const float* pa = a + r * cols;
+    const float* pb = b + r * cols;
+    float s = 0.f;
+    int64_t j0 = c0;
+    if (c0 < c1 && (((uintptr_t)(pa + c0) | (uintptr_t)(pb + c0)) & 15) == 0) {
+        const int64_t n4 = (c1 - c0) / 4;
+        const float4* a4 = reinterpret_cast<const float4*>(pa + c0);
+        const float4* b4 = reinterpret_cast<const float4*>(pb + c0);
+#pragma unroll 4
+        for (int64_t j = threadIdx.x; j < n4; j += 256) {
+            const float4 x = a4[j], y = b4[j];
+            const float d0 = x.x - y.x, d1 = x.y - y.y, d2 = x.z - y.z, d3 = x.w - y.w;
+            s = fmaf(d0, d0, s); s = fmaf(d1, d1, s); s = fmaf(d2, d2, s); s = fmaf(d3, d3, s);
+        }
+        j0 = c0 + n4 * 4;
+    }
+    for (int64_t j = j0 + threadIdx.x; j < c1; j += 256) { const float d = pa[j] - pb[j]; s = fmaf(d, d, s); }
+    s = warp_sum(s);
+    if (lane == 0) part[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < 8 ? part[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0 && c0 < c1) atomicAdd(out + r, 0.5f * t);
+    }
+}
+// many short rows: one warp per row
+__global__ void __launch_bounds__(256) feat_mse_rows_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t rows,
+                                                            int64_t cols) {
     pdl_sync();
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -118,7 +154,18 @@ using namespace vp;
 
 extern "C" int vp_feature_mse_fwd(const float* a, const float* b, float* out, int64_t rows, int64_t cols, void* stream) {
     VP_CHECK_ARG(a && b && out && rows > 0 && cols > 0, "vp_feature_mse_fwd: bad arguments");
-    launch_k(feat_mse_fwd_kernel, dim3(grid_for(rows * 32)), dim3(256), 0, (cudaStream_t)stream, a, b, out, rows, cols);
+    if (cols < 4096 || rows > 65535) {
+        launch_k(feat_mse_rows_kernel, dim3(grid_for(rows * 32)), dim3(256), 0, (cudaStream_t)stream, a, b, out, rows, cols);
+        VP_CHECK_LAUNCH("vp_feature_mse_fwd");
+        return VP_OK;
+    }
+    // long rows (a batch of 64 x 65 536 discriminator features): ~8192 elements per CTA, at most ~8 CTAs per SM in total
+    int64_t splits = (cols + 8191) / 8192;
+    const int64_t cap = (8 * (int64_t)num_sms() + rows - 1) / rows;
+    splits = splits > cap ? cap : splits;
+    splits = splits < 1 ? 1 : splits;
+    zero_async(out, sizeof(float) * (size_t)rows, (cudaStream_t)stream);
+    launch_k(feat_mse_fwd_kernel, dim3((unsigned)splits, (unsigned)rows), dim3(256), 0, (cudaStream_t)stream, a, b, out, rows, cols);
     VP_CHECK_LAUNCH("vp_feature_mse_fwd");
     return VP_OK;
 }

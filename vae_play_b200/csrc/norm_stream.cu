@@ -293,7 +293,12 @@ int norm_stream(int mode, int dtype, const void* x, const void* da, void* out, c
     const int64_t row_bytes = (int64_t)c * es;
     if (c % VMAX != 0 || c / 4 > 256 || row_bytes > 2048 || rows * row_bytes < (1 << 20)) return VP_EUNSUPPORTED;
     if (((uintptr_t)x & 15) || ((uintptr_t)da & 15) || ((uintptr_t)out & 15)) return VP_EUNSUPPORTED;
-    if ((mode == M_BWD_REDUCE || mode == M_BWD_APPLY) && (act & 16)) return VP_EUNSUPPORTED;
+    if (act & 16) {
+        // "derivative from the OUTPUT" (a plain activation backward, no norm): for ReLU the output's sign is the pre-activation's,
+        // so the reduce pass with scale = 1, shift = 0 is exactly dy = da * (a > 0), sums[0:C] = column sums of dy
+        if (mode != M_BWD_REDUCE || (act & 15) != VP_ACT_RELU || mean || scale || !out) return VP_EUNSUPPORTED;
+        act = VP_ACT_RELU;
+    }
     StreamArgs a;
     a.x = x; a.da = da; a.out = out; a.mean = mean; a.invstd = invstd; a.scale = scale; a.shift = shift; a.sums = sums;
     a.dgamma = dgamma; a.dbeta = dbeta; a.rows = rows; a.C = c; a.act = act; a.slope = slope;
