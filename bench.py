@@ -626,6 +626,12 @@ def run_ours(args):
         except Exception as e:       # an extra must not take the headline line down with it
             extra["vaegan128"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         torch.cuda.empty_cache()
+        # ---- config 5: one train_Style_GAN.py iteration at 256x256 ---------------------------------------------------------------
+        try:
+            extra["style256"] = style_bench(args, dev)
+        except Exception as e:
+            extra["style256"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
         line["extra"] = extra
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
@@ -773,6 +779,98 @@ def vaegan_bench(args, dev, peaks, img=128, B=64):
            "note": "FLOPs = 3 x forward MACs x 2 (an upper bound: first-layer data gradients are not computed)"}
     VF.set_grad_sinks({})
     return out
+
+
+def style_bench(args, dev, img=256, B=8, Z=64, ncls=3):
+    """Config 5 of BASELINE.json: one train_random_gan iteration of train_Style_GAN.py (StyleEncoder + Generator with the
+    label-gated dual convolutions + two-headed Discriminator, three Adam optimisers, three backward passes) at 256x256 RGB,
+    launched from Python (no graph: the step interleaves optimiser steps with backward passes through retained graphs)."""
+    import torch
+
+    import vae_play_b200.functional as VF
+    from vae_play_b200 import _lib
+    from vae_play_b200 import train_steps as TS
+    from vae_play_b200.models import network_Style_GAN as S
+    from vae_play_b200.optim import FusedAdam
+    torch.manual_seed(0)
+    VF.set_async_wgrad(False)
+    VF.set_grad_sinks({})
+    G, E, D = S.Generator(img, Z).to(dev).train(), S.StyleEncoder(Z, img).to(dev).train(), S.Discriminator(img, ncls).to(dev).train()
+    g_opt, e_opt, d_opt = (FusedAdam(list(m.parameters()), lr=1e-4, capturable=True) for m in (G, E, D))
+    xt, xc = torch.rand(B, 3, img, img, device=dev), torch.rand(B, 3, img, img, device=dev)
+    y = torch.randint(0, ncls, (B,), device=dev)
+    eps, sz = torch.randn(B, Z, device=dev), torch.randn(B, Z, device=dev)
+    simt0 = _lib.simt_bf16_count()
+
+    def eager():
+        return TS.style_gan_step(G, E, D, g_opt, e_opt, d_opt, xt, xc, y, eps, sz)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            eager()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    # the whole iteration -- three forward / backward groups with the three Adam steps in between -- as ONE CUDA graph: launched
+    # from Python it is host-bound (2 300 launches ~ 57 ms per step at any image size)
+    graphed = False
+    step = eager
+    try:
+        VF.invalidate_caches()
+        for o in (g_opt, e_opt, d_opt):
+            o.zero_grad(set_to_none=True)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            static_losses = eager()
+
+        def step():            # noqa: F811
+            g.replay()
+            return static_losses
+        step()
+        torch.cuda.synchronize()
+        graphed = True
+    except Exception as e:     # fall back to Python launches, say so in the line
+        graph_error = f"{type(e).__name__}: {e}"[:200]
+        step = eager
+        torch.cuda.synchronize()
+    if os.environ.get("VP_PROFILE_STYLE"):       # diagnostic: per-kernel device time of this iteration -> stderr
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+        rows = sorted(((e.device_time_total / 2, e.count / 2, e.key) for e in prof.key_averages() if e.device_time_total), reverse=True)
+        tot = sum(r[0] for r in rows)
+        print(f"[style{img} profile] {tot:.0f} us of kernels per step in {sum(r[1] for r in rows):.0f} launches", file=sys.stderr)
+        for t, c, k in rows[:45]:
+            print(f"[style{img} profile] {t:9.1f} us {100 * t / tot:5.1f}%  n={c:6.1f}  {k.replace('void ', '').replace('vp::', '').replace('(anonymous namespace)::', '')[:120]}", file=sys.stderr)
+    l0 = _lib.launch_count()
+    steps = max(3, min(args.steps, 10))
+    regs = []
+    for _ in range(max(1, min(args.repeats, 3))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            losses = step()
+        e1.record()
+        torch.cuda.synchronize()
+        regs.append(e0.elapsed_time(e1) / steps)
+    launches = (_lib.launch_count() - l0) / (steps * len(regs))
+    if graphed:
+        c0 = _lib.launch_count()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        launches = _lib.launch_count() - c0        # graph replays do not pass through the library's counter: one eager iteration does
+    ms = statistics.median(regs)
+    nparams = sum(p.numel() for m in (G, E, D) for p in m.parameters())
+    return {"workload": f"train_Style_GAN.py train_random_gan iteration: StyleEncoder + Generator({img}) + Discriminator, 3 x Adam, {img}x{img}x3, batch {B}, "
+                        + ("one CUDA graph per iteration" if graphed else f"launched from Python (graph capture failed: {graph_error})"),
+            "value": round(B / ms * 1e3, 1), "unit": "images/s", "ms_per_step": round(ms, 3), "gpu_launches_per_step": int(launches),
+            "bf16_contractions_on_cuda_cores": int(_lib.simt_bf16_count() - simt0), "parameters": int(nparams),
+            "losses": {k: round(float(v), 5) for k, v in losses.items()}}
 
 
 def gpu_library_baseline(img, cin, B, dev, steps):

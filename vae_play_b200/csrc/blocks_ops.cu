@@ -4,6 +4,7 @@
 // attention block, dice on probabilities and the depthwise edge filter.  All HBM-bound: coalesced along the channel axis,
 // one pass each, launched with programmatic dependent launch like every other kernel of the library.
 #include "common.cuh"
+namespace vp { void* splitk_workspace(size_t bytes); }     // tapgemm_tc.cu: the registered scratch buffer, or null when too small
 
 namespace vp {
 namespace {
@@ -144,6 +145,41 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const T* __restrict__ 
         for (int yy = y0; yy < y1; ++yy)
             for (int xx = x0; xx < x1; ++xx) acc += Cvt<T>::ld(x + ((img * h + yy) * w + xx) * c + ch);
         Cvt<T>::st(y + bin * c + ch, acc * inv);
+    }
+}
+// large bins (global pooling of a 256 x 256 map = 65 536 pixels per bin): the rows of a bin are split over gridDim.y CTAs, threads
+// cover (pixel lane, channel), partial sums are added into an fp32 scratch [bins][c]; avgpool_finish_kernel scales and converts.
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_split_kernel(const T* __restrict__ x, float* __restrict__ acc, int h, int w, int c, int oh, int ow) {
+    pdl_sync();
+    const int64_t bin = blockIdx.x;
+    const int bx = (int)(bin % ow), by = (int)((bin / ow) % oh);
+    const int64_t img = bin / ((int64_t)ow * oh);
+    const int y0 = (by * h) / oh, y1 = ((by + 1) * h + oh - 1) / oh, x0 = (bx * w) / ow, x1 = ((bx + 1) * w + ow - 1) / ow;
+    const int rows = y1 - y0, rps = (rows + gridDim.y - 1) / gridDim.y;
+    const int ya = y0 + blockIdx.y * rps, yb = min(ya + rps, y1);
+    const int lanes = c <= 256 ? 256 / c : 1, wb = x1 - x0;
+    const int lane = threadIdx.x / c;
+    if (c <= 256 && lane >= lanes) return;
+    for (int ch = c <= 256 ? (int)(threadIdx.x % c) : (int)threadIdx.x; ch < c; ch += 256) {
+        float a = 0.f;
+        const int64_t npix = (int64_t)(yb > ya ? yb - ya : 0) * wb;
+        for (int64_t p = (c <= 256 ? lane : 0); p < npix; p += lanes) {
+            const int yy = ya + (int)(p / wb), xx = x0 + (int)(p % wb);
+            a += Cvt<T>::ld(x + ((img * h + yy) * w + xx) * c + ch);
+        }
+        if (npix > 0) atomicAdd(acc + bin * c + ch, a);
+        if (c <= 256) break;
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_finish_kernel(const float* __restrict__ acc, T* __restrict__ y, int64_t total, int h, int w, int c, int oh, int ow) {
+    pdl_sync();
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bin = i / c;
+        const int bx = (int)(bin % ow), by = (int)((bin / ow) % oh);
+        const int y0 = (by * h) / oh, y1 = ((by + 1) * h + oh - 1) / oh, x0 = (bx * w) / ow, x1 = ((bx + 1) * w + ow - 1) / ow;
+        Cvt<T>::st(y + i, acc[i] / (float)((y1 - y0) * (x1 - x0)));
     }
 }
 template <typename T>
@@ -489,6 +525,26 @@ extern "C" int vp_avgpool_fwd(const void* x, void* y, int dtype, int64_t n, int 
     VP_CHECK_ARG(n * oh * ow < 0x7fffffff, "vp_avgpool_fwd: too many bins");
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned g = (unsigned)(n * oh * ow);
+    const int64_t bin_pix = (int64_t)((h + oh - 1) / oh) * ((w + ow - 1) / ow);
+    if (bin_pix >= 2048 && (int64_t)g * 4 < 148 * 8) {
+        // few, large bins: split each bin's rows over enough CTAs to fill the GPU (fp32 scratch from the library workspace)
+        const size_t bytes = sizeof(float) * (size_t)g * c;
+        float* acc = (float*)vp::splitk_workspace(bytes);
+        if (acc) {
+            int splits = (148 * 8 + (int)g - 1) / (int)g;
+            const int rows = (h + oh - 1) / oh;
+            splits = splits > rows ? rows : splits;
+            zero_async(acc, bytes, s);
+            VP_DISPATCH_T(dtype, launch_k(avgpool_split_kernel<float>, dim3(g, (unsigned)splits), dim3(256), 0, s, (const float*)x, acc, h, w, c, oh, ow),
+                          launch_k(avgpool_split_kernel<bf16>, dim3(g, (unsigned)splits), dim3(256), 0, s, (const bf16*)x, acc, h, w, c, oh, ow));
+            VP_CHECK_LAUNCH("vp_avgpool_fwd");
+            const int64_t total = (int64_t)g * c;
+            VP_DISPATCH_T(dtype, launch_k(avgpool_finish_kernel<float>, dim3(grid_for(total)), dim3(256), 0, s, (const float*)acc, (float*)y, total, h, w, c, oh, ow),
+                          launch_k(avgpool_finish_kernel<bf16>, dim3(grid_for(total)), dim3(256), 0, s, (const float*)acc, (bf16*)y, total, h, w, c, oh, ow));
+            VP_CHECK_LAUNCH("vp_avgpool_fwd");
+            return VP_OK;
+        }
+    }
     VP_DISPATCH_T(dtype, launch_k(avgpool_fwd_kernel<float>, dim3(g), dim3(256), 0, s, (const float*)x, (float*)y, n, h, w, c, oh, ow),
                   launch_k(avgpool_fwd_kernel<bf16>, dim3(g), dim3(256), 0, s, (const bf16*)x, (bf16*)y, n, h, w, c, oh, ow));
     VP_CHECK_LAUNCH("vp_avgpool_fwd");

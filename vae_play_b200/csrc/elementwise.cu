@@ -304,6 +304,25 @@ __global__ void __launch_bounds__(256) pad_channels16_kernel(const uint4* __rest
         dst[i] = j < c8 ? src[r * c8 + j] : make_uint4(0u, 0u, 0u, 0u);
     }
 }
+// bf16, any c, cp % 8 == 0 (RGB 3 -> 64): one 16-byte OUTPUT chunk per thread, its up-to-8 source elements gathered one by one
+__global__ void __launch_bounds__(256) pad_channels_out16_kernel(const bf16* __restrict__ src, int c, uint4* __restrict__ dst, int cp8, int64_t rows) {
+    pdl_sync();
+    const int64_t total = rows * cp8;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cp8;
+        const int j0 = (int)(i - r * cp8) * 8;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (j0 < c) {
+            const bf16* sp = src + r * c + j0;
+            unsigned short e[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) e[k] = (j0 + k < c) ? __bfloat16_as_ushort(sp[k]) : (unsigned short)0;
+            o = make_uint4((uint32_t)e[0] | ((uint32_t)e[1] << 16), (uint32_t)e[2] | ((uint32_t)e[3] << 16), (uint32_t)e[4] | ((uint32_t)e[5] << 16),
+                           (uint32_t)e[6] | ((uint32_t)e[7] << 16));
+        }
+        dst[i] = o;
+    }
+}
 // weight [d0][d1][taps] with element strides (s0, s1, st)  ->  bf16 [d0p][taps][d1p] (channels-last element order), zero padded
 __global__ void __launch_bounds__(256) pad_weight_cl_kernel(const float* __restrict__ w, bf16* __restrict__ dst, int d0, int d1, int taps, int64_t s0,
                                                             int64_t s1, int64_t st, int d0p, int d1p) {
@@ -582,6 +601,11 @@ extern "C" int vp_pad_channels(const void* src, int c, void* dst, int cp, int64_
         VP_CHECK_LAUNCH("vp_pad_channels");
         return VP_OK;
     }
+    if (dtype == VP_BF16 && cp % 8 == 0 && ((uintptr_t)dst & 15) == 0) {
+        launch_k(pad_channels_out16_kernel, dim3(grid_for(rows * (cp / 8))), dim3(256), 0, (cudaStream_t)stream, (const bf16*)src, c, (uint4*)dst, cp / 8, rows);
+        VP_CHECK_LAUNCH("vp_pad_channels");
+        return VP_OK;
+    }
     if (dtype == VP_F32) launch_k(pad_channels_kernel<float>, dim3(grid_for(rows * cp)), dim3(256), 0, (cudaStream_t)stream, (const float*)src, c, (float*)dst, cp, rows);
     else launch_k(pad_channels_kernel<bf16>, dim3(grid_for(rows * cp)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)src, c, (bf16*)dst, cp, rows);
     VP_CHECK_LAUNCH("vp_pad_channels");
@@ -803,11 +827,14 @@ struct AdamTable {
     float* v[kOptMax];
     bf16* sh[kOptMax];
     int64_t n[kOptMax];
+    int blk0[kOptMax + 1];      // tensor i is served by the CTAs [blk0[i], blk0[i+1]) of a flat grid (as rmsprop_kernel)
 };
-__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable t, float lr, float b1, float b2, float eps, float wd, int64_t step,
-                                                   const unsigned long long* __restrict__ step_dev, int zero_g) {
+__global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamTable t, int ntensors, float lr, float b1, float b2, float eps, float wd,
+                                                   int64_t step, const unsigned long long* __restrict__ step_dev, int zero_g) {
     pdl_wait();     // no early trigger (see rmsprop_kernel)
-    const int ti = blockIdx.y;
+    int ti = 0;
+    while (ti + 1 < ntensors && (int)blockIdx.x >= t.blk0[ti + 1]) ++ti;
+    const int bid = blockIdx.x - t.blk0[ti], nblk = t.blk0[ti + 1] - t.blk0[ti];
     float* __restrict__ p = t.p[ti];
     float* __restrict__ g = const_cast<float*>(t.g[ti]);
     float* __restrict__ m = t.m[ti];
@@ -817,7 +844,29 @@ __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamT
     const double tt = (double)(step_dev ? (int64_t)*step_dev : step);
     const float bc1 = (float)(1.0 - pow((double)b1, tt)), bc2s = (float)sqrt(1.0 - pow((double)b2, tt));
     const float step_size = lr / bc1;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t stride = (int64_t)nblk * blockDim.x;
+    const int64_t n4 = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0 && ((uintptr_t)sh & 7) == 0) ? n / 4 : 0;
+    for (int64_t i = (int64_t)bid * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 p4 = reinterpret_cast<float4*>(p)[i], g4 = reinterpret_cast<float4*>(g)[i];
+        const float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        float pe[4] = {p4.x, p4.y, p4.z, p4.w}, ge[4] = {g4.x, g4.y, g4.z, g4.w}, me[4] = {m4.x, m4.y, m4.z, m4.w}, ve[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gg = ge[j] + wd * pe[j];
+            me[j] = b1 * me[j] + (1.f - b1) * gg;
+            ve[j] = b2 * ve[j] + (1.f - b2) * gg * gg;
+            pe[j] = pe[j] - step_size * (me[j] / (sqrtf(ve[j]) / bc2s + eps));
+        }
+        reinterpret_cast<float4*>(m)[i] = make_float4(me[0], me[1], me[2], me[3]);
+        reinterpret_cast<float4*>(v)[i] = make_float4(ve[0], ve[1], ve[2], ve[3]);
+        reinterpret_cast<float4*>(p)[i] = make_float4(pe[0], pe[1], pe[2], pe[3]);
+        if (zero_g) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (sh) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(pe[0], pe[1]), h1 = __floats2bfloat162_rn(pe[2], pe[3]);
+            reinterpret_cast<uint2*>(sh)[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        }
+    }
+    for (int64_t i = n4 * 4 + (int64_t)bid * blockDim.x + threadIdx.x; i < n; i += stride) {
         const float pv = p[i];
         const float gg = g[i] + wd * pv;
         const float mn = b1 * m[i] + (1.f - b1) * gg;
@@ -842,18 +891,20 @@ extern "C" int vp_adam_step(void* const* params, void* const* grads, void* const
     for (int base = 0; base < count; base += kOptMax) {
         AdamTable t;
         const int mcount = count - base < kOptMax ? count - base : kOptMax;
-        int64_t nmax = 0;
+        const int cap = 2 * num_sms();
+        int total = 0;
         for (int i = 0; i < mcount; ++i) {
             t.p[i] = (float*)params[base + i]; t.g[i] = (const float*)grads[base + i];
             t.m[i] = (float*)exp_avg[base + i]; t.v[i] = (float*)exp_avg_sq[base + i];
             t.sh[i] = shadows ? (bf16*)shadows[base + i] : nullptr;
             t.n[i] = numel[base + i];
-            nmax = numel[base + i] > nmax ? numel[base + i] : nmax;
+            int64_t nb = (numel[base + i] / 4 + 1023) / 1024;
+            nb = nb < 1 ? 1 : (nb > cap ? cap : nb);
+            t.blk0[i] = total;
+            total += (int)nb;
         }
-        int64_t bx = (nmax + 1023) / 1024;
-        if (bx > 148 * 2) bx = 148 * 2;
-        if (bx < 1) bx = 1;
-        launch_k(adam_kernel, dim3((unsigned)bx, (unsigned)mcount), dim3(256), 0, (cudaStream_t)stream, t, lr, beta1, beta2, eps, weight_decay, step,
+        t.blk0[mcount] = total;
+        launch_k(adam_kernel, dim3((unsigned)total), dim3(256), 0, (cudaStream_t)stream, t, mcount, lr, beta1, beta2, eps, weight_decay, step,
                  (const unsigned long long*)step_dev, zero_grads);
         VP_CHECK_LAUNCH("vp_adam_step");
     }
