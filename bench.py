@@ -685,7 +685,7 @@ def vaegan_bench(args, dev, peaks, img=128, B=64):
     from vae_play_b200.models.networks import VaeGan
     from vae_play_b200.optim import FusedRMSprop
     torch.manual_seed(0)
-    VF.set_async_wgrad(False)       # the decoder / discriminator weights are used two and three times per backward: autograd adds on the main stream
+    VF.set_async_wgrad(not args.no_async_wgrad)       # re-used weights (decoder x2, discriminator x2): later uses are added on the side stream too
     net = VaeGan(img, 128).to(dev).train()
     groups = [net.encoder, net.decoder, net.discriminator, net.param_encoder]             # train.py:136-140
     opts = [FusedRMSprop(list(m.parameters()), lr=1e-4, zero_grads=True) for m in groups]

@@ -308,3 +308,59 @@ def test_fused_single_backward_equals_five_backward(vp):
             assert r < FLIP_BOUND, f"{k}: fused-mode deviation from the float64 truth {r:.3e} (reference fp32: {dev[k]:.2e})"
     finally:
         vp.set_precision("bf16")
+
+
+def test_async_wgrad_with_reused_weights(vp):
+    """functional.set_async_wgrad on the full VAE-GAN step: the decoder runs on z and z_p and the discriminator in REC and GAN
+    mode, so their weights receive two gradients per backward -- the first into the persistent slot on the side stream, the
+    later ones into scratch buffers that are added to the slot on the same stream (autograd sees None for them).  ONE forward,
+    backward with the side stream off / off / on / on: the same gradients up to the run-to-run noise of the main-stream path."""
+    import vae_play_b200.functional as VF
+    import vae_play_b200.functional_blocks as VB
+    from vae_play_b200 import train_steps as TS
+    from vae_play_b200.models.networks import VaeGan
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    VF.set_fuse_bn_backward(False)          # bit-comparable backward passes
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    try:
+        with torch.cuda.stream(side):
+            torch.manual_seed(5)
+            net = VaeGan(64, 128).cuda().train()
+            params = list(net.parameters())
+            flat = VF.persistent_grads(params)
+            x, targets = torch.rand(8, 1, 64, 64, device="cuda"), torch.rand(8, 3, device="cuda")
+            eps, z_p = torch.randn(8, 128, device="cuda"), torch.randn(8, 128, device="cuda")
+            losses, parts = TS.vaegan_losses(net, x, targets, eps=eps, z_p=z_p)
+            lam = TS.LAMBDA_MSE
+            total = VB.weighted_sums([parts["recon"], parts["l1"], parts["kl"], parts["mse"], parts["bce_o"], parts["bce_p"], parts["bce_s"]],
+                                     [1.0, 1.0, 1.0, 1.0 + lam, lam, lam, lam])
+            res = []
+            for on in (False, False, True, True):
+                VF.set_async_wgrad(on)
+                for p in params:
+                    p.grad = None
+                flat.zero_()
+                for e in VF._GRAD_SINKS.values():
+                    e[3], e[4] = True, False
+                total.backward(retain_graph=True)
+                VF.join_async()
+                torch.cuda.synchronize()
+                res.append([p.grad.detach().double().cpu().numpy() if p.grad is not None else None for p in params])
+        names = [k for k, _ in net.named_parameters()]
+        # split-K data gradients (fp32 red.add in arrival order) followed by bf16 storage make even two identical backward passes
+        # differ by a few flipped roundings: the side stream must stay within a small multiple of that run-to-run noise
+        for k, a, a2, b, c in zip(names, *res):
+            if a is None:
+                assert a2 is None and b is None and c is None, k
+                continue
+            nrm = np.sqrt((a * a).sum()) + 1e-30
+            noise = np.sqrt(((a2 - a) ** 2).sum()) / nrm
+            for other in (b, c):
+                d = np.sqrt(((other - a) ** 2).sum()) / nrm
+                assert d < max(1e-5, 4 * noise), f"{k}: async vs sync {d:.3e}, sync vs sync {noise:.3e}"
+    finally:
+        VF.set_async_wgrad(False)
+        VF.set_fuse_bn_backward(True)
+        VF.set_grad_sinks({})

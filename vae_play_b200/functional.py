@@ -114,16 +114,15 @@ def set_fuse_bn_backward(on: bool, thin: bool = False):
     _STATE["fuse_bn_bwd_thin"] = bool(on) and bool(thin)
 
 
-_ASYNC = {"on": False, "stream": None, "pending": [], "forked": False, "home": None}
+_ASYNC = {"on": False, "stream": None, "pending": [], "forked": False, "home": None, "slots": set()}
 
 
 def set_async_wgrad(on: bool):
     """Weight gradients of the fused layers on a side stream, concurrent with the rest of the backward pass (the tensor-bound
     weight-gradient kernel of block L overlaps the bandwidth-bound BatchNorm-backward passes of block L-1).  Only gradients that
     go straight into a persistent slot (``persistent_grads`` / data-parallel buckets) take the side stream: nothing on the main
-    stream touches them until the optimiser -- PROVIDED every weight is used once per backward (the VAE step; not the VAE-GAN
-    step, whose decoder / discriminator weights receive several gradients that autograd sums on the main stream).  The caller
-    MUST call ``join_async()`` after ``backward()`` -- inside the same
+    stream touches them until the optimiser.  A weight used several times per backward (the VAE-GAN step) gets its later
+    contributions added into the slot on the side stream as well (``_async_fork``).  The caller MUST call ``join_async()`` after ``backward()`` -- inside the same
     CUDA-graph capture when capturing; the fused optimisers and ``GradBuckets`` also join before they read gradients."""
     _ASYNC["on"] = bool(on)
     if not on:
@@ -131,19 +130,46 @@ def set_async_wgrad(on: bool):
 
 
 def _async_fork(weight):
-    """An event on the current stream if this weight's gradient may be computed on the side stream, else None."""
+    """(event on the current stream, again) if this weight's gradient may be computed on the side stream, else None.
+    ``again``: the weight's slot was already handed to an earlier use in this backward whose kernel runs on the side stream
+    (the decoder on z and z_p, the discriminator in REC and GAN mode): this use is computed into a scratch buffer on the side
+    stream and ADDED into the slot there -- in stream order behind the first use -- and autograd is told nothing (None)."""
     if not _ASYNC["on"]:
         return None
-    hit = _GRAD_SINKS.get(weight.data_ptr())
-    if hit is None or hit[2].grad is not None or hit[4] or hit[2].shape != weight.shape or hit[2].stride() != weight.stride():
-        return None            # no slot, or the slot is taken: autograd will add on the main stream
+    ptr = weight.data_ptr()
+    hit = _GRAD_SINKS.get(ptr)
+    if hit is None or hit[2].shape != weight.shape or hit[2].stride() != weight.stride():
+        return None
+    again = ptr in _ASYNC["slots"]
+    if not again and (hit[2].grad is not None or hit[4]):
+        return None            # the slot is taken by a gradient that lives on the main stream: autograd will add there
     if _ASYNC["stream"] is None or _ASYNC["stream"].device != weight.device:
         _ASYNC["stream"] = torch.cuda.Stream(weight.device)
     ev = torch.cuda.Event()
     _ASYNC["home"] = torch.cuda.current_stream(weight.device)
     ev.record(_ASYNC["home"])
     _ASYNC["forked"] = True
-    return ev
+    _ASYNC["slots"].add(ptr)
+    return ev, again
+
+
+def _wgrad_maybe_async(layer, x, dy, weight, fork):
+    if fork is None:
+        return layer.wgrad(x, dy, weight)
+    ev, again = fork
+    side = _ASYNC["stream"]
+    with torch.cuda.stream(side):
+        side.wait_event(ev)
+        dw = layer.wgrad(x, dy, weight)          # first use: written into the slot; later uses: a scratch buffer (the slot is taken)
+        if again:
+            flat, off = _GRAD_SINKS[weight.data_ptr()][0], _GRAD_SINKS[weight.data_ptr()][1]
+            if dw.data_ptr() == flat.data_ptr() + 4 * off:
+                raise _lib.VaePlayError("async weight gradient: a re-used weight was handed its slot twice")
+            _lib.call("vp_axpy", 1.0, _ptr(dw), C.c_void_p(flat.data_ptr() + 4 * off), dw.numel(), _stream())
+            _ASYNC["pending"].append((x, dy, dw))
+            return None
+    _ASYNC["pending"].append((x, dy))            # keep the operands allocated until join_async()
+    return dw
 
 
 def join_async():
@@ -159,6 +185,7 @@ def join_async():
     if cur is None or _ASYNC.get("home") is None or cur == _ASYNC["home"]:
         _ASYNC["forked"] = False
         _ASYNC["pending"].clear()
+        _ASYNC["slots"].clear()
 
 
 def set_pad_route(on: bool):
@@ -722,8 +749,9 @@ class _FusedLayerFn(torch.autograd.Function):
             if da is None:
                 # only the pre-norm output was used (Discriminator 'REC' mode, networks.py:180-185)
                 dy = dy_extra.contiguous()
-                dw = layer.wgrad(x, dy, weight)
+                fork = _async_fork(weight)
                 dx = layer.dgrad(dy, weight, ctx.x_shape) if ctx.needs_input_grad[0] else None
+                dw = _wgrad_maybe_async(layer, x, dy, weight, fork)
                 return dx, dw, None, None, None, None, None, None, None, None, None, None, None, None
             da = da.contiguous()
             dy = torch.empty_like(y)
@@ -769,15 +797,9 @@ class _FusedLayerFn(torch.autograd.Function):
                 prev["pre"] = (dx.data_ptr(), dx._version, parts, nparts)
             else:
                 dx = layer.dgrad(dy, weight, ctx.x_shape)
-        if fork is None:
-            dw = layer.wgrad(x, dy, weight)
-        else:
-            # launched AFTER the data gradient (the critical path keeps the SMs first), on the side stream: it runs next to the
-            # bandwidth-bound BatchNorm-backward passes of the block below
-            with torch.cuda.stream(_ASYNC["stream"]):
-                _ASYNC["stream"].wait_event(fork)
-                dw = layer.wgrad(x, dy, weight)
-            _ASYNC["pending"].append((x, dy))        # keep the operands allocated until join_async()
+        # launched AFTER the data gradient (the critical path keeps the SMs first); on the side stream it runs next to the
+        # bandwidth-bound BatchNorm-backward passes of the block below
+        dw = _wgrad_maybe_async(layer, x, dy, weight, fork)
         return dx, dw, dbias, dgamma, dbeta, None, None, None, None, None, None, None, None, None
 
 

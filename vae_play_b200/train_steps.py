@@ -50,11 +50,13 @@ def vaegan_backward(losses, parts, fused=True, lambda_mse=LAMBDA_MSE):
         losses["loss_decoder"].backward(retain_graph=True)
         losses["loss_discriminator"].backward(retain_graph=True)
         losses["loss_aux"].backward()
+        VF.join_async()
         return None
     lam = float(lambda_mse)
     total = VB.weighted_sums([parts["recon"], parts["l1"], parts["kl"], parts["mse"], parts["bce_o"], parts["bce_p"], parts["bce_s"]],
                              [1.0, 1.0, 1.0, 1.0 + lam, lam, lam, lam])
     total.backward()
+    VF.join_async()          # weight gradients on the side stream (functional.set_async_wgrad), if any
     return total
 
 
