@@ -205,240 +205,14 @@ def workload_config(args, batch, note=None):
 
 
 class StepRunner:
-    """One model + optimiser + (CUDA-graph) step closure for a given image size; `step(x)` runs one full training step."""
+    """bench.py's view of vae_play_b200.engine.VaeTrainer: the trainer plus the timing loops."""
 
     def __init__(self, args, img, world, rank, dev):
-        import torch
-        import torch.distributed as dist
+        from vae_play_b200.engine import VaeTrainer
+        self._t = VaeTrainer(args, img, world, rank, dev)
 
-        import vae_play_b200.functional as VF
-        from vae_play_b200 import _lib
-        from vae_play_b200.models.networks import VaeGan
-        from vae_play_b200.parallel import GradBuckets
-        self.args, self.img, self.world, self.rank, self.dev = args, img, world, rank, dev
-        B, cin = args.batch, args.cin
-        self.B = B
-        torch.manual_seed(0)
-        model = VaeGan(img, 128).to(dev).train()
-        self.model = model
-        params = list(model.encoder.parameters()) + list(model.decoder.parameters())
-        use_graph = not args.no_graph
-        if args.torch_optim:
-            opt = torch.optim.RMSprop(params, lr=1e-4, capturable=use_graph)
-        else:
-            from vae_play_b200.optim import FusedRMSprop          # same update rule, one multi-tensor kernel
-            # the kernel also refreshes the bf16 operand copies of the weights and clears each gradient after use, so the
-            # next step's weight-gradient kernels accumulate into known-zero persistent slots (no cast pass, no memsets)
-            opt = FusedRMSprop(params, lr=1e-4, zero_grads=True)
-        wire_bf16 = world > 1 and args.grad_wire == "bf16" and not args.torch_optim
-        buckets = GradBuckets(params, world, overlap=not use_graph, wire_dtype=torch.bfloat16 if wire_bf16 else None) if world > 1 else None
-        if buckets is None and not args.torch_optim:
-            VF.persistent_grads(params)
-        if wire_bf16:
-            # bf16 on the wire: pack() converts + clears the fp32 buckets, the optimiser reads the reduced bf16 values directly
-            views = {}
-            for bi in range(len(buckets.buckets)):
-                views.update(buckets.wire_views(bi))
-            opt = FusedRMSprop(params, lr=1e-4, zero_grads=False, wire=views)
-        # data parallel: one optimiser per gradient bucket, so that the update of bucket i runs while NCCL reduces bucket i+1
-        bucket_opts = None
-        if buckets is not None and not args.torch_optim and not args.no_bucket_pipeline:
-            from vae_play_b200.optim import FusedRMSprop
-            bucket_opts = [FusedRMSprop(b["params"], lr=1e-4, zero_grads=not wire_bf16, wire=buckets.wire_views(bi))
-                           for bi, b in enumerate(buckets.buckets)]
-        self.wire = "bf16" if wire_bf16 else "fp32"
-        torch.manual_seed(1234 + rank)
-        self.x_host = torch.rand(B, cin, img, img).pin_memory()
-        self.x_dev = self.x_host.to(dev)
-        off_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        _, eps_inc = VF.philox_policy(B * 128, torch.cuda.get_device_properties(dev).multi_processor_count)
-
-        # weight gradients on a side stream: the tensor-bound wgrad kernel of block L runs next to the bandwidth-bound
-        # BatchNorm-backward passes of block L-1 (functional.set_async_wgrad); joined at the end of every backward (stage)
-        VF.set_async_wgrad(not args.no_async_wgrad and not args.torch_optim)
-
-        def fwd_bwd(x):
-            # disjoint, reproducible Philox streams per rank: seed = rank; the offset lives on the device and
-            # advances by what Tensor.normal_() on B*z elements would consume, so CUDA-graph replays draw fresh eps
-            xt, mulv, kl = model.vae_forward(x, rng=(rank, 0, off_dev))
-            VF.philox_advance(off_dev, eps_inc)
-            loss = VF.vae_loss(x, xt, kl, mse_scale=1.0 / world)
-            loss.backward()
-            VF.join_async()
-            return loss
-
-        # Data parallel, graph mode: the backward is cut at the output of the encoder's conv stack.  Stage 1 (decoder, heads,
-        # encoder.fc: 94 % of the gradient bytes) and stage 2 (the encoder convs) are separate graphs, and the all-reduce of
-        # the stage-1 buckets runs on NCCL's stream while stage 2 executes.
-        enc_conv_params = [p for blk in model.encoder.conv for p in blk.parameters()]
-        enc_conv_ids = {id(p) for p in enc_conv_params}
-        stage1_params = [p for p in params if id(p) not in enc_conv_ids]
-        cut = {}
-
-        def fwd_bwd_stage1(x):
-            taps = []
-            xt, mulv, kl = model.vae_forward(x, rng=(rank, 0, off_dev), taps=taps)
-            VF.philox_advance(off_dev, eps_inc)
-            loss = VF.vae_loss(x, xt, kl, mse_scale=1.0 / world)
-            a3 = taps[0]          # behind VF.grad_cut: naming it in `inputs` executes only that identity node
-            a3.register_hook(lambda g: cut.__setitem__("g", g))
-            loss.backward(inputs=stage1_params + [a3], retain_graph=True)
-            VF.join_async()
-            a3.grad = None        # `inputs` also accumulated it into .grad
-            cut["a"] = taps[1]    # stage 2 starts one identity node further in: no retained .grad to clone or add into
-            return loss
-
-        def bwd_stage2():
-            cut["a"].backward(cut["g"], inputs=enc_conv_params)
-            VF.join_async()
-
-        def eager_step(x):
-            opt.zero_grad(set_to_none=True)
-            loss = fwd_bwd(x)
-            if buckets is not None:
-                buckets.allreduce()
-            if bucket_opts is not None:
-                for o in bucket_opts:
-                    o.step()
-            else:
-                opt.step()
-            return loss
-
-        # One GPU: the optimiser is split in two and its larger part (everything but the encoder convs: 97 % of the bytes) is
-        # launched on its own stream as soon as those gradients are final -- a bandwidth-bound kernel next to the tensor-bound
-        # encoder-conv backward.  The whole step is then ONE CUDA graph.
-        overlap_opt = use_graph and buckets is None and not args.torch_optim and not args.no_overlap_opt
-        if overlap_opt:
-            from vae_play_b200.optim import FusedRMSprop
-            opt1 = FusedRMSprop(stage1_params, lr=1e-4, zero_grads=True)
-            opt2 = FusedRMSprop(enc_conv_params, lr=1e-4, zero_grads=True)
-            opt_stream = torch.cuda.Stream()
-
-            def eager_step(x):            # noqa: F811 -- same step, the optimiser in two parts
-                main = torch.cuda.current_stream()
-                opt1.zero_grad(set_to_none=True)                          # host-side only: the slots are handed out afresh
-                opt2.zero_grad(set_to_none=True)
-                loss = fwd_bwd_stage1(x)                                  # ends with join_async(): every stage-1 gradient is final
-                opt_stream.wait_stream(main)
-                with torch.cuda.stream(opt_stream):
-                    opt1.step()
-                bwd_stage2()
-                opt2.step()
-                main.wait_stream(opt_stream)
-                return loss
-
-        graph_a = graph_b = graph_a2 = None
-        graph_bs = []
-        early = []
-        extra_launches = 0
-        xstream = torch.cuda.Stream() if buckets is not None else None
-        # data parallel: on by default -- the backward graph is cut after encoder.fc's weight gradient (94 % of the gradient
-        # bytes are complete there) and the encoder-conv backward that follows is captured with its persistent grids capped at
-        # (#SMs - sm_reserve), so that NCCL's CTAs find free SMs and the all-reduce really runs next to it
-        split_backward = use_graph and buckets is not None and not args.no_split_backward
-        static_x = self.x_dev.clone()
-        self.static_x = static_x
-        launches_per_replay = launches_opt = 0
-        if use_graph:
-            # two CUDA graphs per step: A = forward + loss + backward (gradients land in the flat buckets),
-            # B = optimiser; the bucketed NCCL all-reduce runs between them, outside the captured regions
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    eager_step(static_x)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            VF.invalidate_caches()
-            opt.zero_grad(set_to_none=True)
-            graph_a, graph_b = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            l0 = _lib.launch_count()
-            if overlap_opt:
-                with torch.cuda.graph(graph_a):
-                    static_loss = eager_step(static_x)
-                graph_b = None
-            elif split_backward:
-                early = sorted(buckets.buckets_within(stage1_params), key=lambda i: -buckets.buckets[i]["buf"].numel())
-                graph_a2 = torch.cuda.CUDAGraph()
-                late = [i for i in range(len(buckets.buckets)) if i not in early]
-                with torch.cuda.graph(graph_a):
-                    static_loss = fwd_bwd_stage1(static_x)
-                l1 = _lib.launch_count()
-                buckets.pack(early)              # per step this runs on the exchange stream, next to stage 2 (see step())
-                extra_launches = _lib.launch_count() - l1
-                nsm = torch.cuda.get_device_properties(dev).multi_processor_count
-                _lib.call("vp_set_sm_limit", max(nsm - args.sm_reserve, nsm // 2))
-                try:
-                    with torch.cuda.graph(graph_a2, pool=graph_a.pool()):
-                        bwd_stage2()
-                        buckets.pack(late)
-                finally:
-                    _lib.call("vp_set_sm_limit", 0)
-            else:
-                with torch.cuda.graph(graph_a):
-                    static_loss = fwd_bwd(static_x)
-                    if buckets is not None:
-                        buckets.pack()
-            launches_per_replay = _lib.launch_count() - l0
-            if buckets is not None:
-                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)
-                buckets.allreduce(check_missing=False)
-            l0 = _lib.launch_count()
-            if overlap_opt:
-                pass
-            elif bucket_opts is not None:
-                graph_bs = []
-                for o in bucket_opts:
-                    gb_ = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(gb_, pool=graph_a.pool()):
-                        o.step()
-                    graph_bs.append(gb_)
-            else:
-                with torch.cuda.graph(graph_b, pool=graph_a.pool()):
-                    opt.step()
-            launches_opt = _lib.launch_count() - l0
-        self.graph = graph_a is not None
-        self.overlap_opt = bool(overlap_opt)
-        self.async_wgrad = not args.no_async_wgrad and not args.torch_optim
-        self.split = graph_a2 is not None
-        self.launches_per_step = (launches_per_replay + launches_opt + extra_launches) if self.graph else None
-
-        def step(x):
-            if graph_a is None:
-                return eager_step(x)
-            if x.data_ptr() != static_x.data_ptr():
-                static_x.copy_(x, non_blocking=True)
-            graph_a.replay()
-            if graph_b is None:
-                return static_loss
-            main = torch.cuda.current_stream()
-            if graph_a2 is not None:
-                # exchange stream: bf16 packing of the stage-1 buckets, then their all-reduce -- all of it next to stage 2
-                xstream.wait_stream(main)
-                with torch.cuda.stream(xstream):
-                    for bi in early:                       # largest first (encoder.fc's weight: 73 % of the bytes)
-                        buckets.pack([bi])
-                        buckets.allreduce_subset([bi], pre_packed=True)
-                graph_a2.replay()
-            if bucket_opts is not None:
-                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)      # the rest, queued on NCCL's stream in order
-                with torch.cuda.stream(xstream):
-                    for bi in early:                                        # their updates too run next to stage 2 / the late exchange:
-                        buckets.wait_bucket(bi)                             # nothing left in the step reads those weights
-                        graph_bs[bi].replay()
-                for bi, gb_ in enumerate(graph_bs):
-                    if bi not in early:
-                        buckets.wait_bucket(bi)
-                        gb_.replay()
-                main.wait_stream(xstream)
-                return static_loss
-            if buckets is not None:
-                buckets.allreduce_subset(range(len(buckets.buckets)), pre_packed=True)
-                buckets.allreduce(check_missing=False)
-            graph_b.replay()
-            return static_loss
-
-        self.step = step
+    def __getattr__(self, name):        # model, step, x_host, x_dev, static_x, graph, split, wire, launches_per_step, ...
+        return getattr(self.__dict__["_t"], name)
 
     def barrier(self):
         import torch
@@ -499,16 +273,8 @@ class StepRunner:
 
 
 def init_nccl(args, dev):
-    """NCCL's kernels get a bounded number of CTAs (the SMs our persistent grids leave free while the exchange overlaps backward)
-    and a high-priority stream (their CTAs are placed first when SMs free up)."""
-    import torch.distributed as dist
-    try:
-        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
-        opts.config.max_ctas = args.sm_reserve
-        opts.config.min_ctas = min(args.sm_reserve, 4)
-        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
-    except Exception:
-        dist.init_process_group("nccl", device_id=dev)
+    from vae_play_b200.engine import init_nccl as _init
+    _init(args.sm_reserve, dev)
 
 
 def run_ours(args):
@@ -1122,6 +888,8 @@ def add_arguments(ap):
     ap.add_argument("--sm-reserve", type=int, default=32, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap-opt", action="store_true", help="one GPU: optimiser as its own graph after the backward (default: its larger part runs next to the encoder-conv backward)")
+    ap.add_argument("--three-stage-backward", action="store_true",
+                    help="data parallel, experimental: cut the backward once more between decoder and sample so that the decoder's gradient exchange starts a stage earlier (diverges after ~100 steps at N=2: see vae_play_b200/engine.py)")
     ap.add_argument("--no-async-wgrad", action="store_true", help="weight gradients on the main stream (default: a side stream, overlapping the BatchNorm-backward passes)")
 
 

@@ -1051,3 +1051,49 @@ def test_async_wgrad_matches_sync(vp):
         VF.set_async_wgrad(False)
         VF.set_fuse_bn_backward(True)
         VF.set_grad_sinks({})
+
+
+def test_three_stage_backward_matches_single(vp):
+    """The data-parallel step of vae_play_b200.engine cuts the backward twice (decoder | sample + heads + encoder.fc | encoder
+    convs) so that each group's gradient exchange can start as soon as the group is complete: the three calls -- the middle one
+    rooted at (z, kl) with d loss / d kl = 1 -- give the gradients of one backward call through the same forward graph."""
+    import vae_play_b200.functional as VF
+    from vae_play_b200.models.networks import VaeGan
+    vp.set_precision("bf16")
+    vp.set_engine("auto")
+    VF.set_fuse_bn_backward(False)
+    torch.manual_seed(2)
+    m = VaeGan(64, 128).cuda().train()
+    x = torch.rand(16, 1, 64, 64, device="cuda")
+    eps = torch.randn(16, 128, device="cuda")
+    params = list(m.encoder.parameters()) + list(m.decoder.parameters())
+    conv_params = [p for blk in m.encoder.conv for p in blk.parameters()]
+    dec_params = list(m.decoder.parameters())
+    skip = {id(p) for p in conv_params} | {id(p) for p in dec_params}
+    mid_params = [p for p in params if id(p) not in skip]
+    try:
+        VF.persistent_grads(params)
+        taps, cut = [], {}
+        xt, mulv, kl = m.vae_forward(x, eps=eps, taps=taps)
+        loss = VF.vae_loss(x, xt, kl, mse_scale=0.5)
+        a_out, a_in, z_out, z_in = taps
+        z_out.register_hook(lambda g: cut.__setitem__("gz", g))
+        loss.backward(inputs=dec_params + [z_out], retain_graph=True)
+        z_out.grad = None
+        assert all(p.grad is None for p in conv_params + mid_params) and all(p.grad is not None for p in dec_params)
+        a_out.register_hook(lambda g: cut.__setitem__("g", g))
+        torch.autograd.backward([z_in, kl], [cut["gz"], torch.ones_like(kl)], inputs=mid_params + [a_out], retain_graph=True)
+        a_out.grad = None
+        assert all(p.grad is None for p in conv_params) and all(p.grad is not None for p in mid_params)
+        a_in.backward(cut["g"], inputs=conv_params, retain_graph=True)
+        staged = [npy(p.grad) for p in params]
+        VF.set_grad_sinks({})
+        for p in params:
+            p.grad = None
+        loss.backward()
+        names = [k for k, _ in list(m.encoder.named_parameters()) + list(m.decoder.named_parameters())]
+        for k, a, p in zip(names, staged, params):
+            assert rel_l2(a, npy(p.grad)) < 1e-4, k
+    finally:
+        VF.set_fuse_bn_backward(True)
+        VF.set_grad_sinks({})

@@ -206,3 +206,17 @@ def test_reference_and_port_cpu_steps_agree():
         torch.Tensor.normal_ = orig
     l_port = float(port.step(x, eps)[0])
     assert abs(l_ref - l_port) / abs(l_port) < 1e-5
+
+
+def test_engine_options_match_bench_flags():
+    """vae_play_b200.engine.VaeTrainer takes bench.py's argparse namespace as its options: every option it reads must exist as
+    a bench flag with the same default, so `bench.py` (and tools/dp_timeline.py) really run the packaged step."""
+    import argparse
+    import bench
+    from vae_play_b200.engine import VaeTrainer
+    ap = argparse.ArgumentParser()
+    bench.add_arguments(ap)
+    args = vars(ap.parse_args([]))
+    for k, v in VaeTrainer.default_options().items():
+        assert k in args, f"bench.py has no flag for engine option {k!r}"
+        assert args[k] == v, (k, args[k], v)

@@ -301,6 +301,13 @@ class VaeGan(nn.Module):
         """Returns (x_tilde NCHW fp32, mu|logvar packed [B,2Z] fp32, kl [B]) without leaving channels-last."""
         mulv = self.encoder.forward_packed(x, taps)
         z, kl = VF.reparam_kl(mulv, None, eps=eps, z_dtype=VF.act_dtype(), rng=rng)
+        if taps is not None:
+            # a second place to cut the backward (taps[2] outer, taps[3] inner): between the decoder and the sample, so that a
+            # data-parallel step can start exchanging the decoder's gradients before the heads / encoder.fc backward runs
+            inner = VF.grad_cut(z)
+            z = VF.grad_cut(inner)
+            taps.append(z)
+            taps.append(inner)
         xt = self.decoder.forward_cl(z.reshape(len(z), 1, 1, -1))
         return VF.from_channels_last(xt), mulv, kl
 

@@ -23,7 +23,7 @@ import torch.distributed as dist
 
 class GradBuckets:
     def __init__(self, params: List[torch.nn.Parameter], world_size: int, bucket_mb: float = 32.0, group=None,
-                 overlap: bool = True, wire_dtype=None):
+                 overlap: bool = True, wire_dtype=None, breaks=()):
         """overlap=True: each bucket's all-reduce is issued from the gradient hook as soon as the bucket is
         complete (overlaps the rest of backward).  overlap=False: hooks only place gradients into the buckets and
         ``allreduce()`` issues all collectives afterwards -- used when forward+backward is replayed as a CUDA
@@ -43,8 +43,11 @@ class GradBuckets:
         order = list(reversed(self.params))
         self.buckets = []          # list of dict(buf, params, ready, handle)
         cur, cur_n = [], 0
+        # breaks: parameters that must START a bucket (in reverse registration order): lets a caller that cuts its backward into
+        # stages keep each stage's gradients in buckets of their own (vae_play_b200.engine)
+        break_ids = {id(p) for p in breaks}
         for p in order:
-            if cur and cur_n + self._padded(p) > cap:
+            if cur and (cur_n + self._padded(p) > cap or id(p) in break_ids):
                 self._close(cur)
                 cur, cur_n = [], 0
             cur.append(p)
