@@ -1,6 +1,6 @@
 """Diagnostic: bisect the padded route vs the native in-place route on K = N = 64 stride-1 shapes."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.nn.functional as F
 import vae_play_b200 as vp
 import vae_play_b200.functional as VF

@@ -1,6 +1,6 @@
 """Diagnostic (not a test): per-tensor deviation of the mirror VaeGan step from the reference fixtures, both precisions."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 import vae_play_b200 as vp
