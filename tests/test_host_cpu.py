@@ -220,3 +220,24 @@ def test_engine_options_match_bench_flags():
     for k, v in VaeTrainer.default_options().items():
         assert k in args, f"bench.py has no flag for engine option {k!r}"
         assert args[k] == v, (k, args[k], v)
+
+
+def test_grad_buckets_breaks_keep_stage_groups_apart():
+    """GradBuckets(breaks=[p]): p starts a bucket of its own run (reverse registration order), so a backward cut into stages can
+    exchange a stage's gradients without waiting for parameters of the next stage that would otherwise share the bucket."""
+    import torch
+    from vae_play_b200.parallel import GradBuckets
+    enc = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    dec = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Linear(8, 8))
+    params = list(enc.parameters()) + list(dec.parameters())
+    plain = GradBuckets(params, 1, bucket_mb=1.0)
+    assert len(plain.buckets) == 1                                   # everything fits one bucket ...
+    plain.remove()
+    gb = GradBuckets(params, 1, bucket_mb=1.0, breaks=[list(enc.parameters())[-1]])
+    try:
+        assert len(gb.buckets) == 2                                  # ... unless the encoder's last parameter must start one
+        dec_ids, enc_ids = {id(p) for p in dec.parameters()}, {id(p) for p in enc.parameters()}
+        assert {id(p) for p in gb.buckets[0]["params"]} == dec_ids and {id(p) for p in gb.buckets[1]["params"]} == enc_ids
+        assert gb.buckets_within(list(dec.parameters())) == [0] and gb.buckets_within(params) == [0, 1]
+    finally:
+        gb.remove()
