@@ -888,8 +888,8 @@ def add_arguments(ap):
     ap.add_argument("--sm-reserve", type=int, default=32, help="data parallel: SMs left to NCCL while the all-reduce overlaps the encoder-conv backward")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-overlap-opt", action="store_true", help="one GPU: optimiser as its own graph after the backward (default: its larger part runs next to the encoder-conv backward)")
-    ap.add_argument("--three-stage-backward", action="store_true",
-                    help="data parallel, experimental: cut the backward once more between decoder and sample so that the decoder's gradient exchange starts a stage earlier (diverges after ~100 steps at N=2: see vae_play_b200/engine.py)")
+    ap.add_argument("--three-stage-backward", default="auto", choices=["auto", "on", "off"],
+                    help="data parallel: cut the backward once more between decoder and sample so that the decoder's gradient exchange starts a stage earlier (auto: from 8 ranks on)")
     ap.add_argument("--no-async-wgrad", action="store_true", help="weight gradients on the main stream (default: a side stream, overlapping the BatchNorm-backward passes)")
 
 

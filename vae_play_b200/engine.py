@@ -34,7 +34,7 @@ class VaeTrainer:
     @staticmethod
     def default_options():
         return dict(batch=256, cin=1, grad_wire="bf16", no_async_wgrad=False, no_bucket_pipeline=False, no_graph=False, no_overlap_opt=False,
-                    no_split_backward=False, sm_reserve=32, torch_optim=False, three_stage_backward=False)
+                    no_split_backward=False, sm_reserve=32, torch_optim=False, three_stage_backward="auto")
 
 
     def __init__(self, opts=None, img=64, world=1, rank=0, dev=None, **overrides):
@@ -65,7 +65,10 @@ class VaeTrainer:
         wire_bf16 = world > 1 and args.grad_wire == "bf16" and not args.torch_optim
         # the decoder's gradients get buckets of their own: their exchange starts one backward stage earlier (see step())
         enc_last = list(model.encoder.parameters())[-1]
-        three_stage = bool(args.three_stage_backward)
+        # "auto": from 8 ranks on.  Measured: up to 4 ranks the decoder bucket's all-reduce (47-74 us) still fits under the encoder-conv
+        # backward behind the big bucket and the extra graph costs ~11 us (N = 2: 1.820 vs 1.809 ms); at 8 ranks it does not fit
+        # (110 us behind 214 us against ~240 us of stage 2: profiles/r02_dp8_timeline.txt) and would move under stage 1b
+        three_stage = (world >= 8) if args.three_stage_backward in ("auto", None) else args.three_stage_backward in (True, "on")
         buckets = (GradBuckets(params, world, overlap=not use_graph, wire_dtype=torch.bfloat16 if wire_bf16 else None,
                                breaks=[enc_last] if three_stage else ())
                    if world > 1 else None)
@@ -129,13 +132,12 @@ class VaeTrainer:
             cut["a"].backward(cut["g"], inputs=enc_conv_params)
             VF.join_async()
 
-        # Three-stage variant (data parallel, ``three_stage_backward=True``, OFF by default): stage 1 is cut once more between the
-        # decoder and the sample z.  The three backward calls are gradient-equivalent to one (test_three_stage_backward_matches_single)
-        # and the step trains normally for ~100 steps, but in bench.py's loop at N = 2 the loss then drifts and diverges; the cause
-        # was not isolated this round, so the validated two-stage step stays the default.
+        # Three-stage variant (data parallel, ``three_stage_backward``: "auto" = from 8 ranks on): stage 1 is cut once more between
+        # the decoder and the sample z.
         #   1a: forward, loss, decoder backward          -> the decoder buckets are complete: their exchange starts
         #   1b: sample / KL / heads / encoder.fc backward  -> encoder.fc.0.weight (73 % of the bytes) is complete
         #   2 : encoder-conv backward
+        # The three backward calls are gradient-equivalent to one (test_three_stage_backward_matches_single).
         dec_params = list(model.decoder.parameters())
         dec_ids = {id(p) for p in dec_params}
         stage1b_params = [p for p in stage1_params if id(p) not in dec_ids]
@@ -276,6 +278,10 @@ class VaeTrainer:
                 with torch.cuda.graph(graph_b, pool=graph_a.pool()):
                     opt.step()
             launches_opt = _lib.launch_count() - l0
+        # Everything the captured graphs address must outlive them: the closures above die with __init__, and a freed block of the
+        # regular allocator is handed to the next small allocation (found the hard way: `ones_kl`, 1 KB, was overwritten by the
+        # first torch.tensor() after construction and every gradient upstream of the sample exploded)
+        self._keep_alive = (off_dev, ones_kl, cut, static_x)
         self.graph = graph_a is not None
         self.overlap_opt = bool(overlap_opt)
         self.async_wgrad = not args.no_async_wgrad and not args.torch_optim
