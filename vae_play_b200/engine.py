@@ -278,9 +278,10 @@ class VaeTrainer:
                 with torch.cuda.graph(graph_b, pool=graph_a.pool()):
                     opt.step()
             launches_opt = _lib.launch_count() - l0
-        # Everything the captured graphs address must outlive them: the closures above die with __init__, and a freed block of the
-        # regular allocator is handed to the next small allocation (found the hard way: `ones_kl`, 1 KB, was overwritten by the
-        # first torch.tensor() after construction and every gradient upstream of the sample exploded)
+        # Everything the captured graphs address must outlive them.  Most of it stays reachable through the `step` closure, but the
+        # capture-only closures die with __init__, and a freed block of the regular allocator is handed to the next small
+        # allocation (found the hard way: `ones_kl`, 1 KB, referenced only by bwd_stage1b, was overwritten by the first
+        # torch.tensor() after construction and every gradient upstream of the sample exploded)
         self._keep_alive = (off_dev, ones_kl, cut, static_x)
         self.graph = graph_a is not None
         self.overlap_opt = bool(overlap_opt)
