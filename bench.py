@@ -341,6 +341,7 @@ def run_ours(args):
                                       f"bucketed NCCL all-reduce, {run.wire} on the wire (<= {args.sm_reserve} CTAs, high-priority stream); the decoder / fc / heads buckets "
                                       f"(94 % of the bytes) run next to the encoder-conv backward graph, whose persistent grids are capped at "
                                       f"#SMs - {args.sm_reserve}; per-bucket optimiser graphs start as each bucket completes"
+                                      + ("; backward in three stages (the decoder buckets are exchanged next to the heads / encoder.fc backward)" if run.three_stage else "")
                                       if run.split else f"bucketed NCCL all-reduce ({run.wire} on the wire) between backward and optimiser")),
             "clocks": clocks,
             "region_ms_per_step": [round(r / args.steps, 4) for r in regions],

@@ -287,6 +287,7 @@ class VaeTrainer:
         self.overlap_opt = bool(overlap_opt)
         self.async_wgrad = not args.no_async_wgrad and not args.torch_optim
         self.split = graph_a2 is not None
+        self.three_stage = graph_a1 is not None
         self.launches_per_step = (launches_per_replay + launches_opt + extra_launches) if self.graph else None
 
         def step(x):
